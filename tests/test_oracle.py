@@ -1,0 +1,106 @@
+"""The oracle (oracle/micn_oracle.py) against the golden vectors generated from the real
+reference module (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_files, load_golden, rel_err
+from oracle import micn_oracle as O
+
+TOL = {"float32": 2e-6, "bfloat16": 1e-2}  # fp32 golden was computed by ATen in fp32; bf16 I/O rounding
+
+
+def _batched(g):
+    x, dy, y, dx = g["x"], g["dy"], g["y"], g["dx"]
+    if not bool(g["batched"]):
+        x, dy, y, dx = x[None], dy[None], y[None], dx[None]
+    return x, dy, y, dx
+
+
+@pytest.mark.parametrize("path", golden_files("norm"), ids=os.path.basename)
+def test_norm_oracle_matches_reference_golden(path):
+    g = load_golden(path)
+    x, dy, y_ref, dx_ref = _batched(g)
+    tol = TOL[str(g["dtype"])]
+    if "bigmean" in path:
+        # x = 50 +- 0.1 in fp32: the subtraction x - mean amplifies fp32 rounding of x and mean by
+        # |mean|/std = 500 in ANY fp32 implementation (the reference's included), so the golden
+        # itself sits ~1e-5 from the exact answer.  Conditioning, not algorithm.
+        tol = 1e-4
+    y, mean, rstd = O.fwd_f64(x, g["styles"], g["gamma"], g["beta"])
+    assert rel_err(y, y_ref) < tol
+    dx, dgamma, dbeta, present = O.bwd_f64(dy, x, g["styles"], g["gamma"], mean, rstd)
+    assert rel_err(dx, dx_ref) < tol
+    assert rel_err(dgamma, g["dgamma"]) < tol * 5
+    assert rel_err(dbeta, g["dbeta"]) < tol * 5
+    # styles absent from the batch: reference leaves .grad None; oracle reports them via `present`
+    assert list(present) == list(g["present"])
+    assert bool(g["y_is_contiguous"])
+
+
+@pytest.mark.parametrize("path", golden_files("block"), ids=os.path.basename)
+def test_block_epilogue_oracle_matches_reference_golden(path):
+    """UnetResBlock / UnetBasicBlock epilogues (dynunet_block.py:100-126, 187-203) restated on the
+    tensors that entered each norm in the real block."""
+    g = load_golden(path)
+    st = g["styles"]
+    tol = 3e-6
+    # norm1 -> lrelu
+    o1, pre1, m1, r1 = O.fwd_epilogue_f64(g["conv1_out"], st, g["norm1_gamma"], g["norm1_beta"])
+    if str(g["kind"]) == "basic":
+        out, pre2, m2, r2 = O.fwd_epilogue_f64(g["conv2_out"], st, g["norm2_gamma"], g["norm2_beta"])
+        assert rel_err(out, g["out"]) < tol
+        da2, _, dg2, db2, _ = O.bwd_epilogue_f64(g["dout"], pre2, g["conv2_out"], st, g["norm2_gamma"], m2, r2)
+    else:
+        if "conv3_out" in g:
+            res, _, _ = O.fwd_f64(g["conv3_out"], st, g["norm3_gamma"], g["norm3_beta"])
+            assert rel_err(res, g["norm3_out"]) < tol
+        else:
+            res = g["x"].astype(np.float64)
+        out, pre2, m2, r2 = O.fwd_epilogue_f64(g["conv2_out"], st, g["norm2_gamma"], g["norm2_beta"], residual=res)
+        assert rel_err(out, g["out"]) < tol
+        da2, dres, dg2, db2, _ = O.bwd_epilogue_f64(g["dout"], pre2, g["conv2_out"], st, g["norm2_gamma"], m2, r2,
+                                                   has_residual=True)
+        if "norm3_out_grad" in g:
+            assert rel_err(dres, g["norm3_out_grad"]) < tol
+    assert rel_err(da2, g["conv2_out_grad"]) < tol
+    assert rel_err(dg2, g["norm2_dgamma"]) < tol * 5
+    assert rel_err(db2, g["norm2_dbeta"]) < tol * 5
+    # first epilogue's backward: gradient arriving at o1 is not recorded, but its output is the
+    # input of conv2, so check forward only plus the closed form against conv1_out_grad via chain
+    # through conv2 is out of the oracle's scope (conv stays in PyTorch/cuDNN).
+    assert o1.shape == g["conv1_out"].shape
+
+
+def test_styles_validation_messages():
+    with pytest.raises(ValueError, match="Expected number of styles as batch size."):
+        O.normalize_styles([0], 2, 2)
+    with pytest.raises(IndexError):
+        O.normalize_styles([0, 2], 2, 2)
+    with pytest.raises(TypeError):
+        O.normalize_styles(np.array([0.0, 1.0]), 2, 2)
+    assert list(O.normalize_styles([-1, -2], 2, 2)) == [1, 0]
+
+
+def test_port_matches_f64_oracle():
+    torch = pytest.importorskip("torch")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 4, 5, 6, 7, generator=g) * 2 + 1
+    dy = torch.randn(3, 4, 5, 6, 7, generator=g)
+    w = [1 + 0.3 * torch.randn(4, generator=g) for _ in range(2)]
+    b = [0.3 * torch.randn(4, generator=g) for _ in range(2)]
+    st = [1, 0, 1]
+    y, dx, dw, db = O.port_fwd_bwd(x, dy, st, w, b)
+    gam = np.stack([t.numpy() for t in w])
+    bet = np.stack([t.numpy() for t in b])
+    y64, mean, rstd = O.fwd_f64(x.numpy(), st, gam, bet)
+    dx64, dg64, db64, _ = O.bwd_f64(dy.numpy(), x.numpy(), st, gam, mean, rstd)
+    assert rel_err(y.numpy(), y64) < 2e-6
+    assert rel_err(dx.numpy(), dx64) < 2e-6
+    assert rel_err(np.stack([t.numpy() for t in dw]), dg64) < 1e-5
+    assert rel_err(np.stack([t.numpy() for t in db]), db64) < 1e-5
+
+
+def test_lrelu_grad_at_zero_uses_slope():
+    assert O.lrelu_grad(np.array([0.0]))[0] == O.LRELU_SLOPE
