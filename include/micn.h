@@ -1,0 +1,125 @@
+/*
+ * micn.h - C ABI of the B200-native modality-conditioned instance norm ("instance_cond") for MI-Seg.
+ *
+ * This is the drop-in boundary for the one hot path this repo accelerates.  Each entry point
+ * replaces a piece of the reference's Python/ATen path (paths relative to the MI-Seg checkout):
+ *
+ *   micn_fwd   <- networks/norms/conditional_instance_norm.py:59-60  (_apply_instance_norm: per-sample
+ *                 nn.InstanceNorm{1,2,3}d picked by styles[i] + torch.stack), :52-57 (un-batched input),
+ *                 and, with epilogue != MICN_EPI_NONE, the activation / residual that follows it in
+ *                 networks/blocks/dynunet_block.py:107-111, :113-125 (UnetResBlock) and :188-202
+ *                 (UnetBasicBlock): LeakyReLU(0.01) and "out += residual".
+ *   micn_bwd   <- the autograd graph of the above (StackBackward -> native_batch_norm_backward ->
+ *                 RepeatBackward -> AccumulateGrad on norms[s].weight / norms[s].bias).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer valid on the
+ *     device that is current when the call is made; `stream` is a cudaStream_t passed as void*.
+ *   - the calls only enqueue work on `stream`: no allocation, no host synchronisation, no
+ *     exceptions.  Return 0 on success, a MICN_ERR_* (< 0) for argument errors, or a positive
+ *     cudaError_t from the launch.  micn_error_string() decodes either.
+ *   - a "slab" is the D*H*W (= M) voxels of one (sample n, channel c); x is addressed as
+ *     x[n*x_stride_n + c*x_stride_c + m] (strides in ELEMENTS, slab itself dense);
+ *     y, residual, act_out, dy, dx, dresidual are dense [N, C, M].
+ *   - statistics, gamma/beta and all accumulations are fp32 regardless of the I/O dtype.
+ *   - gamma/beta are HOST arrays of `num_styles` DEVICE pointers (norms[s].weight / .bias of the
+ *     reference's ModuleList); pass NULL for a non-affine norm (gamma = 1, beta = 0).
+ *   - styles is a DEVICE int64 array [N] read by the kernels (no host sync); python-style negative
+ *     indices wrap; an out-of-range style is clamped and recorded in the workspace status word
+ *     (micn_read_status) instead of faulting.  styles == NULL means style 0 for every sample.
+ */
+#ifndef MICN_H_
+#define MICN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MICN_VERSION 100 /* 0.1.0 */
+#define MICN_MAX_STYLES 16
+
+/* I/O element types */
+enum { MICN_F32 = 0, MICN_BF16 = 1, MICN_F16 = 2 };
+
+/* fused epilogues (dynunet_block.py) */
+enum {
+    MICN_EPI_NONE = 0,      /* y = norm(x)                                  */
+    MICN_EPI_LRELU = 1,     /* y = lrelu(norm(x))            :107-111       */
+    MICN_EPI_ADD_LRELU = 2  /* y = lrelu(norm(x) + residual) :113-125       */
+};
+
+/* error codes (negative; positive values are cudaError_t) */
+enum {
+    MICN_OK = 0,
+    MICN_ERR_BAD_ARG = -1,
+    MICN_ERR_BAD_DTYPE = -2,
+    MICN_ERR_TOO_MANY_STYLES = -3,
+    MICN_ERR_WORKSPACE = -4,
+    MICN_ERR_UNALIGNED = -5,
+    MICN_ERR_NO_DEVICE = -6
+};
+
+int micn_version(void);
+const char* micn_error_string(int code);
+
+/* Tuning / experiment knobs ("cluster_size", "force_path", "chunk_vecs", ...).  Returns 0 or
+ * MICN_ERR_BAD_ARG for an unknown key.  value < 0 restores the automatic choice. */
+int micn_set_option(const char* key, long long value);
+long long micn_get_option(const char* key);
+
+/* Bytes of device workspace micn_fwd/micn_bwd need for this problem.  The workspace must be
+ * zero-filled ONCE when it is allocated; the kernels leave its control words zero again, so it
+ * can be reused by every later call on the same stream. */
+size_t micn_workspace_bytes(int64_t N, int64_t C, int num_styles);
+
+/* Host-blocking read (cudaMemcpy) of the sticky status word: bit 0 = a style index was out of
+ * range.  Clears the word.  Debug aid; never called on the hot path. */
+int micn_read_status(void* workspace, void* stream, int* status_out);
+
+/* Forward.  save_mean / save_rstd: device fp32 [N*C] (needed by micn_bwd; may be NULL for
+ * inference).  residual: device, dense [N,C,M], only for MICN_EPI_ADD_LRELU. */
+int micn_fwd(const void* x, void* y, const void* residual,
+             const float* const* gamma, const float* const* beta, int num_styles,
+             const int64_t* styles,
+             float* save_mean, float* save_rstd,
+             int64_t N, int64_t C, int64_t M,
+             int64_t x_stride_n, int64_t x_stride_c,
+             int dtype, int epilogue, float slope, float eps,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward.  dy is the gradient of the (post-epilogue) output.  act_out is the forward OUTPUT
+ * tensor (needed only for MICN_EPI_ADD_LRELU, to recover the LeakyReLU mask); for MICN_EPI_LRELU the
+ * mask is recomputed from x and the saved statistics.  dresidual (ADD_LRELU only) receives the
+ * gradient of `residual`.  dgamma / dbeta: device fp32 [num_styles*C], OVERWRITTEN with the sums over
+ * the samples of each style (zero rows for styles absent from the batch); either both or neither
+ * may be NULL. */
+int micn_bwd(const void* dy, const void* x, const void* act_out,
+             const float* const* gamma, const float* const* beta, int num_styles,
+             const int64_t* styles,
+             const float* save_mean, const float* save_rstd,
+             void* dx, void* dresidual,
+             float* dgamma, float* dbeta,
+             int64_t N, int64_t C, int64_t M,
+             int64_t x_stride_n, int64_t x_stride_c,
+             int dtype, int epilogue, float slope,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience path: x (and dy) live in HOST memory (pinned for full speed); the call
+ * stages slab groups through `dev_scratch` (device, >= micn_host_scratch_bytes) with
+ * H2D / kernels / D2H overlapped on internal streams, and BLOCKS until y (and dx, dgamma, dbeta)
+ * are back in host memory.  This is what `e2e` in bench.py times. */
+size_t micn_host_scratch_bytes(int64_t N, int64_t C, int64_t M, int dtype, int num_styles, int with_backward);
+int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, void* dx_host,
+                      const float* gamma_host, const float* beta_host, int num_styles, /* [S*C] host */
+                      const int64_t* styles_host,
+                      float* dgamma_host, float* dbeta_host,                           /* [S*C] host */
+                      int64_t N, int64_t C, int64_t M, int dtype, int epilogue, float slope, float eps,
+                      void* dev_scratch, size_t dev_scratch_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICN_H_ */

@@ -1,0 +1,688 @@
+// micn_api.cu - the C ABI declared in include/micn.h: argument checks, path planning and launches.
+//
+// Two kernel families (micn_cluster.cuh, micn_small.cuh); the planner picks, per call,
+//   * small path  : slab bytes < 32 KB, or anything not 16-byte aligned -> warp / CTA per slab
+//   * cluster path: everything else -> cluster size CS in {1,2,4,8,16} from a bandwidth model
+//                   (HBM share per cluster, SMEM residency, waves over the co-resident clusters).
+// Nothing here allocates or synchronises; the only state is per-process launch-attribute and
+// occupancy caches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "micn_cluster.cuh"
+#include "micn_small.cuh"
+
+using namespace micn;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ options
+struct Options {
+    std::atomic<long long> cluster_size{-1};  // force CS (1..16)
+    std::atomic<long long> force_path{-1};    // 0 small, 1 cluster
+    std::atomic<long long> slots{-1};         // force ring slots S
+    std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
+    std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
+    std::atomic<long long> last_path{-1}, last_cs{-1}, last_slots{-1}, last_grid{-1};  // read-back of the last plan
+    std::atomic<long long> launches{0};       // kernels launched by this library (bench "gpu_launches")
+    std::atomic<long long> sm_bw_mbps{90000};   // per-SM bandwidth cap used by the planner (MB/s)
+    std::atomic<long long> hbm_bw_mbps{6500000};
+};
+Options g_opt;
+
+struct OptName {
+    const char* name;
+    std::atomic<long long>* v;
+};
+const OptName kOptNames[] = {
+    {"cluster_size", &g_opt.cluster_size}, {"force_path", &g_opt.force_path}, {"slots", &g_opt.slots},
+    {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps},   {"last_path", &g_opt.last_path},
+    {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid},
+    {"launches", &g_opt.launches},         {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
+};
+
+// ------------------------------------------------------------------------------------------ device
+struct DeviceInfo {
+    int sm_count = 0, smem_optin = 0, cc_major = 0;
+    bool valid = false;
+};
+std::mutex g_mu;
+DeviceInfo g_dev[64];
+
+int device_info(DeviceInfo** out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return MICN_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.valid) {
+        if ((e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+            return (int)e;
+        if ((e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return (int)e;
+        d.valid = true;
+    }
+    *out = &d;
+    return 0;
+}
+
+// per (kernel, device): opt-in attributes set once; per (kernel, device, CS, smem): occupancy
+struct KernelState {
+    const void* fn;
+    int dev;
+    int smem_set;
+    int occ[16];  // co-resident clusters for CS = 1..16 at smem_set bytes (-1 unknown)
+};
+std::vector<KernelState> g_kstate;
+
+int cs_index(int cs) { return cs - 1; }
+
+template <typename K>
+int kernel_prepare(K kernel, int smem, int smem_optin, KernelState** out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& k : g_kstate)
+        if (k.fn == fn && k.dev == dev && k.smem_set == smem) {
+            *out = &k;
+            return 0;
+        }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return (int)e;
+    g_kstate.reserve(256);  // pointers into the vector stay valid below this many entries
+    KernelState ks_new{fn, dev, smem, {}};
+    for (int& o : ks_new.occ) o = -1;
+    g_kstate.push_back(ks_new);
+    *out = &g_kstate.back();
+    return 0;
+}
+
+template <typename K>
+int cluster_occupancy(K kernel, KernelState* ks, int cs, int smem) {
+    const int ci = cs_index(cs);
+    if (ks->occ[ci] >= 0) return ks->occ[ci];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * 64);
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    ks->occ[ci] = n;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------ planner
+struct Plan {
+    int path;  // 0 small, 1 cluster
+    int tps;   // small: threads per slab
+    int cs, slots, grid_clusters;
+};
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename K>
+int plan_cluster(K kernel, int NS_in, int NS_out, long long slabs, long long slab_bytes, const DeviceInfo& d, Plan* pl) {
+    const int slots_max = (d.smem_optin - 2048) / (NS_in * kChunkBytes);
+    int S = slots_max;
+    const long long fs = g_opt.slots.load();
+    if (fs > 0 && fs < S) S = (int)fs;
+    if (S < 2) return MICN_ERR_BAD_ARG;
+    const int smem = cluster_smem_bytes(S, NS_in);
+    KernelState* ks = nullptr;
+    int rc = kernel_prepare(kernel, smem, d.smem_optin, &ks);
+    if (rc) return rc;
+
+    const long long V = slab_bytes / 16;
+    const double bw_sm = (double)g_opt.sm_bw_mbps.load() * 1e6, bw_hbm = (double)g_opt.hbm_bw_mbps.load() * 1e6;
+    const long long forced = g_opt.cluster_size.load();
+    double best = 1e30;
+    int best_cs = 0, best_g = 0;
+    for (int cs = 1; cs <= kMaxCluster; ++cs) {
+        if (forced > 0 && cs != forced) continue;
+        if (forced <= 0 && cs > 1 && V / cs < kChunkVecs / 2) continue;  // keep at least half a chunk per CTA
+        int gmax = cluster_occupancy(kernel, ks, cs, smem);
+        const long long cap = g_opt.max_clusters.load();
+        if (cap > 0 && cap < gmax) gmax = (int)cap;
+        if (gmax <= 0) continue;
+        const long long g = slabs < gmax ? slabs : gmax;
+        const long long share = (V + cs - 1) / cs;
+        const long long nchunks = (share + kChunkVecs - 1) / kChunkVecs;
+        const double reread = nchunks > S ? (double)(nchunks - S) / (double)nchunks : 0.0;
+        const double traffic = (double)slab_bytes * (NS_in + NS_out) + 0.5 * reread * NS_in * (double)slab_bytes;
+        auto t_wave = [&](long long active) {
+            const double bw = std::min((double)cs * bw_sm, bw_hbm / (double)active);
+            return traffic / bw + 1.0e-6;  // + per-slab reduce/exchange bubble
+        };
+        const long long full = slabs / g, rem = slabs % g;
+        const double t = (double)full * t_wave(g) + (rem ? t_wave(rem) : 0.0);
+        if (t < best * 0.999) {
+            best = t;
+            best_cs = cs;
+            best_g = (int)g;
+        }
+    }
+    if (!best_cs) return MICN_ERR_BAD_ARG;
+    pl->path = 1;
+    pl->cs = best_cs;
+    pl->slots = S;
+    pl->grid_clusters = best_g;
+    return 0;
+}
+
+int small_tps(long long slab_bytes) {
+    const long long f = g_opt.small_tps.load();
+    if (f == 32 || f == 256 || f == 1024) return (int)f;
+    if (slab_bytes <= 2048) return 32;
+    if (slab_bytes <= 128 * 1024) return 256;
+    return 1024;
+}
+
+void record_plan(const Plan& pl) {
+    g_opt.last_path.store(pl.path);
+    g_opt.last_cs.store(pl.path ? pl.cs : pl.tps);
+    g_opt.last_slots.store(pl.path ? pl.slots : 0);
+    g_opt.last_grid.store(pl.grid_clusters);
+    g_opt.launches.fetch_add(1);
+}
+
+template <typename K, typename P>
+int launch_cluster(K kernel, const P& p, const Plan& pl, int NS, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pl.grid_clusters * pl.cs));
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = cluster_smem_bytes(pl.slots, NS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int S = pl.slots;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, p, S);
+}
+
+// ------------------------------------------------------------------------------------------ typed dispatch
+template <typename T, int EPI>
+int fwd_typed(const FwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStream_t st) {
+    const long long slabs = p.N * p.C, slab_bytes = p.M * (long long)sizeof(T);
+    Plan pl = {};
+    const long long fp = g_opt.force_path.load();
+    bool use_cluster = can_cluster && slab_bytes >= 32 * 1024;
+    if (fp == 0) use_cluster = false;
+    if (fp == 1 && can_cluster) use_cluster = true;
+    if (use_cluster) {
+        auto kernel = micn_fwd_cluster_kernel<T, EPI>;
+        int rc = plan_cluster(kernel, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, slab_bytes, d, &pl);
+        if (rc) return rc;
+        record_plan(pl);
+        return launch_cluster(kernel, p, pl, 1, st);
+    }
+    pl.path = 0;
+    pl.tps = small_tps(slab_bytes);
+    if (pl.tps == 32) {
+        const unsigned grid = (unsigned)((slabs + 7) / 8);
+        pl.grid_clusters = (int)grid;
+        record_plan(pl);
+        micn_fwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+    } else if (pl.tps == 256) {
+        pl.grid_clusters = (int)slabs;
+        record_plan(pl);
+        micn_fwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
+    } else {
+        pl.grid_clusters = (int)slabs;
+        record_plan(pl);
+        micn_fwd_small_kernel<T, EPI, 1024><<<(unsigned)slabs, 1024, 0, st>>>(p);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int EPI>
+int bwd_typed(const BwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStream_t st) {
+    const long long slabs = p.N * p.C, slab_bytes = p.M * (long long)sizeof(T);
+    constexpr int NS = EPI == MICN_EPI_ADD_LRELU ? 3 : 2;
+    Plan pl = {};
+    const long long fp = g_opt.force_path.load();
+    bool use_cluster = can_cluster && slab_bytes >= 32 * 1024;
+    if (fp == 0) use_cluster = false;
+    if (fp == 1 && can_cluster) use_cluster = true;
+    if (use_cluster) {
+        auto kernel = micn_bwd_cluster_kernel<T, EPI>;
+        int rc = plan_cluster(kernel, NS, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, slab_bytes, d, &pl);
+        if (rc) return rc;
+        record_plan(pl);
+        return launch_cluster(kernel, p, pl, NS, st);
+    }
+    pl.path = 0;
+    pl.tps = small_tps(slab_bytes);
+    if (pl.tps == 32) {
+        const unsigned grid = (unsigned)((slabs + 7) / 8);
+        pl.grid_clusters = (int)grid;
+        record_plan(pl);
+        micn_bwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+    } else if (pl.tps == 256) {
+        pl.grid_clusters = (int)slabs;
+        record_plan(pl);
+        micn_bwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
+    } else {
+        pl.grid_clusters = (int)slabs;
+        record_plan(pl);
+        micn_bwd_small_kernel<T, EPI, 1024><<<(unsigned)slabs, 1024, 0, st>>>(p);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int fwd_by_epi(int epi, const FwdParams& p, bool cc, const DeviceInfo& d, cudaStream_t st) {
+    switch (epi) {
+        case MICN_EPI_NONE: return fwd_typed<T, MICN_EPI_NONE>(p, cc, d, st);
+        case MICN_EPI_LRELU: return fwd_typed<T, MICN_EPI_LRELU>(p, cc, d, st);
+        case MICN_EPI_ADD_LRELU: return fwd_typed<T, MICN_EPI_ADD_LRELU>(p, cc, d, st);
+    }
+    return MICN_ERR_BAD_ARG;
+}
+template <typename T>
+int bwd_by_epi(int epi, const BwdParams& p, bool cc, const DeviceInfo& d, cudaStream_t st) {
+    switch (epi) {
+        case MICN_EPI_NONE: return bwd_typed<T, MICN_EPI_NONE>(p, cc, d, st);
+        case MICN_EPI_LRELU: return bwd_typed<T, MICN_EPI_LRELU>(p, cc, d, st);
+        case MICN_EPI_ADD_LRELU: return bwd_typed<T, MICN_EPI_ADD_LRELU>(p, cc, d, st);
+    }
+    return MICN_ERR_BAD_ARG;
+}
+
+int elem_size(int dtype) { return dtype == MICN_F32 ? 4 : (dtype == MICN_BF16 || dtype == MICN_F16) ? 2 : 0; }
+
+constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32)
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int micn_version(void) { return MICN_VERSION; }
+
+const char* micn_error_string(int code) {
+    switch (code) {
+        case MICN_OK: return "ok";
+        case MICN_ERR_BAD_ARG: return "micn: bad argument";
+        case MICN_ERR_BAD_DTYPE: return "micn: unsupported dtype (fp32, bf16, fp16 only)";
+        case MICN_ERR_TOO_MANY_STYLES: return "micn: num_styles exceeds MICN_MAX_STYLES";
+        case MICN_ERR_WORKSPACE: return "micn: workspace missing or too small";
+        case MICN_ERR_UNALIGNED: return "micn: pointer not aligned to the element size";
+        case MICN_ERR_NO_DEVICE: return "micn: no usable CUDA device";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "micn: unknown error";
+}
+
+int micn_set_option(const char* key, long long value) {
+    if (!key) return MICN_ERR_BAD_ARG;
+    for (const auto& o : kOptNames)
+        if (!std::strcmp(o.name, key)) {
+            o.v->store(value);
+            return 0;
+        }
+    return MICN_ERR_BAD_ARG;
+}
+
+long long micn_get_option(const char* key) {
+    if (!key) return -1;
+    for (const auto& o : kOptNames)
+        if (!std::strcmp(o.name, key)) return o.v->load();
+    return -1;
+}
+
+size_t micn_workspace_bytes(int64_t N, int64_t C, int num_styles) {
+    (void)num_styles;
+    if (N < 0 || C < 0) return 0;
+    size_t b = kWsHeader + (size_t)N * (size_t)C * 2 * sizeof(float);
+    return (b + 255) & ~(size_t)255;
+}
+
+int micn_read_status(void* workspace, void* stream, int* status_out) {
+    if (!workspace || !status_out) return MICN_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* w = reinterpret_cast<int*>(workspace) + 1;
+    cudaError_t e = cudaMemcpyAsync(status_out, w, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(w, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(st);
+}
+
+int micn_fwd(const void* x, void* y, const void* residual, const float* const* gamma, const float* const* beta,
+             int num_styles, const int64_t* styles, float* save_mean, float* save_rstd, int64_t N, int64_t C, int64_t M,
+             int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope, float eps, void* workspace,
+             size_t workspace_bytes, void* stream) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if (N == 0 || C == 0 || M == 0) return MICN_OK;
+    if (!x || !y) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if (epilogue < MICN_EPI_NONE || epilogue > MICN_EPI_ADD_LRELU) return MICN_ERR_BAD_ARG;
+    if (epilogue == MICN_EPI_ADD_LRELU && !residual) return MICN_ERR_BAD_ARG;
+    if ((gamma == nullptr) != (beta == nullptr)) return MICN_ERR_BAD_ARG;
+    if ((save_mean == nullptr) != (save_rstd == nullptr)) return MICN_ERR_BAD_ARG;
+    if (N * C > 0x7fffffffLL) return MICN_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & (es - 1))
+        return MICN_ERR_UNALIGNED;
+    if (workspace && workspace_bytes < kWsHeader) return MICN_ERR_WORKSPACE;
+
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc) return rc;
+
+    FwdParams p = {};
+    p.x = x;
+    p.y = y;
+    p.res = epilogue == MICN_EPI_ADD_LRELU ? residual : nullptr;
+    p.affine = gamma != nullptr;
+    for (int s = 0; s < num_styles && gamma; ++s) {
+        if (!gamma[s] || !beta[s]) return MICN_ERR_BAD_ARG;
+        p.gamma[s] = gamma[s];
+        p.beta[s] = beta[s];
+    }
+    p.styles = reinterpret_cast<const long long*>(styles);
+    p.save_mean = save_mean;
+    p.save_rstd = save_rstd;
+    p.status = workspace ? reinterpret_cast<int*>(workspace) + 1 : nullptr;
+    p.N = N;
+    p.C = C;
+    p.M = M;
+    p.x_sN = x_stride_n;
+    p.x_sC = x_stride_c;
+    p.num_styles = num_styles;
+    p.eps = eps;
+    p.slope = slope;
+
+    const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(y) && (!p.res || aligned16(p.res)) &&
+                             ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case MICN_F32: return fwd_by_epi<float>(epilogue, p, can_cluster, *d, st);
+        case MICN_BF16: return fwd_by_epi<__nv_bfloat16>(epilogue, p, can_cluster, *d, st);
+        case MICN_F16: return fwd_by_epi<__half>(epilogue, p, can_cluster, *d, st);
+    }
+    return MICN_ERR_BAD_DTYPE;
+}
+
+int micn_bwd(const void* dy, const void* x, const void* act_out, const float* const* gamma, const float* const* beta,
+             int num_styles, const int64_t* styles, const float* save_mean, const float* save_rstd, void* dx,
+             void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C, int64_t M, int64_t x_stride_n,
+             int64_t x_stride_c, int dtype, int epilogue, float slope, void* workspace, size_t workspace_bytes,
+             void* stream) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if (N == 0 || C == 0 || M == 0) {
+        if (dgamma && C > 0) {
+            cudaStream_t st = (cudaStream_t)stream;
+            cudaMemsetAsync(dgamma, 0, sizeof(float) * num_styles * C, st);
+            cudaMemsetAsync(dbeta, 0, sizeof(float) * num_styles * C, st);
+        }
+        return MICN_OK;
+    }
+    if (!x || !dy || !dx || !save_mean || !save_rstd) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if (epilogue < MICN_EPI_NONE || epilogue > MICN_EPI_ADD_LRELU) return MICN_ERR_BAD_ARG;
+    if (epilogue == MICN_EPI_ADD_LRELU && (!act_out || !dresidual)) return MICN_ERR_BAD_ARG;
+    if ((gamma == nullptr) != (beta == nullptr)) return MICN_ERR_BAD_ARG;
+    if ((dgamma == nullptr) != (dbeta == nullptr)) return MICN_ERR_BAD_ARG;
+    if (N * C > 0x7fffffffLL) return MICN_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+         reinterpret_cast<uintptr_t>(act_out) | reinterpret_cast<uintptr_t>(dresidual)) &
+        (es - 1))
+        return MICN_ERR_UNALIGNED;
+    if (dgamma && (!workspace || workspace_bytes < micn_workspace_bytes(N, C, num_styles))) return MICN_ERR_WORKSPACE;
+
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc) return rc;
+
+    BwdParams p = {};
+    p.dy = dy;
+    p.x = x;
+    p.act_out = epilogue == MICN_EPI_ADD_LRELU ? act_out : nullptr;
+    p.affine = gamma != nullptr;
+    for (int s = 0; s < num_styles && gamma; ++s) {
+        if (!gamma[s] || !beta[s]) return MICN_ERR_BAD_ARG;
+        p.gamma[s] = gamma[s];
+        p.beta[s] = beta[s];
+    }
+    p.styles = reinterpret_cast<const long long*>(styles);
+    p.save_mean = save_mean;
+    p.save_rstd = save_rstd;
+    p.dx = dx;
+    p.dres = epilogue == MICN_EPI_ADD_LRELU ? dresidual : nullptr;
+    p.dgamma = dgamma;
+    p.dbeta = dbeta;
+    if (workspace) {
+        unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+        p.ws_counter = reinterpret_cast<unsigned int*>(w);
+        p.status = reinterpret_cast<int*>(w) + 1;
+        if (dgamma) {
+            p.ws_sum_dy = reinterpret_cast<float*>(w + kWsHeader);
+            p.ws_sum_dyxh = p.ws_sum_dy + N * C;
+        }
+    }
+    p.N = N;
+    p.C = C;
+    p.M = M;
+    p.x_sN = x_stride_n;
+    p.x_sC = x_stride_c;
+    p.num_styles = num_styles;
+    p.slope = slope;
+
+    const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(dy) && aligned16(dx) &&
+                             (!p.act_out || aligned16(p.act_out)) && (!p.dres || aligned16(p.dres)) &&
+                             ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case MICN_F32: return bwd_by_epi<float>(epilogue, p, can_cluster, *d, st);
+        case MICN_BF16: return bwd_by_epi<__nv_bfloat16>(epilogue, p, can_cluster, *d, st);
+        case MICN_F16: return bwd_by_epi<__half>(epilogue, p, can_cluster, *d, st);
+    }
+    return MICN_ERR_BAD_DTYPE;
+}
+
+// ------------------------------------------------------------------------------------------ host-buffer path
+namespace {
+constexpr int kHostStreams = 3;
+cudaStream_t g_hs[kHostStreams] = {nullptr, nullptr, nullptr};
+std::mutex g_host_mu;
+
+inline size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int host_groups(int64_t C) {
+    int g = C >= 12 ? 12 : (int)C;
+    return g < 1 ? 1 : g;
+}
+}  // namespace
+
+size_t micn_host_scratch_bytes(int64_t N, int64_t C, int64_t M, int dtype, int num_styles, int with_backward) {
+    const int es = elem_size(dtype);
+    if (!es || N <= 0 || C <= 0 || M <= 0 || num_styles < 1) return 0;
+    const size_t E = (size_t)N * C * M * es;
+    const int G = host_groups(C);
+    size_t b = 0;
+    b += up256(E) * (with_backward ? 4 : 2);                        // x, y [, dy, dx]
+    b += up256((size_t)N * C * 4) * 2;                              // mean, rstd
+    b += up256((size_t)num_styles * C * 4) * 4;                     // gamma, beta, dgamma, dbeta
+    b += up256((size_t)N * 8);                                      // styles
+    b += (size_t)G * micn_workspace_bytes(N, (C + G - 1) / G + 1, num_styles);
+    return b + 4096;
+}
+
+int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, void* dx_host, const float* gamma_host,
+                      const float* beta_host, int num_styles, const int64_t* styles_host, float* dgamma_host,
+                      float* dbeta_host, int64_t N, int64_t C, int64_t M, int dtype, int epilogue, float slope, float eps,
+                      void* dev_scratch, size_t dev_scratch_bytes) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N <= 0 || C <= 0 || M <= 0 || !x_host || !y_host || !dev_scratch) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if (epilogue != MICN_EPI_NONE && epilogue != MICN_EPI_LRELU) return MICN_ERR_BAD_ARG;
+    const bool bwd = dy_host != nullptr;
+    if (bwd && !dx_host) return MICN_ERR_BAD_ARG;
+    if ((dgamma_host == nullptr) != (dbeta_host == nullptr)) return MICN_ERR_BAD_ARG;
+    if (dev_scratch_bytes < micn_host_scratch_bytes(N, C, M, dtype, num_styles, bwd ? 1 : 0)) return MICN_ERR_WORKSPACE;
+
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    cudaError_t e;
+    for (int i = 0; i < kHostStreams; ++i)
+        if (!g_hs[i] && (e = cudaStreamCreateWithFlags(&g_hs[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+
+    // carve the scratch
+    unsigned char* w = reinterpret_cast<unsigned char*>(dev_scratch);
+    auto take = [&](size_t bytes) {
+        unsigned char* r = w;
+        w += up256(bytes);
+        return r;
+    };
+    const size_t E = (size_t)N * C * M * es;
+    unsigned char* xd = take(E);
+    unsigned char* yd = take(E);
+    unsigned char* dyd = bwd ? take(E) : nullptr;
+    unsigned char* dxd = bwd ? take(E) : nullptr;
+    float* mean = reinterpret_cast<float*>(take((size_t)N * C * 4));
+    float* rstd = reinterpret_cast<float*>(take((size_t)N * C * 4));
+    const size_t SCb = (size_t)num_styles * C * 4;
+    float* gd = reinterpret_cast<float*>(take(SCb));
+    float* bd = reinterpret_cast<float*>(take(SCb));
+    float* dgd = reinterpret_cast<float*>(take(SCb));
+    float* dbd = reinterpret_cast<float*>(take(SCb));
+    int64_t* sd = reinterpret_cast<int64_t*>(take((size_t)N * 8));
+    const int G = host_groups(C);
+    const int64_t cg = (C + G - 1) / G;
+    const size_t ws_each = micn_workspace_bytes(N, cg + 1, num_styles);
+    unsigned char* ws0 = take((size_t)G * ws_each);
+
+    // small parameters first (stream 0), everyone else waits on them through an event
+    cudaStream_t s0 = g_hs[0];
+    const bool affine = gamma_host != nullptr;
+    if (affine) {
+        if ((e = cudaMemcpyAsync(gd, gamma_host, SCb, cudaMemcpyHostToDevice, s0)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(bd, beta_host, SCb, cudaMemcpyHostToDevice, s0)) != cudaSuccess) return (int)e;
+    }
+    if (styles_host && (e = cudaMemcpyAsync(sd, styles_host, (size_t)N * 8, cudaMemcpyHostToDevice, s0)) != cudaSuccess)
+        return (int)e;
+    if ((e = cudaMemsetAsync(ws0, 0, (size_t)G * ws_each, s0)) != cudaSuccess) return (int)e;
+    cudaEvent_t ready;
+    if ((e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+    cudaEventRecord(ready, s0);
+    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(g_hs[i], ready, 0);
+
+    // channel groups: sub-tensors [N, cg, M] staged densely on the device, 2-D copies on the host side
+    int rc = 0;
+    const size_t row_pitch = (size_t)C * M * es;
+    std::vector<const float*> gp(num_styles), bp(num_styles);
+    size_t dev_off = 0;  // dense sub-tensors are packed one after the other
+    for (int g = 0; g < G && !rc; ++g) {
+        const int64_t c0 = g * cg, c1 = std::min<int64_t>(C, c0 + cg);
+        if (c0 >= c1) break;
+        const int64_t cc = c1 - c0;
+        cudaStream_t st = g_hs[g % kHostStreams];
+        const size_t width = (size_t)cc * M * es;
+        const size_t sub = (size_t)N * width;
+        const unsigned char* xh = reinterpret_cast<const unsigned char*>(x_host) + (size_t)c0 * M * es;
+        unsigned char* yh = reinterpret_cast<unsigned char*>(y_host) + (size_t)c0 * M * es;
+        if ((e = cudaMemcpy2DAsync(xd + dev_off, width, xh, row_pitch, width, N, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+            rc = (int)e;
+            break;
+        }
+        for (int s = 0; s < num_styles; ++s) {
+            gp[s] = gd + (size_t)s * C + c0;
+            bp[s] = bd + (size_t)s * C + c0;
+        }
+        // per-group stats live in the [N*C] arrays at a dense per-group offset
+        float* gmean = mean + (size_t)N * c0;
+        float* grstd = rstd + (size_t)N * c0;
+        unsigned char* ws = ws0 + (size_t)g * ws_each;
+        rc = micn_fwd(xd + dev_off, yd + dev_off, nullptr, affine ? gp.data() : nullptr, affine ? bp.data() : nullptr,
+                      num_styles, styles_host ? sd : nullptr, gmean, grstd, N, cc, M, cc * M, M, dtype, epilogue, slope, eps,
+                      ws, ws_each, st);
+        if (rc) break;
+        if ((e = cudaMemcpy2DAsync(yh, row_pitch, yd + dev_off, width, width, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+            rc = (int)e;
+            break;
+        }
+        if (bwd) {
+            const unsigned char* dyh = reinterpret_cast<const unsigned char*>(dy_host) + (size_t)c0 * M * es;
+            unsigned char* dxh = reinterpret_cast<unsigned char*>(dx_host) + (size_t)c0 * M * es;
+            if ((e = cudaMemcpy2DAsync(dyd + dev_off, width, dyh, row_pitch, width, N, cudaMemcpyHostToDevice, st)) !=
+                cudaSuccess) {
+                rc = (int)e;
+                break;
+            }
+            // group-dense [S, cc] gradient blocks, scattered into [S, C] on the host afterwards
+            float* gdg = dgamma_host ? dgd + (size_t)num_styles * c0 : nullptr;
+            float* gdb = dgamma_host ? dbd + (size_t)num_styles * c0 : nullptr;
+            rc = micn_bwd(dyd + dev_off, xd + dev_off, nullptr, affine ? gp.data() : nullptr, affine ? bp.data() : nullptr,
+                          num_styles, styles_host ? sd : nullptr, gmean, grstd, dxd + dev_off, nullptr, gdg, gdb, N, cc, M,
+                          cc * M, M, dtype, epilogue, slope, ws, ws_each, st);
+            if (rc) break;
+            if ((e = cudaMemcpy2DAsync(dxh, row_pitch, dxd + dev_off, width, width, N, cudaMemcpyDeviceToHost, st)) !=
+                cudaSuccess) {
+                rc = (int)e;
+                break;
+            }
+        }
+        dev_off += sub;  // dense packing: the groups tile [0, E) exactly
+    }
+    std::vector<float> tg, tb;
+    if (!rc && bwd && dgamma_host) {
+        tg.resize((size_t)num_styles * C);
+        tb.resize((size_t)num_styles * C);
+        for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(g_hs[i]);
+        if ((e = cudaMemcpy(tg.data(), dgd, SCb, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = (int)e;
+        if (!rc && (e = cudaMemcpy(tb.data(), dbd, SCb, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = (int)e;
+        for (int g = 0; g < G && !rc; ++g) {
+            const int64_t c0 = g * cg, c1 = std::min<int64_t>(C, c0 + cg);
+            if (c0 >= c1) break;
+            const int64_t cc = c1 - c0;
+            for (int s = 0; s < num_styles; ++s)
+                for (int64_t c = 0; c < cc; ++c) {
+                    dgamma_host[(size_t)s * C + c0 + c] = tg[(size_t)num_styles * c0 + (size_t)s * cc + c];
+                    dbeta_host[(size_t)s * C + c0 + c] = tb[(size_t)num_styles * c0 + (size_t)s * cc + c];
+                }
+        }
+    }
+    for (int i = 0; i < kHostStreams; ++i) {
+        e = cudaStreamSynchronize(g_hs[i]);
+        if (e != cudaSuccess && !rc) rc = (int)e;
+    }
+    cudaEventDestroy(ready);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+// micn_common.cuh - device building blocks shared by the instance_cond kernels (sm_100a only).
+//
+//  * 16-byte vector traits for fp32 / bf16 / fp16 slabs (128-bit coalesced HBM traffic)
+//  * Welford/Chan partial statistics (count, mean, M2) and their fixed-order merges
+//  * thin PTX wrappers: mbarrier (local + remote/cluster), 1-D TMA bulk copies
+//    (cp.async.bulk global->shared with an mbarrier transaction count), L2 eviction policies,
+//    DSMEM stores (st.shared::cluster), named barriers.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/micn.h"
+
+namespace micn {
+
+constexpr int kMaxStyles = MICN_MAX_STYLES;
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameter blocks (passed by value; < 1 KB)
+// ---------------------------------------------------------------------------------------------
+struct FwdParams {
+    const void* x;
+    void* y;
+    const void* res;
+    const float* gamma[kMaxStyles];
+    const float* beta[kMaxStyles];
+    const long long* styles;
+    float* save_mean;
+    float* save_rstd;
+    int* status;  // workspace status word (sticky bit 0: style out of range)
+    long long N, C, M;
+    long long x_sN, x_sC;
+    int num_styles;
+    int affine;  // 0 -> gamma = 1, beta = 0
+    float eps, slope;
+};
+
+struct BwdParams {
+    const void* dy;
+    const void* x;
+    const void* act_out;
+    const float* gamma[kMaxStyles];
+    const float* beta[kMaxStyles];
+    const long long* styles;
+    const float* save_mean;
+    const float* save_rstd;
+    void* dx;
+    void* dres;
+    float* dgamma;  // [S*C] or null
+    float* dbeta;
+    float* ws_sum_dy;    // [N*C] per-slab sum(g)
+    float* ws_sum_dyxh;  // [N*C] per-slab sum(g*xhat)
+    unsigned int* ws_counter;
+    int* status;
+    long long N, C, M;
+    long long x_sN, x_sC;
+    int num_styles;
+    int affine;
+    float slope;
+};
+
+// ---------------------------------------------------------------------------------------------
+// element / vector traits: one 16-byte vector per thread per access
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct VecT;
+
+template <>
+struct VecT<float> {
+    static constexpr int N = 4;
+    __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
+        f[0] = __uint_as_float(v.x);
+        f[1] = __uint_as_float(v.y);
+        f[2] = __uint_as_float(v.z);
+        f[3] = __uint_as_float(v.w);
+    }
+    __device__ __forceinline__ static uint4 pack(const float* f) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    __device__ __forceinline__ static float load1(const float* p) { return *p; }
+    __device__ __forceinline__ static void store1(float* p, float v) { *p = v; }
+};
+
+template <>
+struct VecT<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
+        // bf16 -> fp32 is a 16-bit shift: no conversion instruction needed
+        f[0] = __uint_as_float(v.x << 16);
+        f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16);
+        f[3] = __uint_as_float(v.y & 0xffff0000u);
+        f[4] = __uint_as_float(v.z << 16);
+        f[5] = __uint_as_float(v.z & 0xffff0000u);
+        f[6] = __uint_as_float(v.w << 16);
+        f[7] = __uint_as_float(v.w & 0xffff0000u);
+    }
+    __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __device__ __forceinline__ static uint4 pack(const float* f) {
+        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+    __device__ __forceinline__ static float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ __forceinline__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+template <>
+struct VecT<__half> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void unpack2(uint32_t u, float& lo, float& hi) {
+        float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+        lo = f.x;
+        hi = f.y;
+    }
+    __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
+        unpack2(v.x, f[0], f[1]);
+        unpack2(v.y, f[2], f[3]);
+        unpack2(v.z, f[4], f[5]);
+        unpack2(v.w, f[6], f[7]);
+    }
+    __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __device__ __forceinline__ static uint4 pack(const float* f) {
+        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+    __device__ __forceinline__ static float load1(const __half* p) { return __half2float(*p); }
+    __device__ __forceinline__ static void store1(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// streaming global accesses (each voxel is touched once per pass: keep it out of L1)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Welford / Chan partial statistics
+// ---------------------------------------------------------------------------------------------
+struct Stat {
+    float n, mean, m2;
+};
+
+__device__ __forceinline__ Stat stat_merge(const Stat& a, const Stat& b) {
+    Stat r;
+    r.n = a.n + b.n;
+    const float inv = r.n > 0.f ? __fdividef(1.f, r.n) : 0.f;
+    const float d = b.mean - a.mean;
+    const float wb = b.n * inv;
+    r.mean = fmaf(d, wb, a.mean);
+    r.m2 = a.m2 + b.m2 + d * d * a.n * wb;
+    return r;
+}
+
+// shifted sums (sum(x-K), sum((x-K)^2), n) -> (n, mean, M2)
+__device__ __forceinline__ Stat stat_from_shifted(float K, float s1, float s2, float n) {
+    Stat r;
+    r.n = n;
+    if (n > 0.f) {
+        const float m = s1 / n;
+        r.mean = K + m;
+        r.m2 = fmaxf(s2 - s1 * m, 0.f);
+    } else {
+        r.mean = 0.f;
+        r.m2 = 0.f;
+    }
+    return r;
+}
+
+__device__ __forceinline__ Stat stat_warp_reduce(Stat s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Stat t;
+        t.n = __shfl_xor_sync(0xffffffffu, s.n, o);
+        t.mean = __shfl_xor_sync(0xffffffffu, s.mean, o);
+        t.m2 = __shfl_xor_sync(0xffffffffu, s.m2, o);
+        // fixed pairing -> every lane ends with the same bits (xor butterfly merges (lo,hi) in the
+        // same order on both sides only if the merge is symmetric; make it so by ordering on lane)
+        const bool lo = ((threadIdx.x & o) == 0);
+        s = lo ? stat_merge(s, t) : stat_merge(t, s);
+    }
+    return s;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// style / affine lookup
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int load_style(const long long* styles, long long n, int num_styles, int* status) {
+    long long s = styles ? styles[n] : 0;
+    if (s < 0) s += num_styles;  // python indexing of the ModuleList (conditional_instance_norm.py:60)
+    if (s < 0 || s >= num_styles) {
+        if (status) atomicOr(status, 1);
+        s = s < 0 ? 0 : num_styles - 1;
+    }
+    return (int)s;
+}
+
+template <typename P>
+__device__ __forceinline__ void load_affine(const P& p, int s, long long c, float& g, float& b) {
+    if (p.affine) {
+        // pointer tables live in the kernel parameter block; a dynamic index would force a local
+        // copy, so select with a short unrolled scan
+        const float* gp = p.gamma[0];
+        const float* bp = p.beta[0];
+#pragma unroll
+        for (int i = 1; i < kMaxStyles; ++i) {
+            if (i == s) {
+                gp = p.gamma[i];
+                bp = p.beta[i];
+            }
+        }
+        g = __ldg(gp + c);
+        b = __ldg(bp + c);
+    } else {
+        g = 1.f;
+        b = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX: shared addresses, mbarrier, TMA bulk copies, cluster
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier that lives in another CTA of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// A lost arrival must surface as a trapped kernel, never as a hung GPU: bound every wait (~4 s).
+#ifndef MICN_WAIT_TIMEOUT_NS
+#define MICN_WAIT_TIMEOUT_NS 4000000000ull
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (((++spins) & 0x3ffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (((++spins) & 0x3ffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+    }
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// 1-D TMA bulk copy global -> this CTA's shared memory; completion is signalled on `bar` as
+// `bytes` of transaction count.  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t nclusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+// map a shared::cta address of this CTA to the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// named barrier over a subset of the CTA's warps (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace micn
