@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py - the instance_cond hot path on B200: `python bench.py --gpus N --steps K --warmup W`.
+
+A step = one pass of the hot path over one batch: `micn_fwd` + `micn_bwd` (include/micn.h) on the
+north-star activation, 1 x 48 x 96^3 bf16 per GPU (C-Swin-UNETR f=48 `encoder1.norm*`, BASELINE.json
+configs[1]).  N > 1: one process per GPU (torchrun), every rank runs its own
+patch (the norm is per-sample, no forward collective) and the per-style d(gamma)/d(beta) are
+all-reduced over NCCL inside the step - weak scaling.
+
+Prints ONE JSON line (rank 0):
+  value     algorithmic GB/s, (2 + 3) * E * s bytes per step per GPU, inputs resident in HBM, CUDA events
+  e2e       the same metric through `micn_fwd_bwd_host` (host pinned buffers in, host buffers out;
+            H2D / D2H inside the timed region)
+  roofline  the dominant kernel (backward: 3 * E * s bytes per launch) against MEASURED_PEAKS.json
+  cpu_baseline  the oracle's torch-CPU port of the reference call sequence on the box's host cores
+`--impl reference` times that CPU port alone (the reference's own path: per-sample F.instance_norm +
+torch.stack + autograd) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "instance_cond_fwd_bwd_hbm_GBps"
+UNIT = "GB/s"
+DT_BYTES = {"bf16": 2, "fp32": 4, "fp16": 2}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="1,48,96", help="N,C,S per GPU (S^3 voxels per slab)")
+    ap.add_argument("--dtype", default="bf16", choices=list(DT_BYTES))
+    ap.add_argument("--epilogue", default="none", choices=["none", "lrelu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time the BASELINE.json microbench sweep (extra key)")
+    return ap.parse_args()
+
+
+def workload(args):
+    n, c, s = (int(v) for v in args.shape.split(","))
+    return n, c, s, s * s * s
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0 - 0.05) and (t1 is None or t <= t1 + 0.15)] or \
+               [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [v.strip() for v in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU port (reference arm / cpu_baseline)
+def cpu_port_time(n, c, s, dtype_name, budget_s, warmup, steps=None):
+    """The reference's call sequence (per-sample F.instance_norm + torch.stack, autograd backward) on the host
+    cores, through oracle.port_fwd_bwd.  Returns (seconds per fwd+bwd, iterations, cores)."""
+    import torch
+
+    from oracle import micn_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dt = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[dtype_name]
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(n, c, s, s, s, generator=g) * 2 + 1).to(dt)
+    dy = torch.randn(n, c, s, s, s, generator=g).to(dt)
+    w = [1 + 0.3 * torch.randn(c, generator=g) for _ in range(2)]
+    b = [0.3 * torch.randn(c, generator=g) for _ in range(2)]
+    styles = [i % 2 for i in range(n)]
+    for _ in range(max(1, warmup)):
+        O.port_fwd_bwd(x, dy, styles, w, b)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        O.port_fwd_bwd(x, dy, styles, w, b)
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif len(times) >= 3 and time.perf_counter() - t_start > budget_s:
+            break
+    return sum(times) / len(times), len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, c, s, m = workload(args)
+    es = DT_BYTES[args.dtype]
+    steps = min(args.steps, 40)  # bounded sample: each step is one full fwd+bwd of the workload on the CPU
+    sec, iters, cores = cpu_port_time(n, c, s, args.dtype, 0, min(args.warmup, 3), steps=steps)
+    gbps = 5.0 * n * c * m * es / sec / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbps, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
+        "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"instance_cond fwd+bwd {n}x{c}x{s}^3 {args.dtype} (C-Swin-UNETR encoder1 norm), "
+                               "reference call sequence on host CPU"},
+        "cpu_baseline": {"value": gbps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{iters} full fwd+bwd passes of the workload, torch CPU, {cores} threads"},
+        "e2e": {"value": gbps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "voxels_per_s": n * m / sec,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mi_seg_b200 as pkg
+
+    lib = pkg._lib.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, c, s, m = workload(args)
+    S = 2
+    es = DT_BYTES[args.dtype]
+    tdt = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[args.dtype]
+    code = {"fp32": 0, "bf16": 1, "fp16": 2}[args.dtype]
+    epi = {"none": 0, "lrelu": 1}[args.epilogue]
+    E = n * c * m
+    bytes_fwd, bytes_bwd = 2 * E * es, 3 * E * es
+
+    # rotating buffer sets, footprint >> L2 (126 MB): every launch reads HBM-cold inputs
+    R = max(3, int(600e6 // (4 * E * es)) + 1)
+    torch.manual_seed(rank)
+    xs = [(torch.randn(n, c, m, device=dev) * 2 + 1).to(tdt) for _ in range(R)]
+    dys = [torch.randn(n, c, m, device=dev).to(tdt) for _ in range(R)]
+    ys = [torch.empty_like(xs[0]) for _ in range(R)]
+    dxs = [torch.empty_like(xs[0]) for _ in range(R)]
+    means = [torch.empty(n * c, device=dev) for _ in range(R)]
+    rstds = [torch.empty(n * c, device=dev) for _ in range(R)]
+    gamma = 1 + 0.3 * torch.randn(S, c, device=dev)
+    beta = 0.3 * torch.randn(S, c, device=dev)
+    styles = (torch.arange(n, device=dev) % S).to(torch.int64)
+    grads = torch.empty(2, S, c, device=dev)  # dgamma, dbeta: one bucket for the all-reduce
+    wsb = lib.micn_workspace_bytes(n, c, S)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    gp = (ctypes.c_void_p * S)(*[gamma[k].data_ptr() for k in range(S)])
+    bp = (ctypes.c_void_p * S)(*[beta[k].data_ptr() for k in range(S)])
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def fwd(i):
+        rc = lib.micn_fwd(xs[i].data_ptr(), ys[i].data_ptr(), None, gp, bp, S, styles.data_ptr(), means[i].data_ptr(),
+                          rstds[i].data_ptr(), n, c, m, c * m, m, code, epi, 0.01, 1e-5, ws.data_ptr(), wsb, stream)
+        if rc:
+            raise RuntimeError(f"micn_fwd rc={rc}")
+
+    def bwd(i):
+        rc = lib.micn_bwd(dys[i].data_ptr(), xs[i].data_ptr(), None, gp, bp, S, styles.data_ptr(), means[i].data_ptr(),
+                          rstds[i].data_ptr(), dxs[i].data_ptr(), None, grads[0].data_ptr(), grads[1].data_ptr(),
+                          n, c, m, c * m, m, code, epi, 0.01, ws.data_ptr(), wsb, stream)
+        if rc:
+            raise RuntimeError(f"micn_bwd rc={rc}")
+
+    def step(i):
+        # forward on set i, backward on the NEXT set (its statistics come from an earlier forward of the
+        # same data): neither kernel finds its inputs in L2 from the launch before it
+        fwd(i % R)
+        bwd((i + 1) % R)
+        if world > 1:
+            dist.all_reduce(grads)
+
+    for i in range(R):  # statistics for every set
+        fwd(i)
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = pkg._lib.get_option("launches")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    launches = pkg._lib.get_option("launches") - launches0
+    ms_total = e0.elapsed_time(e1)
+
+    # per-kernel durations (roofline), same loop with an event after every launch
+    K2 = min(args.steps, 200)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K2)]
+    for i in range(K2):
+        evs[i][0].record()
+        fwd(i % R)
+        evs[i][1].record()
+        bwd((i + 1) % R)
+        evs[i][2].record()
+    torch.cuda.synchronize()
+    t_region_end = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_region_end) if rank == 0 else None
+    fwd_us = [e[0].elapsed_time(e[1]) * 1e3 for e in evs]
+    bwd_us = [e[1].elapsed_time(e[2]) * 1e3 for e in evs]
+    fwd_avg, bwd_avg = sum(fwd_us) / K2, sum(bwd_us) / K2
+
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI (micn_fwd_bwd_host), blocking call, wall clock
+    e2e = None
+    if not args.no_e2e:
+        scratch_b = lib.micn_host_scratch_bytes(n, c, m, code, S, 1)
+        scratch = torch.empty(scratch_b, dtype=torch.uint8, device=dev)
+        hx = xs[0].cpu().pin_memory()
+        hdy = dys[0].cpu().pin_memory()
+        hy = torch.empty_like(hx).pin_memory()
+        hdx = torch.empty_like(hx).pin_memory()
+        hg, hb = gamma.cpu().contiguous(), beta.cpu().contiguous()
+        hst = styles.cpu()
+        hdg, hdb = torch.empty(S, c), torch.empty(S, c)
+
+        def host_step():
+            rc = lib.micn_fwd_bwd_host(hx.data_ptr(), hdy.data_ptr(), hy.data_ptr(), hdx.data_ptr(), hg.data_ptr(),
+                                       hb.data_ptr(), S, hst.data_ptr(), hdg.data_ptr(), hdb.data_ptr(), n, c, m, code,
+                                       epi, 0.01, 1e-5, scratch.data_ptr(), scratch_b)
+            if rc:
+                raise RuntimeError(f"micn_fwd_bwd_host rc={rc}")
+
+        ke = max(3, min(args.steps, 20))
+        for _ in range(3):
+            host_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            host_step()
+        sec = (time.perf_counter() - t0) / ke
+        if world > 1:
+            t = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        # check the host path against the device path once (same data as set 0)
+        torch.cuda.synchronize()
+        def _rel(a, b):
+            return float((a.float() - b.float()).abs().max() / b.float().abs().max())
+        tol = 1e-5 if args.dtype == "fp32" else 2e-2
+        ok = _rel(hy.to(dev), ys[0]) < tol and _rel(hdx.to(dev), dxs[0]) < tol
+        small = 2 * S * c * 4 + n * 8
+        e2e = {"value": world * (bytes_fwd + bytes_bwd) / sec / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": 2 * E * es + small, "d2h_bytes_per_step": 2 * E * es + 2 * S * c * 4,
+               "ms_per_step": sec * 1e3, "steps": ke, "timer": "host wall clock around the blocking C-ABI call",
+               "api": "micn_fwd_bwd_host (pinned host x, dy -> host y, dx, dgamma, dbeta)",
+               "matches_device_path": ok}
+
+    # ---- like-for-like GPU competitor: the reference's call sequence on the same B200 through PyTorch
+    torch_gpu = None
+    if rank == 0:
+        import torch.nn.functional as F
+        xg = xs[0].reshape(n, c, s, s, s).detach().requires_grad_(True)
+        dyg = dys[0].reshape(n, c, s, s, s)
+        wg = [gamma[k].clone().requires_grad_(True) for k in range(S)]
+        bg = [beta[k].clone().requires_grad_(True) for k in range(S)]
+        st_host = styles.tolist()
+
+        def ref_step():
+            y = torch.stack([F.instance_norm(xg[i].unsqueeze(0), None, None, wg[st_host[i]], bg[st_host[i]], True, 0.1,
+                                             1e-5).squeeze(0) for i in range(n)])
+            y.backward(dyg)
+            xg.grad = None
+        for _ in range(3):
+            ref_step()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            ref_step()
+        b_.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b_) / 10
+        torch_gpu = {"ms_per_step": ms, "value": (bytes_fwd + bytes_bwd) / (ms * 1e-3) / 1e9, "unit": UNIT,
+                     "what": "per-sample F.instance_norm + torch.stack + autograd on the same GPU (PyTorch/ATen)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    bwd_gbps = bytes_bwd / (bwd_avg * 1e-6) / 1e9
+    fwd_gbps = bytes_fwd / (fwd_avg * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "micn_bwd (backward, 3*E*s algorithmic bytes per launch)",
+                "achieved": bwd_gbps, "peak": peak, "unit": "GB/s", "frac": bwd_gbps / peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_us": bwd_avg, "bytes_per_launch": bytes_bwd,
+                "fwd": {"achieved": fwd_gbps, "frac": fwd_gbps / peak, "avg_launch_us": fwd_avg,
+                        "bytes_per_launch": bytes_fwd},
+                "fwd_plus_bwd": {"achieved": (bytes_fwd + bytes_bwd) / ((fwd_avg + bwd_avg) * 1e-6) / 1e9,
+                                 "frac": (bytes_fwd + bytes_bwd) / ((fwd_avg + bwd_avg) * 1e-6) / 1e9 / peak}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(f"bwd_{args.dtype}_{n}x{c}x{s}")
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        sec, iters, cores = cpu_port_time(n, c, s, args.dtype, 10.0, 1)
+        cpu_baseline = {"value": 5.0 * E * es / sec / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                        "ms_per_step": sec * 1e3,
+                        "sample": f"{iters} full fwd+bwd passes of the same {n}x{c}x{s}^3 {args.dtype} workload "
+                                  f"(reference call sequence on torch CPU, {cores} threads)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic",
+        "config": {"workload": f"instance_cond fwd+bwd, {n}x{c}x{s}^3 {args.dtype} per GPU (C-Swin-UNETR f=48 encoder1 "
+                               f"norm; BASELINE.json configs[1] hot path), epilogue={args.epilogue}",
+                   "global_batch": n * world, "parallelism": f"dp{world}",
+                   "l2": f"{R} rotating buffer sets ({R * 4 * E * es / 1e6:.0f} MB) > 126 MB L2; backward reads a "
+                         "different set than the forward before it",
+                   "collective": "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none"},
+        "voxels_per_s": world * n * m / (ms_step * 1e-3),
+        "frac_of_peak": value / world / peak,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "torch_gpu_reference": torch_gpu,
+        "plan": {k: pkg._lib.get_option(k) for k in ("last_path", "last_cs", "last_slots", "last_grid")},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""mi-seg_b200: B200-native `instance_cond` (modality-conditioned instance norm) for MI-Seg.
+
+One hot path only: hand-written sm_100a CUDA forward/backward kernels behind
+the C ABI of include/micn.h (csrc/ -> libmicn.so), and the Python mirror of the reference's module
+interface that calls them.  The directory name carries a hyphen, so import it with
+`importlib.import_module("mi-seg_b200")` or through the `mi_seg_b200` alias module at the repo root.
+"""
+from . import _lib
+from .functional import instance_cond, reset_workspaces
+from .integration import convert_module, install, uninstall
+from .norms import (FastConditionalInstanceNorm1d, FastConditionalInstanceNorm2d, FastConditionalInstanceNorm3d,
+                    make_dropin_classes)
+
+__all__ = ["instance_cond", "reset_workspaces", "install", "uninstall", "convert_module",
+           "FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
+           "make_dropin_classes", "_lib"]

@@ -148,7 +148,10 @@ int plan_cluster(K kernel, int NS_in, int NS_out, long long slabs, long long sla
     int S = slots_max;
     const long long fs = g_opt.slots.load();
     if (fs > 0 && fs < S) S = (int)fs;
-    if (S < 2) return MICN_ERR_BAD_ARG;
+    // the 16 consumer warps span 4 consecutive chunks; parity waits are only sound when a slot cannot
+    // be two phases away from any waiter, i.e. the ring holds more than those 4 chunks
+    if (S < 5) S = 5;
+    if (slots_max < 5) return MICN_ERR_BAD_ARG;
     const int smem = cluster_smem_bytes(S, NS_in);
     KernelState* ks = nullptr;
     int rc = kernel_prepare(kernel, smem, d.smem_optin, &ks);

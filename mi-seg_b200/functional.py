@@ -1,0 +1,195 @@
+"""Autograd entry point of the B200 instance_cond kernels.
+
+`instance_cond(x, styles, weights, biases, ...)` computes, per sample n and channel c,
+
+    y[n, c] = (x[n, c] - mean) * rstd * weights[styles[n]][c] + biases[styles[n]][c]
+
+(+ optional fused epilogue) by calling `micn_fwd` / `micn_bwd` of libmicn.so on the current CUDA
+stream.  It replaces the per-sample loop + torch.stack of the reference
+(/root/reference/networks/norms/conditional_instance_norm.py:59-60) and the autograd graph behind
+it; the epilogues replace dynunet_block.py:107-111 / :113-125.
+
+No CPU path: CPU tensors raise.  All statistics / parameter math is fp32; I/O dtype = x.dtype.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.MICN_F32, torch.bfloat16: _lib.MICN_BF16, torch.float16: _lib.MICN_F16}
+_EPILOGUES = {"none": _lib.EPI_NONE, "lrelu": _lib.EPI_LRELU, "add_lrelu": _lib.EPI_ADD_LRELU}
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device, n: int, c: int, num_styles: int) -> torch.Tensor:
+    """Zero-filled device workspace, one per (device, stream), grown on demand (micn.h: must be
+    zero-filled once when allocated; the kernels leave it reusable)."""
+    need = int(_lib.lib().micn_workspace_bytes(n, c, num_styles))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def reset_workspaces() -> None:
+    """Drop every cached workspace (call after a CUDA error so stale control words cannot survive)."""
+    _workspaces.clear()
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _dense_spatial(x: torch.Tensor) -> bool:
+    """True when dims 2.. form one dense block (so a slab is M consecutive elements)."""
+    expect = 1
+    for size, stride in zip(reversed(x.shape[2:]), reversed(x.stride()[2:])):
+        if size != 1 and stride != expect:
+            return False
+        expect *= size
+    return True
+
+
+def _as_ncm(x: torch.Tensor):
+    """Return (tensor, stride_n, stride_c) with dense slabs; copies only when the layout forces it."""
+    if not _dense_spatial(x):
+        x = x.contiguous()
+    n, c = x.shape[0], x.shape[1]
+    m = 1
+    for s in x.shape[2:]:
+        m *= s
+    sn = x.stride(0) if n > 1 else c * m
+    sc = x.stride(1) if c > 1 else m
+    if sn < 0 or sc < 0 or (n > 1 and sn == 0) or (c > 1 and sc == 0):  # expanded / flipped views
+        x = x.contiguous()
+        sn, sc = c * m, m
+    return x, sn, sc, m
+
+
+def _f32_params(ts: Sequence[torch.Tensor], device) -> List[torch.Tensor]:
+    out = []
+    for t in ts:
+        if t.device != device:
+            raise RuntimeError(f"instance_cond: parameter on {t.device}, input on {device}")
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        out.append(t)
+    return out
+
+
+class _InstanceCondFn(torch.autograd.Function):
+    """forward(x, styles_dev, residual, eps, epilogue, slope, present, S, *weights, *biases)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, styles_dev, residual, eps, epilogue, slope, present, num_styles, *params):
+        if not x.is_cuda:
+            raise RuntimeError("instance_cond (mi-seg_b200) runs on CUDA tensors only: there is no CPU fallback")
+        if x.dtype not in _DTYPES:
+            raise TypeError(f"instance_cond: unsupported dtype {x.dtype} (float32, bfloat16, float16)")
+        lib = _lib.lib()
+        dev = x.device
+        affine = len(params) > 0
+        weights = _f32_params(params[:num_styles], dev) if affine else []
+        biases = _f32_params(params[num_styles:], dev) if affine else []
+        xs, sn, sc, m = _as_ncm(x)
+        n, c = xs.shape[0], xs.shape[1]
+        if affine and any(w.numel() != c for w in weights + biases):
+            raise ValueError("instance_cond: parameter length does not match the channel count")
+        y = torch.empty(xs.shape, dtype=xs.dtype, device=dev)  # fresh contiguous NC* (as torch.stack gives)
+        mean = torch.empty(n * c, dtype=torch.float32, device=dev)
+        rstd = torch.empty(n * c, dtype=torch.float32, device=dev)
+        res = None
+        if epilogue == _lib.EPI_ADD_LRELU:
+            if residual is None or residual.shape != xs.shape or residual.dtype != xs.dtype:
+                raise ValueError("instance_cond: add_lrelu needs a residual of the input's shape and dtype")
+            res = residual.contiguous()
+        ws = _workspace(dev, n, c, num_styles)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            gp = _ptr_array(weights) if affine else None
+            bp = _ptr_array(biases) if affine else None
+            rc = lib.micn_fwd(xs.data_ptr(), y.data_ptr(), res.data_ptr() if res is not None else None, gp, bp,
+                              num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
+                              mean.data_ptr(), rstd.data_ptr(), n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue,
+                              float(slope), float(eps), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "micn_fwd")
+        ctx.save_for_backward(xs, styles_dev, mean, rstd, y if epilogue == _lib.EPI_ADD_LRELU else None, *weights,
+                              *biases)
+        ctx.meta = (n, c, m, sn, sc, epilogue, float(slope), num_styles, affine, present,
+                    residual is not None and epilogue == _lib.EPI_ADD_LRELU)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        n, c, m, sn, sc, epilogue, slope, num_styles, affine, present, has_res = ctx.meta
+        xs, styles_dev, mean, rstd, act_out, *params = ctx.saved_tensors
+        weights, biases = params[:num_styles], params[num_styles:]
+        lib = _lib.lib()
+        dev = xs.device
+        dy = dy.contiguous()
+        if dy.dtype != xs.dtype:
+            dy = dy.to(xs.dtype)
+        dx = torch.empty(dy.shape, dtype=xs.dtype, device=dev)
+        dres = torch.empty_like(dx) if has_res else None
+        need_param_grads = affine and any(ctx.needs_input_grad[8:])
+        dgamma = torch.empty((num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
+        dbeta = torch.empty((num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
+        ws = _workspace(dev, n, c, num_styles)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            gp = _ptr_array(weights) if affine else None
+            bp = _ptr_array(biases) if affine else None
+            rc = lib.micn_bwd(dy.data_ptr(), xs.data_ptr(), act_out.data_ptr() if act_out is not None else None,
+                              gp, bp, num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
+                              mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                              dres.data_ptr() if dres is not None else None,
+                              dgamma.data_ptr() if dgamma is not None else None,
+                              dbeta.data_ptr() if dbeta is not None else None, n, c, m, sn, sc, _DTYPES[xs.dtype],
+                              epilogue, slope, ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "micn_bwd")
+        grads: List[Optional[torch.Tensor]] = [dx, None, dres, None, None, None, None, None]
+        if affine:
+            for which in (dgamma, dbeta):
+                for s in range(num_styles):
+                    # styles absent from the batch keep .grad None like the reference (when known on the host)
+                    absent = present is not None and not present[s]
+                    grads.append(None if (which is None or absent) else which[s])
+        return tuple(grads)
+
+
+def instance_cond(x: torch.Tensor, styles_dev: Optional[torch.Tensor], weights: Sequence[torch.Tensor],
+                  biases: Sequence[torch.Tensor], eps: float = 1e-5, epilogue: str = "none",
+                  residual: Optional[torch.Tensor] = None, slope: float = 0.01,
+                  present: Optional[Sequence[bool]] = None, num_styles: Optional[int] = None) -> torch.Tensor:
+    """Batched input [N, C, *spatial]; `styles_dev` an int64 CUDA tensor [N] (None = style 0 everywhere);
+    `weights` / `biases` per-style lists of [C] tensors (norms[s].weight / .bias), or empty for a
+    non-affine norm.  `epilogue`: "none" | "lrelu" (lrelu(norm(x))) | "add_lrelu" (lrelu(norm(x)+residual))."""
+    if epilogue not in _EPILOGUES:
+        raise ValueError(f"instance_cond: unknown epilogue {epilogue!r}")
+    s = len(weights) if len(weights) else (num_styles or 1)
+    if len(weights) != len(biases):
+        raise ValueError("instance_cond: weights and biases must have one entry per style")
+    if s > _lib.MAX_STYLES:
+        raise ValueError(f"instance_cond: at most {_lib.MAX_STYLES} styles are supported")
+    if x.dim() < 3:
+        raise ValueError("instance_cond: expected [N, C, *spatial] input")
+    if styles_dev is not None:
+        if styles_dev.device != x.device or styles_dev.dtype != torch.int64 or styles_dev.numel() != x.shape[0]:
+            raise ValueError("instance_cond: styles must be an int64 tensor [N] on the input's device")
+        styles_dev = styles_dev.reshape(-1).contiguous()
+    return _InstanceCondFn.apply(x, styles_dev, residual, eps, _EPILOGUES[epilogue], slope,
+                                 tuple(present) if present is not None else None, s, *weights, *biases)

@@ -1,0 +1,72 @@
+"""Registration of the fast classes behind MI-Seg's own layer factory (the drop-in boundary).
+
+    import sys; sys.path.insert(0, "/path/to/MI-Seg")
+    import importlib; importlib.import_module("mi-seg_b200").install()
+    # ... from here on `--encoder_norm_name=instance_cond` builds FastConditionalInstanceNorm*d
+
+`Norm.add_factory_callable` (networks/layers/factories.py:97-102) overwrites the "instance_cond"
+entry that `instance_cond_factory` (:227-232) registered; `get_norm_layer` (networks/layers/utils.py:
+43-50) then instantiates our class with the same kwargs (num_styles, affine, num_features).  Nothing in
+`networks/` is edited.
+"""
+from __future__ import annotations
+
+import importlib
+
+from . import norms
+
+_installed = None
+
+
+def install(factories_module: str = "networks.layers.factories",
+            norm_module: str = "networks.norms.conditional_instance_norm"):
+    """Register the fast classes under "instance_cond".  Returns the (1d, 2d, 3d) classes.
+    MI-Seg's repository root must already be importable (sys.path)."""
+    global _installed
+    factories = importlib.import_module(factories_module)
+    ref = importlib.import_module(norm_module)
+    classes = norms.make_dropin_classes(ref)
+
+    def fast_instance_cond_factory(dim: int):
+        return classes[dim - 1]
+
+    factories.Norm.add_factory_callable("instance_cond", fast_instance_cond_factory)
+    _installed = (factories, ref, classes)
+    return classes
+
+
+def uninstall():
+    """Restore MI-Seg's own classes under "instance_cond"."""
+    global _installed
+    if _installed is None:
+        return
+    factories, ref, _ = _installed
+    types = (ref.ConditionalInstanceNorm1d, ref.ConditionalInstanceNorm2d, ref.ConditionalInstanceNorm3d)
+    factories.Norm.add_factory_callable("instance_cond", lambda dim: types[dim - 1])
+    _installed = None
+
+
+def convert_module(model, classes=None):
+    """Swap already-constructed reference `_ConditionalInstanceNorm` modules in `model` for fast ones
+    sharing the same parameters (state-dict keys unchanged).  For checkpoints built before install()."""
+    import torch.nn as nn
+
+    if classes is None:
+        classes = _installed[2] if _installed is not None else (
+            norms.FastConditionalInstanceNorm1d, norms.FastConditionalInstanceNorm2d,
+            norms.FastConditionalInstanceNorm3d)
+    by_norm = {nn.InstanceNorm1d: classes[0], nn.InstanceNorm2d: classes[1], nn.InstanceNorm3d: classes[2]}
+    for name, child in list(model.named_children()):
+        inner = getattr(child, "norms", None)
+        if isinstance(inner, nn.ModuleList) and len(inner) and type(inner[0]) in by_norm \
+                and hasattr(child, "num_styles") and not isinstance(child, norms.FastForwardMixin):
+            cls = by_norm[type(inner[0])]
+            new = cls.__new__(cls)
+            nn.Module.__init__(new)
+            new.num_styles = child.num_styles
+            new.norms = inner
+            new.train(child.training)
+            setattr(model, name, new)
+        else:
+            convert_module(child, classes)
+    return model

@@ -1,0 +1,220 @@
+"""Drop-in `instance_cond` modules: same constructor, `forward(input, styles)` signature, validation
+messages and `norms.{s}.weight/bias` state-dict layout as the reference classes
+(/root/reference/networks/norms/conditional_instance_norm.py:11-107), with the per-sample Python
+loop + torch.stack (:59-60) replaced by one call into the sm_100a kernels.
+
+Two ways to use them:
+
+* stand-alone: `FastConditionalInstanceNorm{1,2,3}d` below derive from a local mirror of the
+  reference base class, so they work where MI-Seg is not importable (the GPU box, the tests);
+* inside MI-Seg: `integration.install()` re-creates the three classes on top of MI-Seg's own
+  `_ConditionalInstanceNorm` (every block gates on `isinstance(norm, _ConditionalInstanceNorm)`,
+  SURVEY.md section 8b) and registers them under the factory key "instance_cond".
+"""
+from __future__ import annotations
+
+import warnings
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .functional import instance_cond
+
+__all__ = ["FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
+           "FastForwardMixin", "make_dropin_classes"]
+
+_STYLE_CACHE = {}
+_STYLE_CACHE_MAX = 256
+
+
+def _host_styles(styles, num_styles: int) -> Optional[List[int]]:
+    """Styles as a list of python ints when they are visible on the host without a device sync
+    (list / int / CPU tensor); None for CUDA tensors.  Mirrors how the reference indexes its
+    ModuleList (:57, :60): negative ids wrap, out of range -> IndexError, floats -> TypeError."""
+    if isinstance(styles, Tensor):
+        if styles.is_floating_point() or styles.is_complex() or styles.dtype == torch.bool:
+            # ModuleList.__getitem__ -> operator.index(tensor) raises TypeError for non-integer tensors
+            raise TypeError(f"only integer tensors of a single element can be converted to an index "
+                            f"(got styles of dtype {styles.dtype})")
+        if styles.is_cuda:
+            return None
+        vals = [int(v) for v in styles.reshape(-1).tolist()]
+    elif isinstance(styles, int):
+        vals = [styles]
+    else:
+        vals = []
+        for v in styles:
+            if isinstance(v, Tensor):
+                if v.is_floating_point():
+                    raise TypeError("only integer tensors of a single element can be converted to an index")
+                v = int(v.item())
+            elif isinstance(v, bool) or not isinstance(v, int):
+                if hasattr(v, "__index__"):
+                    v = v.__index__()
+                else:
+                    raise TypeError(f"list indices must be integers or slices, not {type(v).__name__}")
+            vals.append(int(v))
+    out = []
+    for v in vals:
+        if v < -num_styles or v >= num_styles:
+            raise IndexError(f"index {v} is out of range")
+        out.append(v + num_styles if v < 0 else v)
+    return out
+
+
+def _device_styles(host: Sequence[int], device: torch.device) -> Tensor:
+    key = (tuple(host), device.index)
+    t = _STYLE_CACHE.get(key)
+    if t is None:
+        if len(_STYLE_CACHE) >= _STYLE_CACHE_MAX:
+            _STYLE_CACHE.clear()
+        t = torch.tensor(list(host), dtype=torch.int64, device=device)
+        _STYLE_CACHE[key] = t
+    return t
+
+
+class FastForwardMixin:
+    """forward() shared by the stand-alone and the MI-Seg-derived classes.  Relies on the host
+    class for `_check_input_dim`, `_check_input_styles`, `_get_no_batch_dim`, `norms`, `num_styles`."""
+
+    #: fused epilogue applied by forward(); set by blocks.fuse_* ("none" | "lrelu" | "add_lrelu")
+    fused_epilogue: str = "none"
+    fused_slope: float = 0.01
+
+    def _params(self) -> Tuple[List[Tensor], List[Tensor]]:
+        return [n.weight for n in self.norms], [n.bias for n in self.norms]
+
+    def forward(self, input: Tensor, styles: Union[List, Tensor, int], residual: Optional[Tensor] = None) -> Tensor:
+        self._check_input_dim(input)
+        self._check_input_styles(input, styles)
+        unbatched = input.dim() == self._get_no_batch_dim()
+        x = input.unsqueeze(0) if unbatched else input
+        host = _host_styles(styles, self.num_styles)
+        if x.shape[1] != self.norms[0].num_features:
+            # message of nn.InstanceNorm*d._check_input_dim via _get_no_batch_dim / num_features
+            raise ValueError(f"expected input's size at dim=1 to match num_features "
+                             f"({self.norms[0].num_features}), but got: {x.shape[1]}.")
+        m = 1
+        for s in x.shape[2:]:
+            m *= s
+        if m <= 1 and x.numel() > 0:
+            raise ValueError(f"Expected more than 1 spatial element when training, got input size {x.size()}")
+        if host is not None:
+            styles_dev = _device_styles(host, x.device)
+            present = [s in host for s in range(self.num_styles)]
+        else:
+            styles_dev = styles.reshape(-1).to(torch.int64)
+            present = None  # unknown without a device sync: absent styles get zero grads instead of None
+        w, b = self._params()
+        eps = self.norms[0].eps
+        y = instance_cond(x, styles_dev, w, b, eps=eps, epilogue=self.fused_epilogue if residual is None
+                          else "add_lrelu", residual=residual, slope=self.fused_slope, present=present)
+        return y.squeeze(0) if unbatched else y
+
+
+def _init_checks(track_running_stats: bool) -> None:
+    if track_running_stats:
+        raise NotImplementedError("track_running_stats=True is unreachable from MI-Seg's CLI "
+                                  "(parse_normalization never sets it) and is not supported")
+
+
+class _ConditionalInstanceNormBase(nn.Module):
+    """Local mirror of the reference `_ConditionalInstanceNorm` (:11-68): constructor arguments,
+    the `norms` ModuleList of affine nn.InstanceNorm*d (one per style) and the validation helpers."""
+
+    def __init__(self, num_styles: int, num_features: int, eps: float = 1e-5, momentum: float = 0.1,
+                 affine: bool = True, track_running_stats: bool = False, device=None, dtype=None) -> None:
+        super().__init__()
+        _init_checks(track_running_stats)
+        if not affine:
+            warnings.warn("Ignored affine=False for ConditionalInstanceNorm1D, set to True")
+        factory_kwargs = {"device": device, "dtype": dtype}
+        self.num_styles = num_styles
+        self.norms = nn.ModuleList([
+            self._get_norm()(num_features, eps, momentum, True, track_running_stats, **factory_kwargs)
+            for _ in range(num_styles)])
+
+    def _get_norm(self):
+        raise NotImplementedError
+
+    def _get_no_batch_dim(self):
+        raise NotImplementedError
+
+    def _check_input_dim(self, input):
+        raise NotImplementedError
+
+    def _check_input_styles(self, input, styles):
+        if input.dim() == self._get_no_batch_dim():
+            if not isinstance(styles, (int, list, Tensor)) or (isinstance(styles, Tensor) and torch.numel(styles) != 1) \
+                    or (isinstance(styles, list) and len(styles) != 1):
+                raise ValueError("Expected one style when input is not a batch.")
+        else:
+            if not isinstance(styles, (list, Tensor)) or len(styles) != len(input):
+                raise ValueError("Expected number of styles as batch size.")
+
+
+class _Base1d(_ConditionalInstanceNormBase):
+    def _get_norm(self):
+        return nn.InstanceNorm1d
+
+    def _get_no_batch_dim(self):
+        return 2
+
+    def _check_input_dim(self, input):
+        if input.dim() not in (2, 3):
+            raise ValueError("expected 2D or 3D input (got {}D input)".format(input.dim()))
+
+
+class _Base2d(_ConditionalInstanceNormBase):
+    def _get_norm(self):
+        return nn.InstanceNorm2d
+
+    def _get_no_batch_dim(self):
+        return 3
+
+    def _check_input_dim(self, input):
+        if input.dim() not in (3, 4):  # the reference's 2d message says "2D or 3D" too (:93)
+            raise ValueError("expected 2D or 3D input (got {}D input)".format(input.dim()))
+
+
+class _Base3d(_ConditionalInstanceNormBase):
+    def _get_norm(self):
+        return nn.InstanceNorm3d
+
+    def _get_no_batch_dim(self):
+        return 4
+
+    def _check_input_dim(self, input):
+        if input.dim() not in (4, 5):
+            raise ValueError("expected 4D or 5D input (got {}D input)".format(input.dim()))
+
+
+class FastConditionalInstanceNorm1d(FastForwardMixin, _Base1d):
+    pass
+
+
+class FastConditionalInstanceNorm2d(FastForwardMixin, _Base2d):
+    pass
+
+
+class FastConditionalInstanceNorm3d(FastForwardMixin, _Base3d):
+    pass
+
+
+def make_dropin_classes(ref_module):
+    """Build the three fast classes on top of MI-Seg's own classes (module
+    `networks.norms.conditional_instance_norm`) so `isinstance(m, _ConditionalInstanceNorm)` holds."""
+
+    def build(name, base):
+        def __init__(self, num_styles: int, num_features: int, eps: float = 1e-5, momentum: float = 0.1,
+                     affine: bool = True, track_running_stats: bool = False, device=None, dtype=None) -> None:
+            _init_checks(track_running_stats)
+            base.__init__(self, num_styles, num_features, eps, momentum, affine, track_running_stats, device, dtype)
+
+        return type(name, (FastForwardMixin, base), {"__init__": __init__, "__module__": __name__})
+
+    return (build("FastConditionalInstanceNorm1d", ref_module.ConditionalInstanceNorm1d),
+            build("FastConditionalInstanceNorm2d", ref_module.ConditionalInstanceNorm2d),
+            build("FastConditionalInstanceNorm3d", ref_module.ConditionalInstanceNorm3d))

@@ -1,0 +1,390 @@
+"""GPU parity tests proper (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+of libmicn.so (ctypes) - either via the drop-in nn.Module / autograd function or by raw pointers.
+
+Tolerances are BASELINE.json's: 1e-5 relative for fp32, 1e-2 for bf16/fp16, measured as
+max|a-b| / max|b| per tensor; parameter gradients (long fp32 sums) get 5x."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_golden, rel_err
+from oracle import micn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 1e-2, torch.float16: 1e-2}
+DT = {"float32": torch.float32, "bfloat16": torch.bfloat16, "float16": torch.float16}
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import mi_seg_b200
+    mi_seg_b200._lib.lib()  # fail loudly if the extension is missing
+    return mi_seg_b200
+
+
+def _module(pkg, dim, num_styles, gamma, beta, device="cuda"):
+    cls = {1: pkg.FastConditionalInstanceNorm1d, 2: pkg.FastConditionalInstanceNorm2d,
+           3: pkg.FastConditionalInstanceNorm3d}[dim]
+    mod = cls(num_styles=num_styles, num_features=gamma.shape[1]).to(device)
+    with torch.no_grad():
+        for s in range(num_styles):
+            mod.norms[s].weight.copy_(torch.from_numpy(gamma[s]))
+            mod.norms[s].bias.copy_(torch.from_numpy(beta[s]))
+    return mod
+
+
+def _styles_arg(g, device):
+    st, how = g["styles"], str(g["styles_as"])
+    if how == "list":
+        return [int(v) for v in st]
+    if how == "int":
+        return int(st[0])
+    t = torch.tensor(st, dtype=torch.int64, device=device)
+    return t.reshape(-1, 1) if how == "tensor_b1" else t
+
+
+def _grads(mod):
+    c = mod.norms[0].num_features
+    z = np.zeros(c, np.float32)
+    dg = np.stack([n.weight.grad.cpu().numpy() if n.weight.grad is not None else z for n in mod.norms])
+    db = np.stack([n.bias.grad.cpu().numpy() if n.bias.grad is not None else z for n in mod.norms])
+    present = [n.weight.grad is not None for n in mod.norms]
+    return dg, db, present
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("path", golden_files("norm"), ids=os.path.basename)
+@pytest.mark.parametrize("styles_on", ["as_recorded", "cuda_tensor"])
+def test_module_matches_reference_golden(pkg, path, styles_on):
+    g = load_golden(path)
+    dtype = DT[str(g["dtype"])]
+    tol = TOL[dtype]
+    if "bigmean" in path:
+        tol = 1e-4  # |mean|/std = 500 conditioning of the fp32 golden itself (see tests/test_oracle.py)
+    mod = _module(pkg, int(g["dim"]), int(g["num_styles"]), g["gamma"], g["beta"])
+    x = torch.from_numpy(g["x"]).to("cuda", dtype).requires_grad_(True)
+    dy = torch.from_numpy(g["dy"]).to("cuda", dtype)
+    styles = _styles_arg(g, "cuda")
+    if styles_on == "cuda_tensor":
+        if str(g["styles_as"]) == "int":
+            pytest.skip("unbatched int style has no tensor form to vary")
+        styles = torch.tensor(g["styles"], dtype=torch.int64, device="cuda")
+    y = mod(x, styles)
+    assert y.is_contiguous() and y.dtype == dtype and y.shape == x.shape
+    y.backward(dy)
+    assert rel_err(y.detach().float().cpu().numpy(), g["y"]) < tol
+    assert rel_err(x.grad.float().cpu().numpy(), g["dx"]) < tol
+    dg, db, present = _grads(mod)
+    assert rel_err(dg, g["dgamma"]) < 5 * tol
+    assert rel_err(db, g["dbeta"]) < 5 * tol
+    if styles_on == "as_recorded" and not isinstance(styles, torch.Tensor):
+        assert present == list(g["present"])  # absent styles keep .grad None, as in the reference
+
+
+@pytest.mark.parametrize("path", golden_files("block"), ids=os.path.basename)
+def test_fused_epilogues_match_reference_block_golden(pkg, path):
+    """lrelu(norm1(conv1_out)) and lrelu(norm2(conv2_out) + residual) against tensors recorded inside
+    the real UnetResBlock / UnetBasicBlock (dynunet_block.py:100-126, 187-203)."""
+    g = load_golden(path)
+    tol = 1e-5
+    st = torch.tensor(g["styles"], dtype=torch.int64, device="cuda")
+    S = int(g["num_styles"])
+
+    def params(nm):
+        w = [torch.from_numpy(g[f"{nm}_gamma"][s]).cuda().requires_grad_(True) for s in range(S)]
+        b = [torch.from_numpy(g[f"{nm}_beta"][s]).cuda().requires_grad_(True) for s in range(S)]
+        return w, b
+
+    a2 = torch.from_numpy(g["conv2_out"]).cuda().requires_grad_(True)
+    dout = torch.from_numpy(g["dout"]).cuda()
+    w2, b2 = params("norm2")
+    if str(g["kind"]) == "basic":
+        out = pkg.instance_cond(a2, st, w2, b2, epilogue="lrelu")
+        out.backward(dout)
+    else:
+        if "conv3_out" in g:
+            a3 = torch.from_numpy(g["conv3_out"]).cuda().requires_grad_(True)
+            w3, b3 = params("norm3")
+            res = pkg.instance_cond(a3, st, w3, b3)
+            assert rel_err(res.detach().cpu().numpy(), g["norm3_out"]) < tol
+        else:
+            res = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+        out = pkg.instance_cond(a2, st, w2, b2, epilogue="add_lrelu", residual=res)
+        out.backward(dout)
+        if "conv3_out" in g:
+            assert rel_err(a3.grad.cpu().numpy(), g["conv3_out_grad"]) < tol
+            assert rel_err(np.stack([w.grad.cpu().numpy() for w in w3]), g["norm3_dgamma"]) < 5 * tol
+            assert rel_err(np.stack([b.grad.cpu().numpy() for b in b3]), g["norm3_dbeta"]) < 5 * tol
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < tol
+    assert rel_err(a2.grad.cpu().numpy(), g["conv2_out_grad"]) < tol
+    assert rel_err(np.stack([w.grad.cpu().numpy() for w in w2]), g["norm2_dgamma"]) < 5 * tol
+    assert rel_err(np.stack([b.grad.cpu().numpy() for b in b2]), g["norm2_dbeta"]) < 5 * tol
+    # norm1 -> lrelu forward
+    w1, b1 = params("norm1")
+    o1 = pkg.instance_cond(torch.from_numpy(g["conv1_out"]).cuda(), st, w1, b1, epilogue="lrelu")
+    ref1, _, _, _ = O.fwd_epilogue_f64(g["conv1_out"], g["styles"], g["norm1_gamma"], g["norm1_beta"])
+    assert rel_err(o1.cpu().numpy(), ref1) < tol
+
+
+# ------------------------------------------------------------------------------------------------ seeded cases vs oracle
+def _case(pkg, shape, styles, num_styles, dtype, epilogue="none", seed=0, stride_pad=0, mean=1.0, std=2.0):
+    gen = torch.Generator().manual_seed(seed)
+    n, c = shape[0], shape[1]
+    gamma = (1 + 0.3 * torch.randn(num_styles, c, generator=gen)).numpy()
+    beta = (0.3 * torch.randn(num_styles, c, generator=gen)).numpy()
+    x32 = torch.randn(*shape, generator=gen) * std + mean
+    dy32 = torch.randn(*shape, generator=gen)
+    r32 = torch.randn(*shape, generator=gen) * 0.7
+    xq, dyq, rq = x32.to(dtype), dy32.to(dtype), r32.to(dtype)
+    if stride_pad:  # x as a channel-padded view: slabs dense, stride_c != M
+        big = torch.zeros((n, c + stride_pad) + tuple(shape[2:]), dtype=dtype, device="cuda")
+        big[:, :c] = xq.cuda()
+        x = big[:, :c].detach().requires_grad_(True)
+        assert not x.is_contiguous()
+    else:
+        x = xq.cuda().requires_grad_(True)
+    w = [torch.from_numpy(gamma[s]).cuda().requires_grad_(True) for s in range(num_styles)]
+    b = [torch.from_numpy(beta[s]).cuda().requires_grad_(True) for s in range(num_styles)]
+    st = torch.tensor(styles, dtype=torch.int64, device="cuda")
+    res = rq.cuda().requires_grad_(True) if epilogue == "add_lrelu" else None
+    y = pkg.instance_cond(x, st, w, b, epilogue=epilogue, residual=res)
+    y.backward(dyq.cuda())
+    torch.cuda.synchronize()
+    # oracle on the SAME (quantised) inputs
+    xn, dyn, rn = xq.float().numpy(), dyq.float().numpy(), rq.float().numpy()
+    if epilogue == "none":
+        yr, m_, r_ = O.fwd_f64(xn, styles, gamma, beta)
+        dxr, dgr, dbr, _ = O.bwd_f64(dyn, xn, styles, gamma, m_, r_)
+        drr = None
+    else:
+        yr, pre, m_, r_ = O.fwd_epilogue_f64(xn, styles, gamma, beta, residual=rn if epilogue == "add_lrelu" else None)
+        dxr, drr, dgr, dbr, _ = O.bwd_epilogue_f64(dyn, pre, xn, styles, gamma, m_, r_,
+                                                   has_residual=epilogue == "add_lrelu")
+    tol = TOL[dtype] * max(1.0, abs(mean) / std / 0.5)
+    assert rel_err(y.detach().float().cpu().numpy(), yr) < tol
+    assert rel_err(x.grad.float().cpu().numpy(), dxr) < tol
+    if drr is not None:
+        assert rel_err(res.grad.float().cpu().numpy(), drr) < tol
+    ptol = (5e-5 if dtype == torch.float32 else 5e-3) * max(1.0, abs(mean) / std / 0.5)
+    assert rel_err(np.stack([t.grad.cpu().numpy() for t in w]), dgr) < ptol
+    assert rel_err(np.stack([t.grad.cpu().numpy() for t in b]), dbr) < ptol
+
+
+SHAPES = [
+    ((3, 20, 3, 3, 3), "tiny_27"),            # encoder10-like 3^3 slabs (unaligned, warp per slab)
+    ((2, 12, 6, 6, 6), "6^3"),
+    ((2, 8, 12, 12, 12), "12^3"),
+    ((2, 6, 24, 24, 24), "24^3"),
+    ((2, 5, 48, 48, 48), "48^3"),             # one slab = 221 KB bf16: multi-piece path
+    ((1, 3, 96, 96, 96), "96^3"),             # north-star slab size
+    ((2, 3, 17, 19, 23), "odd_7429"),         # M not a multiple of the vector width
+    ((4, 7, 768), "1d_tokens"),               # ConditionalInstanceNorm1d-like [B, C, L]
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("shape,name", SHAPES, ids=[s[1] for s in SHAPES])
+def test_norm_vs_oracle(pkg, shape, name, dtype):
+    styles = [(i * 7 + 1) % 2 for i in range(shape[0])]
+    _case(pkg, shape, styles, 2, dtype, seed=sum(map(ord, name)) % 1000)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("epilogue", ["lrelu", "add_lrelu"])
+@pytest.mark.parametrize("shape", [(2, 6, 6, 6, 6), (2, 4, 24, 24, 24), (2, 3, 48, 48, 48)], ids=["6^3", "24^3", "48^3"])
+def test_epilogues_vs_oracle(pkg, shape, epilogue, dtype):
+    _case(pkg, shape, [1, 0], 2, dtype, epilogue=epilogue, seed=11)
+
+
+def test_strided_channel_view(pkg):
+    _case(pkg, (2, 5, 16, 16, 16), [0, 1], 2, torch.float32, stride_pad=3, seed=5)
+    _case(pkg, (2, 5, 48, 48, 48), [1, 1], 2, torch.bfloat16, stride_pad=2, seed=6)
+
+
+def test_three_styles_and_absent(pkg):
+    _case(pkg, (5, 4, 8, 8, 8), [2, 0, 2, 2, 0], 3, torch.float32, seed=7)
+
+
+def test_large_mean_small_std(pkg):
+    _case(pkg, (2, 3, 32, 32, 32), [0, 1], 2, torch.float32, mean=50.0, std=0.1, seed=8)
+
+
+def test_channels_last_input_gives_contiguous_output(pkg):
+    """PatchMerging / ViT feed channels-last strided views (patch_merging.py:136-141); the result must
+    equal the contiguous computation and come back as a dense NC* tensor."""
+    mod = pkg.FastConditionalInstanceNorm3d(2, 16).cuda()
+    xcl = torch.randn(2, 6, 6, 6, 16, device="cuda")
+    xv = xcl.permute(0, 4, 1, 2, 3)
+    y1 = mod(xv, [0, 1])
+    y2 = mod(xv.contiguous(), [0, 1])
+    assert y1.is_contiguous()
+    assert torch.equal(y1, y2)
+
+
+# ------------------------------------------------------------------------------------------------ behaviours
+def test_error_messages_match_reference(pkg):
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4).cuda()
+    x = torch.randn(2, 4, 4, 4, 4, device="cuda")
+    with pytest.raises(ValueError, match="Expected number of styles as batch size."):
+        mod(x, [0])
+    with pytest.raises(ValueError, match="Expected number of styles as batch size."):
+        mod(x, 1)
+    with pytest.raises(ValueError, match="Expected one style when input is not a batch."):
+        mod(x[0], [0, 1])
+    with pytest.raises(ValueError, match="expected 4D or 5D input"):
+        mod(x[0, 0], [0])
+    with pytest.raises(ValueError, match="to match num_features"):
+        mod(torch.randn(2, 3, 4, 4, 4, device="cuda"), [0, 1])
+    with pytest.raises(IndexError):
+        mod(x, [0, 2])
+    with pytest.raises(TypeError):
+        mod(x, torch.tensor([0.0, 1.0]))
+    with pytest.raises(ValueError, match="Expected more than 1 spatial element"):
+        mod(torch.randn(2, 4, 1, 1, 1, device="cuda"), [0, 1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.FastConditionalInstanceNorm3d(2, 4)(torch.randn(2, 4, 4, 4, 4), [0, 1])
+
+
+def test_unbatched_and_negative_styles(pkg):
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4).cuda()
+    with torch.no_grad():
+        mod.norms[1].weight.fill_(2.0)
+        mod.norms[1].bias.fill_(0.5)
+    x = torch.randn(4, 5, 5, 5, device="cuda")
+    for st in (1, [1], torch.tensor([1]), -1, torch.tensor(-1, device="cuda")):
+        y = mod(x, st)
+        ref, _, _ = O.fwd_f64(x[None].cpu().numpy(), [1], np.full((2, 4), 2.0), np.full((2, 4), 0.5))
+        assert y.shape == x.shape
+        assert rel_err(y.cpu().numpy(), ref[0]) < 1e-5
+
+
+def test_autocast_keeps_input_dtype(pkg):
+    """instance_norm is in neither autocast list: bf16 in -> bf16 out, fp32 in -> fp32 out."""
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4).cuda()
+    x = torch.randn(2, 4, 8, 8, 8, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert mod(x, [0, 1]).dtype == torch.float32
+        assert mod(x.bfloat16(), [0, 1]).dtype == torch.bfloat16
+
+
+def test_repeated_calls_are_bitwise_deterministic(pkg):
+    mod = pkg.FastConditionalInstanceNorm3d(2, 6).cuda()
+    x = torch.randn(2, 6, 48, 48, 48, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    dy = torch.randn_like(x)
+    outs = []
+    for _ in range(3):
+        x.grad = None
+        mod.zero_grad(set_to_none=True)
+        y = mod(x, [0, 1])
+        y.backward(dy)
+        outs.append((y.detach().clone(), x.grad.clone(), mod.norms[0].weight.grad.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(o, outs[0]))
+
+
+def test_raw_c_abi_call(pkg):
+    """micn_fwd / micn_bwd by raw pointers, as a non-Python host would call them (include/micn.h)."""
+    lib = pkg._lib.lib()
+    n, c, m, S = 2, 3, 4096, 2
+    x = torch.randn(n, c, m, device="cuda") * 2 + 1
+    dy = torch.randn(n, c, m, device="cuda")
+    gam = torch.rand(S, c, device="cuda") + 0.5
+    bet = torch.randn(S, c, device="cuda")
+    st = torch.tensor([1, 0], device="cuda")
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    mean, rstd = torch.empty(n * c, device="cuda"), torch.empty(n * c, device="cuda")
+    dg, db = torch.empty(S, c, device="cuda"), torch.empty(S, c, device="cuda")
+    wsb = lib.micn_workspace_bytes(n, c, S)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+    gp = (ctypes.c_void_p * S)(*[gam[s].data_ptr() for s in range(S)])
+    bp = (ctypes.c_void_p * S)(*[bet[s].data_ptr() for s in range(S)])
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.micn_fwd(x.data_ptr(), y.data_ptr(), None, gp, bp, S, st.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                      n, c, m, c * m, m, 0, 0, 0.01, 1e-5, ws.data_ptr(), wsb, stream)
+    assert rc == 0
+    rc = lib.micn_bwd(dy.data_ptr(), x.data_ptr(), None, gp, bp, S, st.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                      dx.data_ptr(), None, dg.data_ptr(), db.data_ptr(), n, c, m, c * m, m, 0, 0, 0.01,
+                      ws.data_ptr(), wsb, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    yr, m_, r_ = O.fwd_f64(x.cpu().numpy(), [1, 0], gam.cpu().numpy(), bet.cpu().numpy())
+    dxr, dgr, dbr, _ = O.bwd_f64(dy.cpu().numpy(), x.cpu().numpy(), [1, 0], gam.cpu().numpy(), m_, r_)
+    assert rel_err(y.cpu().numpy(), yr) < 1e-5 and rel_err(dx.cpu().numpy(), dxr) < 1e-5
+    assert rel_err(mean.cpu().numpy(), m_.reshape(-1)) < 1e-5 and rel_err(rstd.cpu().numpy(), r_.reshape(-1)) < 1e-5
+    assert rel_err(dg.cpu().numpy(), dgr) < 5e-5 and rel_err(db.cpu().numpy(), dbr) < 5e-5
+    # argument errors are reported, not raised
+    assert lib.micn_fwd(x.data_ptr(), y.data_ptr(), None, gp, bp, 17, st.data_ptr(), None, None, n, c, m, c * m, m,
+                        0, 0, 0.01, 1e-5, None, 0, stream) == -3
+    assert lib.micn_fwd(x.data_ptr(), y.data_ptr(), None, gp, bp, S, st.data_ptr(), None, None, n, c, m, c * m, m,
+                        9, 0, 0.01, 1e-5, None, 0, stream) == -2
+
+
+def test_out_of_range_device_style_is_flagged_not_fatal(pkg):
+    lib = pkg._lib.lib()
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4).cuda()
+    x = torch.randn(2, 4, 8, 8, 8, device="cuda")
+    y = mod(x, torch.tensor([0, 5], device="cuda"))  # CUDA tensor: cannot be validated without a sync
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    from importlib import import_module
+    f = import_module("mi-seg_b200.functional")
+    ws = next(iter(f._workspaces.values()))
+    status = ctypes.c_int(0)
+    assert lib.micn_read_status(ws.data_ptr(), torch.cuda.current_stream().cuda_stream, ctypes.byref(status)) == 0
+    assert status.value & 1
+
+
+# ------------------------------------------------------------------------------------------------ full size (properties)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_north_star_shape_properties_and_torch_reference(pkg, dtype):
+    """1x48x96^3 (BASELINE.json headline).  Size-independent properties of instance norm:
+      * per slab, y has mean beta and variance gamma^2 * var/(var+eps);
+      * per slab, sum(dx) = 0 and sum(dx * xhat) = 0 (dx is orthogonal to 1 and xhat);
+      * backward is linear in dy.
+    plus a torch fp32 reference (F.instance_norm on the same GPU) within BASELINE tolerance."""
+    torch.manual_seed(0)
+    n, c, s = 1, 48, 96
+    mod = pkg.FastConditionalInstanceNorm3d(2, c).cuda()
+    with torch.no_grad():
+        for k in range(2):
+            mod.norms[k].weight.copy_(1 + 0.3 * torch.randn(c))
+            mod.norms[k].bias.copy_(0.3 * torch.randn(c))
+    x = (torch.randn(n, c, s, s, s, device="cuda") * 2 + 1).to(dtype).requires_grad_(True)
+    dy = torch.randn(n, c, s, s, s, device="cuda").to(dtype)
+    y = mod(x, [1])
+    y.backward(dy)
+    gamma, beta = mod.norms[1].weight.detach(), mod.norms[1].bias.detach()
+    yf = y.detach().float().reshape(c, -1)
+    tol = 2e-3 if dtype == torch.bfloat16 else 2e-5
+    assert (yf.mean(1) - beta).abs().max().item() < tol * 5
+    assert (yf.var(1, unbiased=False).sqrt() - gamma.abs()).abs().max().item() < tol * 5
+    xf = x.detach().float().reshape(c, -1)
+    xhat = (xf - xf.mean(1, keepdim=True)) / (xf.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt()
+    dxf = x.grad.float().reshape(c, -1)
+    scale = dxf.abs().sum(1)
+    assert (dxf.sum(1).abs() / scale).max().item() < (2e-3 if dtype == torch.bfloat16 else 1e-5)
+    assert ((dxf * xhat).sum(1).abs() / scale).max().item() < (2e-3 if dtype == torch.bfloat16 else 1e-5)
+    # torch fp32 reference on the GPU
+    x32 = x.detach().float().requires_grad_(True)
+    g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.nn.functional.instance_norm(x32, None, None, g32, b32, True, 0.1, 1e-5)
+    yr.backward(dy.float())
+    t = TOL[dtype]
+    assert ((y.detach().float() - yr).abs().max() / yr.abs().max()).item() < t
+    assert ((x.grad.float() - x32.grad).abs().max() / x32.grad.abs().max()).item() < t
+    pt = 5e-5 if dtype == torch.float32 else 5e-3
+    assert ((mod.norms[1].weight.grad - g32.grad).abs().max() / g32.grad.abs().max()).item() < pt
+    assert ((mod.norms[1].bias.grad - b32.grad).abs().max() / b32.grad.abs().max()).item() < pt
+    assert mod.norms[0].weight.grad is None
+    # linearity of backward in dy
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = mod(x2, [1])
+    y2.backward((2 * dy.float()).to(dtype))
+    lin = (x2.grad.float() - 2 * x.grad.float()).abs().max() / x.grad.float().abs().max()
+    assert lin.item() < (1e-2 if dtype == torch.bfloat16 else 1e-6)

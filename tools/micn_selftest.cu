@@ -543,8 +543,8 @@ int main(int argc, char** argv) {
                 Case a = mk("cluster_cs2_48^3", 2, 5, 110592, dt, epi);
                 a.cs = 2;
                 cs.push_back(a);
-                Case b = mk("cluster_cs4_slots3_refetch", 2, 3, 110592, dt, epi);
-                b.cs = 4; b.slots = 3;
+                Case b = mk("cluster_cs4_slots5_refetch", 2, 3, 110592, dt, epi);
+                b.cs = 4; b.slots = 5;
                 cs.push_back(b);
                 Case e6 = mk("cluster_cs6_96^3", 1, 2, 884736, dt, epi);
                 e6.cs = 6;
