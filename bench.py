@@ -211,7 +211,7 @@ def run_ours(args):
     beta = 0.3 * torch.randn(S, c, device=dev)
     styles = (torch.arange(n, device=dev) % S).to(torch.int64)
     grads = torch.empty(2, S, c, device=dev)  # dgamma, dbeta: one bucket for the all-reduce
-    wsb = lib.micn_workspace_bytes(n, c, S)
+    wsb = lib.micn_workspace_bytes(n, c, m, code, S)
     ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
     gp = (ctypes.c_void_p * S)(*[gamma[k].data_ptr() for k in range(S)])
     bp = (ctypes.c_void_p * S)(*[beta[k].data_ptr() for k in range(S)])

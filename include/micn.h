@@ -65,15 +65,19 @@ enum {
 int micn_version(void);
 const char* micn_error_string(int code);
 
-/* Tuning / experiment knobs ("cluster_size", "force_path", "chunk_vecs", ...).  Returns 0 or
+/* Tuning / experiment knobs ("force_path" 0 small / 1 cluster / 2 flat, "flat_slots", "flat_lag",
+ * "flat_piece_vecs", "cluster_size", ...) and read-backs ("last_path", "launches").  Returns 0 or
  * MICN_ERR_BAD_ARG for an unknown key.  value < 0 restores the automatic choice. */
 int micn_set_option(const char* key, long long value);
 long long micn_get_option(const char* key);
 
-/* Bytes of device workspace micn_fwd/micn_bwd need for this problem.  The workspace must be
- * zero-filled ONCE when it is allocated; the kernels leave its control words zero again, so it
- * can be reused by every later call on the same stream. */
-size_t micn_workspace_bytes(int64_t N, int64_t C, int num_styles);
+/* Bytes of device workspace micn_fwd/micn_bwd need for this problem (cross-CTA exchange records of
+ * the flat path, per-slab sums).  The workspace must be zero-filled ONCE when it is allocated and can
+ * then be reused by every later call on the same stream: records are tagged with a per-launch epoch
+ * and the few control words are left zero again.  Two kernels running CONCURRENTLY (different
+ * streams) need different workspaces.  Without a workspace (or with one that is too small) the
+ * calls still work through the slower cluster / small paths. */
+size_t micn_workspace_bytes(int64_t N, int64_t C, int64_t M, int dtype, int num_styles);
 
 /* Host-blocking read (cudaMemcpy) of the sticky status word: bit 0 = a style index was out of
  * range.  Clears the word.  Debug aid; never called on the hot path. */

@@ -26,7 +26,7 @@ SYMBOLS = {
     "micn_error_string": (ctypes.c_char_p, [c_int]),
     "micn_set_option": (c_int, [ctypes.c_char_p, ctypes.c_longlong]),
     "micn_get_option": (ctypes.c_longlong, [ctypes.c_char_p]),
-    "micn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "micn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
     "micn_read_status": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
     "micn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_float,

@@ -1,9 +1,11 @@
 // micn_api.cu - the C ABI declared in include/micn.h: argument checks, path planning and launches.
 //
-// Two kernel families (micn_cluster.cuh, micn_small.cuh); the planner picks, per call,
-//   * small path  : slab bytes < 32 KB, or anything not 16-byte aligned -> warp / CTA per slab
-//   * cluster path: everything else -> cluster size CS in {1,2,4,8,16} from a bandwidth model
-//                   (HBM share per cluster, SMEM residency, waves over the co-resident clusters).
+// Three kernel families; the planner picks, per call,
+//   * flat path    (micn_flat.cuh, default): 16-byte aligned slabs >= flat_min_bytes -> every slab cut
+//                   into pieces dealt round-robin to one persistent CTA per SM, read-once/write-once
+//   * small path   (micn_small.cuh): tiny slabs, or anything not 16-byte aligned -> warp / CTA per slab
+//   * cluster path (micn_cluster.cuh): cluster-per-slab with DSMEM combine; kept selectable
+//                   (force_path = 1) and as the fallback for slabs too large for the flat ring.
 // Nothing here allocates or synchronises; the only state is per-process launch-attribute and
 // occupancy caches.
 #include <cuda_runtime.h>
@@ -17,6 +19,7 @@
 #include <vector>
 
 #include "micn_cluster.cuh"
+#include "micn_flat.cuh"
 #include "micn_small.cuh"
 
 using namespace micn;
@@ -26,7 +29,13 @@ namespace {
 // ------------------------------------------------------------------------------------------ options
 struct Options {
     std::atomic<long long> cluster_size{-1};  // force CS (1..16)
-    std::atomic<long long> force_path{-1};    // 0 small, 1 cluster
+    std::atomic<long long> force_path{-1};    // 0 small, 1 cluster, 2 flat
+    std::atomic<long long> flat_slots{-1};    // ring slots K of the flat path
+    std::atomic<long long> flat_lag{-1};      // rounds P2 trails P1
+    std::atomic<long long> flat_piece_vecs{-1};  // cap on vectors per piece
+    std::atomic<long long> flat_min_bytes{-1};   // smallest slab the flat path takes
+    std::atomic<long long> flat_grid{-1};     // cap on the persistent grid
+    std::atomic<long long> flat_ovh_vecs{-1}; // planner: per-piece overhead in vector-equivalents
     std::atomic<long long> slots{-1};         // force ring slots S
     std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
     std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
@@ -46,6 +55,8 @@ const OptName kOptNames[] = {
     {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps},   {"last_path", &g_opt.last_path},
     {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid},
     {"launches", &g_opt.launches},         {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
+    {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
+    {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
 };
 
 // ------------------------------------------------------------------------------------------ device
@@ -228,15 +239,186 @@ int launch_cluster(K kernel, const P& p, const Plan& pl, int NS, cudaStream_t st
     return (int)cudaLaunchKernelEx(&cfg, kernel, p, S);
 }
 
+
+// ------------------------------------------------------------------------------------------ flat path
+struct FlatWs {
+    uint4* piece;
+    uint4* slab;
+};
+std::atomic<unsigned> g_epoch{0};
+
+unsigned next_epoch() {
+    unsigned e = g_epoch.fetch_add(1u) + 1u;
+    if (e == 0u) e = g_epoch.fetch_add(1u) + 1u;  // 0 is what a zero-filled workspace holds
+    return e;
+}
+
+constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32)
+
+// upper bound of the pieces the flat planner can cut one slab into
+long long flat_max_pieces(long long slab_bytes) {
+    const long long V = slab_bytes / 16;
+    long long p = (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs;
+    if (p < 1) p = 1;
+    return p > kFlatMaxPieces ? kFlatMaxPieces : p;
+}
+
+struct WsLayout {
+    size_t sums_off, slab_off, piece_off, total;
+};
+WsLayout ws_layout(long long N, long long C, long long M, int es) {
+    WsLayout w;
+    const size_t slabs = (size_t)N * (size_t)C;
+    w.sums_off = kWsHeader;
+    w.slab_off = (w.sums_off + slabs * 2 * sizeof(float) + 15) & ~(size_t)15;
+    w.piece_off = w.slab_off + slabs * 16;
+    w.total = w.piece_off + slabs * (size_t)flat_max_pieces(M * es) * 16;
+    w.total = (w.total + 255) & ~(size_t)255;
+    return w;
+}
+
+struct FlatPlan {
+    FlatGeom g;
+    int grid, smem;
+};
+
+// occupancy of a flat kernel at its full shared-memory footprint (cached per kernel/device)
+template <typename K>
+int flat_blocks_per_sm(K kernel, int smem, int smem_optin) {
+    KernelState* ks = nullptr;
+    if (kernel_prepare(kernel, smem, smem_optin, &ks)) return 0;
+    if (ks->occ[0] >= 0) return ks->occ[0];
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFlatThreads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        nb = 0;
+    }
+    ks->occ[0] = nb;
+    return nb;
+}
+
+// returns 0 and fills *fp when the flat path can take the problem, 1 when it cannot, < 0 / > 0 codes on error
+template <typename KernelT>
+int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, const DeviceInfo& d, FlatPlan* fp) {
+    long long G = d.sm_count;
+    const long long gcap = g_opt.flat_grid.load();
+    if (gcap > 0 && gcap < G) G = gcap;
+    const long long V = slab_bytes / 16;
+    const long long ring = (long long)d.smem_optin - flat_ctl_bytes() - 128;
+    long long ovh = g_opt.flat_ovh_vecs.load();
+    if (ovh < 0) ovh = 256;
+
+    // (lag, slots) candidates, shallow-lag / deep-ring first; a forced pair replaces the list.  A slab of
+    // P pieces spans <= ceil((P-1)/G)+1 rounds and P2 trails P1 by L rounds, so P <= L*G is required.
+    struct Cand { long long lag, slots; };
+    Cand cands[4] = {{2, 6}, {2, 5}, {2, 4}, {3, 5}};
+    int ncand = 4;
+    const long long fK = g_opt.flat_slots.load(), fL = g_opt.flat_lag.load();
+    if (fK > 0 || fL > 0) {
+        long long L_ = fL > 0 ? fL : 2;
+        if (L_ > kFlatMaxLag) L_ = kFlatMaxLag;
+        long long K_ = fK > 0 ? fK : 6;
+        if (K_ < L_ + 2) K_ = L_ + 2;
+        if (K_ > kFlatMaxSlots) K_ = kFlatMaxSlots;
+        cands[0] = {L_, K_};
+        ncand = 1;
+    }
+    for (int ci = 0; ci < ncand; ++ci) {
+        const long long L_ = cands[ci].lag, K_ = cands[ci].slots;
+        const long long slot_vecs = (ring / (K_ * NS * 16)) & ~7LL;
+        if (slot_vecs < kFlatMinPieceVecs) continue;
+        long long pvmax = slot_vecs;
+        const long long cap = g_opt.flat_piece_vecs.load();
+        if (cap >= kFlatMinPieceVecs && cap < pvmax) pvmax = cap;
+        const long long pmax_hw = std::min<long long>(kFlatMaxPieces, L_ * G);
+        const long long P0 = (V + pvmax - 1) / pvmax;
+        if (P0 > pmax_hw) continue;  // slab too large for this ring geometry
+        const int smem = (int)(K_ * NS * slot_vecs * 16 + flat_ctl_bytes());
+        if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) continue;
+        const long long Pend =
+            std::min<long long>(pmax_hw, std::max<long long>(P0, (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs));
+        double best = 1e300;
+        long long bestP = 0, bestPV = 0;
+        for (long long P = P0; P <= Pend; ++P) {
+            const long long PV = (V + P - 1) / P;
+            const long long Pe = (V + PV - 1) / PV;
+            if (Pe != P) continue;  // same split as a smaller P: already scored
+            const long long T = slabs * Pe;
+            if (T > 0x7fffffffLL) break;
+            const long long rounds = (T + G - 1) / G;
+            const double cost = (double)rounds * (double)(PV + ovh);
+            if (cost < best * 0.9999) {
+                best = cost;
+                bestP = Pe;
+                bestPV = PV;
+            }
+        }
+        if (!bestP) continue;
+        fp->g.V = (unsigned long long)V;
+        fp->g.P = (unsigned)bestP;
+        fp->g.PV = (unsigned)bestPV;
+        fp->g.T = (unsigned)(slabs * bestP);
+        fp->g.K = (unsigned)K_;
+        fp->g.L = (unsigned)L_;
+        fp->g.slot_vecs = (unsigned)slot_vecs;
+        fp->g.epoch = next_epoch();
+        fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
+        fp->smem = smem;
+        return 0;
+    }
+    return 1;
+}
+
+template <typename K, typename P>
+int launch_flat(K kernel, const P& p, const FlatPlan& fp, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)fp.grid);
+    cfg.blockDim = dim3(kFlatThreads);
+    cfg.dynamicSmemBytes = fp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on each other's records
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FlatGeom g = fp.g;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, p, g);
+}
+
+void record_flat(const FlatPlan& fp) {
+    g_opt.last_path.store(2);
+    g_opt.last_cs.store(fp.g.P);
+    g_opt.last_slots.store(fp.g.K);
+    g_opt.last_grid.store(fp.grid);
+    g_opt.launches.fetch_add(1);
+}
+
+long long flat_min_bytes() {
+    const long long v = g_opt.flat_min_bytes.load();
+    return v >= 0 ? v : 32 * 1024;
+}
+
 // ------------------------------------------------------------------------------------------ typed dispatch
 template <typename T, int EPI>
-int fwd_typed(const FwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStream_t st) {
+int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const DeviceInfo& d, cudaStream_t st) {
     const long long slabs = p.N * p.C, slab_bytes = p.M * (long long)sizeof(T);
     Plan pl = {};
     const long long fp = g_opt.force_path.load();
     bool use_cluster = can_cluster && slab_bytes >= 32 * 1024;
     if (fp == 0) use_cluster = false;
     if (fp == 1 && can_cluster) use_cluster = true;
+    if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
+        auto kernel = micn_fwd_flat_kernel<T, EPI>;
+        FlatPlan fpl = {};
+        const int rc = plan_flat(kernel, 1, slabs, slab_bytes, d, &fpl);
+        if (rc == 0) {
+            fpl.g.ws_piece = ws_flat->piece;
+            fpl.g.ws_slab = ws_flat->slab;
+            record_flat(fpl);
+            return launch_flat(kernel, p, fpl, st);
+        }
+        if (rc != 1) return rc;
+    }
     if (use_cluster) {
         auto kernel = micn_fwd_cluster_kernel<T, EPI>;
         int rc = plan_cluster(kernel, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, slab_bytes, d, &pl);
@@ -264,7 +446,7 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStr
 }
 
 template <typename T, int EPI>
-int bwd_typed(const BwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStream_t st) {
+int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const DeviceInfo& d, cudaStream_t st) {
     const long long slabs = p.N * p.C, slab_bytes = p.M * (long long)sizeof(T);
     constexpr int NS = EPI == MICN_EPI_ADD_LRELU ? 3 : 2;
     Plan pl = {};
@@ -272,6 +454,18 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStr
     bool use_cluster = can_cluster && slab_bytes >= 32 * 1024;
     if (fp == 0) use_cluster = false;
     if (fp == 1 && can_cluster) use_cluster = true;
+    if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
+        auto kernel = micn_bwd_flat_kernel<T, EPI>;
+        FlatPlan fpl = {};
+        const int rc = plan_flat(kernel, NS, slabs, slab_bytes, d, &fpl);
+        if (rc == 0) {
+            fpl.g.ws_piece = ws_flat->piece;
+            fpl.g.ws_slab = ws_flat->slab;
+            record_flat(fpl);
+            return launch_flat(kernel, p, fpl, st);
+        }
+        if (rc != 1) return rc;
+    }
     if (use_cluster) {
         auto kernel = micn_bwd_cluster_kernel<T, EPI>;
         int rc = plan_cluster(kernel, NS, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, slab_bytes, d, &pl);
@@ -299,27 +493,25 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const DeviceInfo& d, cudaStr
 }
 
 template <typename T>
-int fwd_by_epi(int epi, const FwdParams& p, bool cc, const DeviceInfo& d, cudaStream_t st) {
+int fwd_by_epi(int epi, const FwdParams& p, bool cc, const FlatWs* wf, const DeviceInfo& d, cudaStream_t st) {
     switch (epi) {
-        case MICN_EPI_NONE: return fwd_typed<T, MICN_EPI_NONE>(p, cc, d, st);
-        case MICN_EPI_LRELU: return fwd_typed<T, MICN_EPI_LRELU>(p, cc, d, st);
-        case MICN_EPI_ADD_LRELU: return fwd_typed<T, MICN_EPI_ADD_LRELU>(p, cc, d, st);
+        case MICN_EPI_NONE: return fwd_typed<T, MICN_EPI_NONE>(p, cc, wf, d, st);
+        case MICN_EPI_LRELU: return fwd_typed<T, MICN_EPI_LRELU>(p, cc, wf, d, st);
+        case MICN_EPI_ADD_LRELU: return fwd_typed<T, MICN_EPI_ADD_LRELU>(p, cc, wf, d, st);
     }
     return MICN_ERR_BAD_ARG;
 }
 template <typename T>
-int bwd_by_epi(int epi, const BwdParams& p, bool cc, const DeviceInfo& d, cudaStream_t st) {
+int bwd_by_epi(int epi, const BwdParams& p, bool cc, const FlatWs* wf, const DeviceInfo& d, cudaStream_t st) {
     switch (epi) {
-        case MICN_EPI_NONE: return bwd_typed<T, MICN_EPI_NONE>(p, cc, d, st);
-        case MICN_EPI_LRELU: return bwd_typed<T, MICN_EPI_LRELU>(p, cc, d, st);
-        case MICN_EPI_ADD_LRELU: return bwd_typed<T, MICN_EPI_ADD_LRELU>(p, cc, d, st);
+        case MICN_EPI_NONE: return bwd_typed<T, MICN_EPI_NONE>(p, cc, wf, d, st);
+        case MICN_EPI_LRELU: return bwd_typed<T, MICN_EPI_LRELU>(p, cc, wf, d, st);
+        case MICN_EPI_ADD_LRELU: return bwd_typed<T, MICN_EPI_ADD_LRELU>(p, cc, wf, d, st);
     }
     return MICN_ERR_BAD_ARG;
 }
 
 int elem_size(int dtype) { return dtype == MICN_F32 ? 4 : (dtype == MICN_BF16 || dtype == MICN_F16) ? 2 : 0; }
-
-constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32)
 
 }  // namespace
 
@@ -361,11 +553,11 @@ long long micn_get_option(const char* key) {
     return -1;
 }
 
-size_t micn_workspace_bytes(int64_t N, int64_t C, int num_styles) {
+size_t micn_workspace_bytes(int64_t N, int64_t C, int64_t M, int dtype, int num_styles) {
     (void)num_styles;
-    if (N < 0 || C < 0) return 0;
-    size_t b = kWsHeader + (size_t)N * (size_t)C * 2 * sizeof(float);
-    return (b + 255) & ~(size_t)255;
+    const int es = elem_size(dtype);
+    if (N < 0 || C < 0 || M < 0 || !es) return 0;
+    return ws_layout(N, C, M, es).total;
 }
 
 int micn_read_status(void* workspace, void* stream, int* status_out) {
@@ -429,10 +621,18 @@ int micn_fwd(const void* x, void* y, const void* residual, const float* const* g
     const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(y) && (!p.res || aligned16(p.res)) &&
                              ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    FlatWs wf = {nullptr, nullptr};
+    const WsLayout wl = ws_layout(N, C, M, es);
+    const bool have_flat_ws = workspace && workspace_bytes >= wl.total;
+    if (have_flat_ws) {
+        wf.slab = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.slab_off);
+        wf.piece = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.piece_off);
+    }
+    const FlatWs* wfp = have_flat_ws ? &wf : nullptr;
     switch (dtype) {
-        case MICN_F32: return fwd_by_epi<float>(epilogue, p, can_cluster, *d, st);
-        case MICN_BF16: return fwd_by_epi<__nv_bfloat16>(epilogue, p, can_cluster, *d, st);
-        case MICN_F16: return fwd_by_epi<__half>(epilogue, p, can_cluster, *d, st);
+        case MICN_F32: return fwd_by_epi<float>(epilogue, p, can_cluster, wfp, *d, st);
+        case MICN_BF16: return fwd_by_epi<__nv_bfloat16>(epilogue, p, can_cluster, wfp, *d, st);
+        case MICN_F16: return fwd_by_epi<__half>(epilogue, p, can_cluster, wfp, *d, st);
     }
     return MICN_ERR_BAD_DTYPE;
 }
@@ -465,7 +665,7 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
          reinterpret_cast<uintptr_t>(act_out) | reinterpret_cast<uintptr_t>(dresidual)) &
         (es - 1))
         return MICN_ERR_UNALIGNED;
-    if (dgamma && (!workspace || workspace_bytes < micn_workspace_bytes(N, C, num_styles))) return MICN_ERR_WORKSPACE;
+    if (dgamma && (!workspace || workspace_bytes < kWsHeader + (size_t)N * (size_t)C * 2 * sizeof(float))) return MICN_ERR_WORKSPACE;
 
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
@@ -509,10 +709,18 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
                              (!p.act_out || aligned16(p.act_out)) && (!p.dres || aligned16(p.dres)) &&
                              ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    FlatWs wf = {nullptr, nullptr};
+    const WsLayout wl = ws_layout(N, C, M, es);
+    const bool have_flat_ws = workspace && workspace_bytes >= wl.total;
+    if (have_flat_ws) {
+        wf.slab = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.slab_off);
+        wf.piece = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.piece_off);
+    }
+    const FlatWs* wfp = have_flat_ws ? &wf : nullptr;
     switch (dtype) {
-        case MICN_F32: return bwd_by_epi<float>(epilogue, p, can_cluster, *d, st);
-        case MICN_BF16: return bwd_by_epi<__nv_bfloat16>(epilogue, p, can_cluster, *d, st);
-        case MICN_F16: return bwd_by_epi<__half>(epilogue, p, can_cluster, *d, st);
+        case MICN_F32: return bwd_by_epi<float>(epilogue, p, can_cluster, wfp, *d, st);
+        case MICN_BF16: return bwd_by_epi<__nv_bfloat16>(epilogue, p, can_cluster, wfp, *d, st);
+        case MICN_F16: return bwd_by_epi<__half>(epilogue, p, can_cluster, wfp, *d, st);
     }
     return MICN_ERR_BAD_DTYPE;
 }
@@ -541,7 +749,7 @@ size_t micn_host_scratch_bytes(int64_t N, int64_t C, int64_t M, int dtype, int n
     b += up256((size_t)N * C * 4) * 2;                              // mean, rstd
     b += up256((size_t)num_styles * C * 4) * 4;                     // gamma, beta, dgamma, dbeta
     b += up256((size_t)N * 8);                                      // styles
-    b += (size_t)G * micn_workspace_bytes(N, (C + G - 1) / G + 1, num_styles);
+    b += (size_t)G * micn_workspace_bytes(N, (C + G - 1) / G + 1, M, dtype, num_styles);
     return b + 4096;
 }
 
@@ -587,7 +795,7 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
     int64_t* sd = reinterpret_cast<int64_t*>(take((size_t)N * 8));
     const int G = host_groups(C);
     const int64_t cg = (C + G - 1) / G;
-    const size_t ws_each = micn_workspace_bytes(N, cg + 1, num_styles);
+    const size_t ws_each = micn_workspace_bytes(N, cg + 1, M, dtype, num_styles);
     unsigned char* ws0 = take((size_t)G * ws_each);
 
     // small parameters first (stream 0), everyone else waits on them through an event

@@ -11,11 +11,7 @@
 //   16 consumer warps                work unit = a 2 KB quarter of a chunk (4 warp-wide 128-bit
 //                                    rounds), dealt round-robin to the warps, so a warp pays one
 //                                    barrier wait / release per 4 vectors.
-//        pass 1  statistics.  fp32 slabs: per-thread shifted sums.  bf16/fp16 slabs: the thread's
-//                16-byte vector IS an mma.m16n8k16 A-fragment, and sums are invariant under
-//                permutation of the elements, so three tensor-core MMAs per vector give
-//                sum(d) [A x ones] and sum(d^2) [diagonals of A x A^T] in fp32 with d = x - K taken
-//                by one packed subtract (exact whenever |mean| >> std, i.e. when the shift matters).
+//        pass 1  statistics: per-thread shifted sums in fp32 for every element type.
 //                Partials: warp shuffle -> CTA -> pushed into every peer CTA's shared memory
 //                (st.shared::cluster + remote mbarrier arrive), merged in rank order with Chan's
 //                formula (bit-identical in every CTA, no atomics).
@@ -246,40 +242,7 @@ __device__ __forceinline__ float mma_rowsum(const float (&ds)[4]) {
 // forward statistics accumulators (one per warp; finish() returns the warp's Stat in every lane)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-struct FwdStats {  // 16-bit element types: tensor-core sums of d = x - K (K = the warp's first element)
-    using H = Half2Ops<T>;
-    uint32_t K2;
-    bool have;
-    float ds[4], d1[4], d2[4], n;
-    __device__ __forceinline__ void init() {
-        K2 = 0u;
-        have = false;
-        n = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ds[i] = d1[i] = d2[i] = 0.f;
-    }
-    // all 32 lanes call; `ok` false -> the lane contributes nothing
-    __device__ __forceinline__ void add(uint4 v, bool ok) {
-        if (!have) {  // warp-uniform: first vector of the warp's first non-empty unit (lane 0 is valid)
-            const uint32_t w = __shfl_sync(0xffffffffu, v.x, 0) & 0xffffu;
-            K2 = w | (w << 16);
-            have = true;
-        }
-        if (!ok) v = make_uint4(K2, K2, K2, K2);
-        const uint32_t a0 = H::sub2(v.x, K2), a1 = H::sub2(v.y, K2), a2 = H::sub2(v.z, K2), a3 = H::sub2(v.w, K2);
-        H::mma(ds, a0, a1, a2, a3, H::kOnes, H::kOnes);
-        H::mma(d1, a0, a1, a2, a3, a0, a2);
-        H::mma(d2, a0, a1, a2, a3, a1, a3);
-        n += ok ? (float)VecT<T>::N : 0.f;
-    }
-    __device__ __forceinline__ Stat finish() {
-        const float sd = warp_sum(mma_rowsum(ds)), sq = warp_sum(mma_diag(d1, d2)), cnt = warp_sum(n);
-        return stat_from_shifted(H::low_to_float(K2), sd, sq, cnt);
-    }
-};
-
-template <>
-struct FwdStats<float> {  // fp32 slabs: per-thread shifted sums, Chan-merged across the warp
+struct FwdStats {  // per-thread shifted sums in fp32 (any element type), Chan-merged across the warp
     float K, s1a, s1b, s2a, s2b, n;
     bool have;
     __device__ __forceinline__ void init() {
@@ -288,20 +251,22 @@ struct FwdStats<float> {  // fp32 slabs: per-thread shifted sums, Chan-merged ac
     }
     __device__ __forceinline__ void add(uint4 v, bool ok) {
         if (!ok) return;
-        float f[4];
-        VecT<float>::unpack(v, f);
+        constexpr int VN = VecT<T>::N;
+        float f[VN];
+        VecT<T>::unpack(v, f);
         if (!have) {
             K = f[0];
             have = true;
         }
-        const float d0 = f[0] - K, d1 = f[1] - K, d2 = f[2] - K, d3 = f[3] - K;
-        s1a += d0 + d2;
-        s1b += d1 + d3;
-        s2a = fmaf(d0, d0, s2a);
-        s2b = fmaf(d1, d1, s2b);
-        s2a = fmaf(d2, d2, s2a);
-        s2b = fmaf(d3, d3, s2b);
-        n += 4.f;
+#pragma unroll
+        for (int e = 0; e < VN; e += 2) {
+            const float d0 = f[e] - K, d1 = f[e + 1] - K;
+            s1a += d0;
+            s1b += d1;
+            s2a = fmaf(d0, d0, s2a);
+            s2b = fmaf(d1, d1, s2b);
+        }
+        n += (float)VN;
     }
     __device__ __forceinline__ Stat finish() { return stat_warp_reduce(stat_from_shifted(K, s1a + s1b, s2a + s2b, n)); }
 };
@@ -526,31 +491,28 @@ __device__ __forceinline__ uint32_t bwd_mask2(const BwdSlab& s, uint32_t x2, uin
 }
 
 template <typename T, int EPI>
-struct BwdSums {  // 16-bit: tensor-core sum(g) and sum(g*d), d = x - K
-    using H = Half2Ops<T>;
-    float ds[4], d1[4], d2[4];
-    __device__ __forceinline__ void init() {
+struct BwdSums {  // 16-bit: the packed masked gradient (same mask as pass 2), sums in fp32
+    float s1a, s1b, s2a, s2b;
+    __device__ __forceinline__ void init() { s1a = s1b = s2a = s2b = 0.f; }
+    __device__ __forceinline__ void add(const BwdSlab& s, const uint4& x, const uint4& dy, const uint4& o, bool ok) {
+        if (!ok) return;
+        const uint4 gq = make_uint4(bwd_mask2<T, EPI>(s, x.x, dy.x, o.x), bwd_mask2<T, EPI>(s, x.y, dy.y, o.y),
+                                    bwd_mask2<T, EPI>(s, x.z, dy.z, o.z), bwd_mask2<T, EPI>(s, x.w, dy.w, o.w));
+        float xf[8], gf[8];
+        VecT<T>::unpack(x, xf);
+        VecT<T>::unpack(gq, gf);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ds[i] = d1[i] = d2[i] = 0.f;
-    }
-    __device__ __forceinline__ void add(const BwdSlab& s, uint4 x, uint4 dy, uint4 o, bool ok) {
-        if (!ok) {
-            x = make_uint4(s.K2, s.K2, s.K2, s.K2);
-            dy = make_uint4(0u, 0u, 0u, 0u);
-            o = dy;
+        for (int e = 0; e < 8; e += 2) {
+            s1a += gf[e];
+            s1b += gf[e + 1];
+            s2a = fmaf(gf[e], xf[e] - s.mean, s2a);
+            s2b = fmaf(gf[e + 1], xf[e + 1] - s.mean, s2b);
         }
-        const uint32_t g0 = bwd_mask2<T, EPI>(s, x.x, dy.x, o.x), g1 = bwd_mask2<T, EPI>(s, x.y, dy.y, o.y),
-                       g2 = bwd_mask2<T, EPI>(s, x.z, dy.z, o.z), g3 = bwd_mask2<T, EPI>(s, x.w, dy.w, o.w);
-        const uint32_t a0 = H::sub2(x.x, s.K2), a1 = H::sub2(x.y, s.K2), a2 = H::sub2(x.z, s.K2), a3 = H::sub2(x.w, s.K2);
-        H::mma(ds, g0, g1, g2, g3, H::kOnes, H::kOnes);
-        H::mma(d1, a0, a1, a2, a3, g0, g2);
-        H::mma(d2, a0, a1, a2, a3, g1, g3);
     }
     // warp totals (every lane): s1 = sum g, s2 = sum g * (x - mean)   [not yet scaled by rstd]
-    __device__ __forceinline__ void finish(const BwdSlab& s, float& s1, float& s2) {
-        s1 = warp_sum(mma_rowsum(ds));
-        const float sgd = warp_sum(mma_diag(d1, d2));
-        s2 = fmaf(-(s.mean - s.Kf), s1, sgd);
+    __device__ __forceinline__ void finish(const BwdSlab&, float& s1, float& s2) {
+        s1 = warp_sum(s1a + s1b);
+        s2 = warp_sum(s2a + s2b);
     }
 };
 

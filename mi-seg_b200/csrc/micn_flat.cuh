@@ -1,0 +1,563 @@
+// micn_flat.cuh - flat-partition instance_cond forward / backward (sm_100a): the default large-slab path.
+//
+// Why: the copy roofline of a B200 is set by the L2<->SM fabric as much as by HBM, so a voxel must
+// cross it exactly once per tensor, and every one of the 148 SMs has to carry an equal share.  Binding
+// whole slabs to clusters cannot do both (48 slabs of 1.7 MB on 148 SMs: either the slab does not fit
+// the cluster's shared memory and is re-fetched from L2, or most SMs idle in the last wave).
+//
+// How: every (n, c) slab is cut into P pieces of <= PV 16-byte vectors; piece g = slab*P + k belongs
+// to CTA g % G at its local round g / G (G = one persistent CTA per SM, launched cooperatively so all
+// are co-resident).  Inside a CTA three roles run decoupled over a ring of K shared-memory slots:
+//
+//   producer warp (1 lane)  1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the next
+//                           piece into a free slot, L2 evict_first (each voxel is read once).
+//   16 consumer warps       P1(j): statistics of piece j out of shared memory (fp32 shifted sums,
+//                           warp shuffle) -> per-warp partials.  P2(j-L): normalise / epilogue /
+//                           backward formula out of the SAME shared-memory copy, 128-bit streaming
+//                           stores, then the slot goes back to the producer.  P2 trails P1 by L rounds.
+//   stats warp              publish(j): merges the 16 warp partials (Chan) and writes the piece record
+//                           to the workspace; gather(j-L): polls the P records of the piece's slab,
+//                           merges them in a fixed order (bit-identical in every CTA, no atomics),
+//                           turns them into the per-slab coefficients for P2; backward: also emits
+//                           the per-slab sums and, for the last sample of a channel, d(gamma)/d(beta)
+//                           per style in a fixed order.
+//
+// Cross-CTA exchange is by 16-byte self-validating records {a, tag, b, tag} (tag = per-launch epoch):
+// no counters to reset, an aborted launch cannot poison the next one.  The planner keeps P <= L * G, so
+// a slab spans at most L + 1 consecutive rounds and P2(j - L) only needs records from rounds <= j,
+// which every CTA publishes before it can block on anything newer: no cycle, and with P <= G (the
+// common case) nobody waits in steady state.  Every wait is bounded and traps instead of hanging.
+//
+// HBM / L2 traffic: forward reads x once, writes y once (2*E*s); backward reads x, dy [, act_out]
+// once and writes dx [, dresidual] once (3*E*s / 5*E*s) - the algorithmic minimum.
+//
+// Reference semantics: networks/norms/conditional_instance_norm.py:59-60 (+ ATen instance_norm:
+// biased variance, eps inside the sqrt), epilogues networks/blocks/dynunet_block.py:107-125.
+#pragma once
+
+#include "micn_common.cuh"
+
+namespace micn {
+
+constexpr int kFlatConsumerWarps = 16;
+constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512
+constexpr int kFlatThreads = kFlatConsumerThreads + 64;        // + producer warp + stats warp
+constexpr int kFlatMaxSlots = 16;
+constexpr int kFlatMaxLag = 3;
+constexpr int kFlatMaxPieces = 512;  // pieces per slab; the planner keeps P <= L * G (a slab spans <= L + 1 rounds)
+constexpr int kFlatMinPieceVecs = 128;
+constexpr uint32_t kFlatTmaChunk = 32768;
+
+struct FlatGeom {
+    unsigned long long V;  // 16-byte vectors per slab
+    unsigned T;            // total pieces = num_slabs * P
+    unsigned P;            // pieces per slab
+    unsigned PV;           // vectors per piece (the last piece of a slab may be shorter)
+    unsigned K;            // ring slots
+    unsigned L;            // rounds P2 trails P1
+    unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
+    unsigned epoch;        // per-launch tag of the workspace records (never 0)
+    uint4* ws_piece;       // [T] piece records
+    uint4* ws_slab;        // [num_slabs] per-slab records (backward parameter gradients)
+};
+
+__host__ __device__ constexpr int flat_ctl_bytes() {
+    return kFlatMaxSlots * 16 /*full+empty*/ + (kFlatMaxLag + 1) * 16 /*p1done+coef*/ +
+           (kFlatMaxLag + 1) * kFlatConsumerWarps * 16 /*warp partials*/ + (kFlatMaxLag + 1) * 32 /*coefficients*/ +
+           kFlatMaxSlots * 16 /*per-slot slab constants*/;
+}
+
+struct FlatCtx {
+    uint32_t data0, full0, empty0, p1d0, coef0;  // shared::cta addresses
+    float* warp_part;                            // [NB][16][4]
+    float* coefv;                                // [NB][8]
+    float* prec;                                 // [K][4]
+    uint32_t stream_bytes, slot_bytes;
+};
+
+template <int NS>
+__device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeom& g) {
+    FlatCtx c;
+    c.stream_bytes = g.slot_vecs * 16u;
+    c.slot_bytes = c.stream_bytes * NS;
+    c.data0 = smem_u32(smem);
+    unsigned char* ctl = smem + (size_t)g.K * c.slot_bytes;
+    c.full0 = smem_u32(ctl);
+    c.empty0 = c.full0 + kFlatMaxSlots * 8;
+    c.p1d0 = c.empty0 + kFlatMaxSlots * 8;
+    c.coef0 = c.p1d0 + (kFlatMaxLag + 1) * 8;
+    c.warp_part = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 16 + (kFlatMaxLag + 1) * 16);
+    c.coefv = c.warp_part + (kFlatMaxLag + 1) * kFlatConsumerWarps * 4;
+    c.prec = c.coefv + (kFlatMaxLag + 1) * 8;
+    if (threadIdx.x == 0) {
+        for (unsigned i = 0; i < g.K; ++i) {
+            mbar_init(c.full0 + 8 * i, 1);
+            mbar_init(c.empty0 + 8 * i, kFlatConsumerWarps);
+        }
+        for (unsigned i = 0; i <= g.L; ++i) {
+            mbar_init(c.p1d0 + 8 * i, kFlatConsumerWarps);
+            mbar_init(c.coef0 + 8 * i, 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    return c;
+}
+
+struct PieceId {
+    unsigned slab, k, pv;  // slab index, piece index inside the slab, vectors in this piece
+};
+__device__ __forceinline__ unsigned piece_vecs(const FlatGeom& g, unsigned k) {
+    const unsigned long long left = g.V - (unsigned long long)k * g.PV;
+    return left < g.PV ? (unsigned)left : g.PV;
+}
+__device__ __forceinline__ PieceId piece_of(const FlatGeom& g, unsigned gidx) {
+    PieceId p;
+    p.slab = gidx / g.P;
+    p.k = gidx - p.slab * g.P;
+    p.pv = piece_vecs(g, p.k);
+    return p;
+}
+
+// ring cursor with phase parity
+struct Ring {
+    unsigned i, ph;
+    __device__ __forceinline__ void next(unsigned n) {
+        if (++i == n) {
+            i = 0;
+            ph ^= 1u;
+        }
+    }
+};
+
+// ---- self-validating workspace records {a, tag, b, tag}: each 8-byte half carries its own tag, so a
+//      torn 16-byte access can never be mistaken for a complete record
+__device__ __forceinline__ void ll_store(uint4* p, float a, float b, unsigned tag) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag),
+                 "r"(__float_as_uint(b)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_try(const uint4* p, unsigned tag, float& a, float& b) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    a = __uint_as_float(v.x);
+    b = __uint_as_float(v.z);
+    return v.y == tag && v.w == tag;
+}
+__device__ __forceinline__ void ll_wait(const uint4* p, unsigned tag, float& a, float& b) {
+    if (ll_try(p, tag, a, b)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!ll_try(p, tag, a, b)) {
+        __nanosleep(64);
+        if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+    }
+}
+
+// vectors of piece (pv vectors, strided over 512 consumer threads) that land in consumer warp w
+__device__ __forceinline__ unsigned warp_vecs(unsigned pv, unsigned w) {
+    const unsigned full = pv / kFlatConsumerThreads, rem = pv % kFlatConsumerThreads;
+    int r = (int)rem - 32 * (int)w;
+    r = r < 0 ? 0 : (r > 32 ? 32 : r);
+    return 32u * full + (unsigned)r;
+}
+
+template <typename T>
+__device__ __forceinline__ float first_elem(uint32_t smem_addr) {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(smem_addr));
+    if (sizeof(T) == 4) return __uint_as_float(w);
+    if (sizeof(T) == 2) {
+        float f[8];
+        VecT<T>::unpack(make_uint4(w, 0u, 0u, 0u), f);
+        return f[0];
+    }
+    return 0.f;
+}
+
+// producer: one bulk copy per <= 32 KB chunk of each stream of the piece, all on the slot's barrier
+__device__ __forceinline__ void flat_issue(uint32_t dst, const char* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    for (uint32_t off = 0; off < bytes; off += kFlatTmaChunk) {
+        const uint32_t n = bytes - off < kFlatTmaChunk ? bytes - off : kFlatTmaChunk;
+        tma_load_1d(dst + off, src + off, n, bar, pol);
+    }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <typename T, int EPI>
+__global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const FwdParams p, const FlatGeom g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int VN = VecT<T>::N;
+    const FlatCtx c = flat_setup<1>(smem, g);
+    const unsigned cta = blockIdx.x, G = gridDim.x;
+    const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
+    const unsigned NB = g.L + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned C = (unsigned)p.C;
+
+    if (warp == kFlatConsumerWarps) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            Ring r{0u, 0u};
+            for (unsigned j = 0; j < nj; ++j) {
+                if (j >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
+                const PieceId pc = piece_of(g, j * G + cta);
+                const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+                const char* src = reinterpret_cast<const char*>(p.x) +
+                                  ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) +
+                                  (size_t)pc.k * g.PV * 16;
+                const uint32_t bytes = pc.pv * 16u, bar = c.full0 + 8 * r.i;
+                flat_issue(c.data0 + r.i * c.slot_bytes, src, bytes, bar, pol);
+                mbar_arrive_expect_tx(bar, bytes);
+                r.next(g.K);
+            }
+        }
+    } else if (warp == kFlatConsumerWarps + 1) {
+        // ------------------------------------------------------------------ stats warp
+        Ring b1{0u, 0u}, b2{0u, 0u};
+        for (unsigned step = 0; step < nj + g.L; ++step) {
+            if (step < nj) {  // publish(step)
+                const unsigned gidx = step * G + cta;
+                const PieceId pc = piece_of(g, gidx);
+                mbar_wait(c.p1d0 + 8 * b1.i, b1.ph);
+                Stat st{0.f, 0.f, 0.f};
+                if (lane < kFlatConsumerWarps) {
+                    const float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + lane) * 4;
+                    st = stat_from_shifted(wp[2], wp[0], wp[1], (float)(warp_vecs(pc.pv, lane) * VN));
+                }
+                st = stat_warp_reduce(st);
+                if (lane == 0) ll_store(g.ws_piece + gidx, st.mean, st.m2, g.epoch);
+                b1.next(NB);
+            }
+            if (step >= g.L) {  // gather(step - L)
+                const PieceId pc = piece_of(g, (step - g.L) * G + cta);
+                const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+                // parameters first: their latency hides behind the polls
+                const int style = load_style(p.styles, n, p.num_styles, p.status);
+                float gamma, beta;
+                load_affine(p, style, ch, gamma, beta);
+                Stat acc{0.f, 0.f, 0.f};
+                const uint4* recs = g.ws_piece + (size_t)pc.slab * g.P;
+                for (unsigned q = lane; q < g.P; q += 32) {
+                    float a, b;
+                    ll_wait(recs + q, g.epoch, a, b);
+                    acc = stat_merge(acc, Stat{(float)(piece_vecs(g, q) * VN), a, b});
+                }
+                acc = stat_warp_reduce(acc);
+                const float mean = acc.mean;
+                const float rstd = 1.f / sqrtf(acc.m2 / (float)p.M + p.eps);  // biased variance, eps inside the sqrt
+                if (lane == 0) {
+                    const float a = rstd * gamma;
+                    float* cf = c.coefv + b2.i * 8;
+                    // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element
+                    cf[0] = sizeof(T) == 4 ? mean : 0.f;
+                    cf[1] = a;
+                    cf[2] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
+                    if (pc.k == 0 && p.save_mean) {
+                        p.save_mean[pc.slab] = mean;
+                        p.save_rstd[pc.slab] = rstd;
+                    }
+                    mbar_arrive(c.coef0 + 8 * b2.i);
+                }
+                __syncwarp();
+                b2.next(NB);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        Ring s1r{0u, 0u}, b1{0u, 0u}, s2r{0u, 0u}, b2{0u, 0u};
+        for (unsigned step = 0; step < nj + g.L; ++step) {
+            if (step < nj) {  // P1(step): statistics
+                const PieceId pc = piece_of(g, step * G + cta);
+                mbar_wait(c.full0 + 8 * s1r.i, s1r.ph);
+                const uint32_t base = c.data0 + s1r.i * c.slot_bytes;
+                float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, Kw = 0.f;
+                if ((unsigned)warp * 32u < pc.pv) {
+                    Kw = first_elem<T>(base + warp * 512);  // shift = the warp's first element of the piece
+#pragma unroll 2
+                    for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
+                        float f[VN];
+                        VecT<T>::unpack(lds128(base + v * 16), f);
+#pragma unroll
+                        for (int e = 0; e < VN; e += 2) {
+                            const float d0 = f[e] - Kw, d1 = f[e + 1] - Kw;
+                            sa += d0;
+                            sb += d1;
+                            qa = fmaf(d0, d0, qa);
+                            qb = fmaf(d1, d1, qb);
+                        }
+                    }
+                }
+                const float s1 = warp_sum(sa + sb), s2 = warp_sum(qa + qb);
+                if (lane == 0) {
+                    float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + warp) * 4;
+                    wp[0] = s1;
+                    wp[1] = s2;
+                    wp[2] = Kw;
+                    mbar_arrive(c.p1d0 + 8 * b1.i);
+                }
+                s1r.next(g.K);
+                b1.next(NB);
+            }
+            if (step >= g.L) {  // P2(step - L): normalise + epilogue out of the same shared-memory copy
+                const PieceId pc = piece_of(g, (step - g.L) * G + cta);
+                const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
+                char* ydst = reinterpret_cast<char*>(p.y) + goff;
+                const char* rsrc = EPI == MICN_EPI_ADD_LRELU ? reinterpret_cast<const char*>(p.res) + goff : nullptr;
+                const uint32_t base = c.data0 + s2r.i * c.slot_bytes;
+                uint4 rv0 = make_uint4(0u, 0u, 0u, 0u);
+                if (EPI == MICN_EPI_ADD_LRELU && (unsigned)tid < pc.pv) rv0 = ldg_stream(rsrc + (size_t)tid * 16);
+                mbar_wait(c.coef0 + 8 * b2.i, b2.ph);
+                const float* cf = c.coefv + b2.i * 8;
+                const float sub = cf[0], a = cf[1], b = cf[2];
+#pragma unroll 2
+                for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
+                    uint4 rv = rv0;
+                    if (EPI == MICN_EPI_ADD_LRELU) {  // residual straight from HBM, next one in flight
+                        const unsigned vn = v + kFlatConsumerThreads;
+                        if (vn < pc.pv) rv0 = ldg_stream(rsrc + (size_t)vn * 16);
+                    }
+                    float f[VN], r[VN];
+                    VecT<T>::unpack(lds128(base + v * 16), f);
+                    if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(rv, r);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) {
+                        float o = sizeof(T) == 4 ? fmaf(f[e] - sub, a, b) : fmaf(f[e], a, b);
+                        if (EPI == MICN_EPI_ADD_LRELU) o += r[e];
+                        if (EPI != MICN_EPI_NONE) o = o > 0.f ? o : o * p.slope;
+                        f[e] = o;
+                    }
+                    stg_stream(ydst + (size_t)v * 16, VecT<T>::pack(f));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.empty0 + 8 * s2r.i);
+                s2r.next(g.K);
+                b2.next(NB);
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// backward:  g = dy * act'(.) ; S1 = sum g ; S2 = sum g*(x-mean) ;
+//            dx = a*(g - S1/M - xhat*rstd*S2/M) ; dresidual = g ; dgamma/dbeta from rstd*S2 / S1
+// =================================================================================================
+template <typename T, int EPI>
+__device__ __forceinline__ float bwd_masked(float x, float gy, float o, float mean, float a, float bq, float slope) {
+    // the LeakyReLU mask is the sign of the SAME expression the forward evaluated
+    if (EPI == MICN_EPI_LRELU) {
+        const float pre = sizeof(T) == 4 ? fmaf(x - mean, a, bq) : fmaf(x, a, bq);
+        return pre > 0.f ? gy : gy * slope;
+    }
+    if (EPI == MICN_EPI_ADD_LRELU) return o > 0.f ? gy : gy * slope;
+    return gy;
+}
+
+template <typename T, int EPI>
+__global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
+    constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
+    constexpr int VN = VecT<T>::N;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FlatCtx c = flat_setup<NS>(smem, g);
+    const unsigned cta = blockIdx.x, G = gridDim.x;
+    const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
+    const unsigned NB = g.L + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned C = (unsigned)p.C;
+
+    if (warp == kFlatConsumerWarps) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            Ring r{0u, 0u};
+            for (unsigned j = 0; j < nj; ++j) {
+                if (j >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
+                const PieceId pc = piece_of(g, j * G + cta);
+                const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+                const size_t poff = (size_t)pc.k * g.PV * 16;
+                const size_t doff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + poff;
+                const char* xsrc = reinterpret_cast<const char*>(p.x) +
+                                   ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) + poff;
+                const uint32_t bytes = pc.pv * 16u, bar = c.full0 + 8 * r.i;
+                const uint32_t dst = c.data0 + r.i * c.slot_bytes;
+                flat_issue(dst, xsrc, bytes, bar, pol);
+                flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
+                if (NS == 3) flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(p.act_out) + doff, bytes, bar, pol);
+                // per-slab constants for P1, visible to the consumers through the barrier below
+                const int style = load_style(p.styles, n, p.num_styles, p.status);
+                float gamma, beta;
+                load_affine(p, style, ch, gamma, beta);
+                float* pr = c.prec + r.i * 4;
+                pr[0] = __ldg(p.save_mean + pc.slab);
+                pr[1] = __ldg(p.save_rstd + pc.slab);
+                pr[2] = gamma;
+                pr[3] = beta;
+                mbar_arrive_expect_tx(bar, bytes * NS);
+                r.next(g.K);
+            }
+        }
+    } else if (warp == kFlatConsumerWarps + 1) {
+        // ------------------------------------------------------------------ stats warp
+        Ring b1{0u, 0u}, b2{0u, 0u}, s2r{0u, 0u};
+        const float invM = 1.f / (float)p.M;
+        for (unsigned step = 0; step < nj + g.L; ++step) {
+            if (step < nj) {  // publish(step)
+                const unsigned gidx = step * G + cta;
+                mbar_wait(c.p1d0 + 8 * b1.i, b1.ph);
+                float s1 = 0.f, s2 = 0.f;
+                if (lane < kFlatConsumerWarps) {
+                    const float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + lane) * 4;
+                    s1 = wp[0];
+                    s2 = wp[1];
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) ll_store(g.ws_piece + gidx, s1, s2, g.epoch);
+                b1.next(NB);
+            }
+            if (step >= g.L) {  // gather(step - L)
+                const PieceId pc = piece_of(g, (step - g.L) * G + cta);
+                const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+                // slab constants of this piece's slot (visible: its publish() came after the consumers' full
+                // wait); read BEFORE the shuffles below so every lane holds them before lane 0 lets P2 go
+                const float* pr = c.prec + s2r.i * 4;
+                const float mean = pr[0], rstd = pr[1], gamma = pr[2], beta = pr[3];
+                float S1 = 0.f, S2 = 0.f;
+                const uint4* recs = g.ws_piece + (size_t)pc.slab * g.P;
+                for (unsigned q = lane; q < g.P; q += 32) {
+                    float a, b;
+                    ll_wait(recs + q, g.epoch, a, b);
+                    S1 += a;
+                    S2 += b;
+                }
+                S1 = warp_sum(S1);
+                S2 = warp_sum(S2);
+                const float a = rstd * gamma;
+                const float S2r = S2 * rstd;  // sum g * xhat
+                if (lane == 0) {
+                    // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
+                    const float B1 = -a * S2r * invM * rstd, B0c = -a * S1 * invM;
+                    float* cf = c.coefv + b2.i * 8;
+                    cf[0] = a;
+                    cf[1] = B1;
+                    cf[2] = sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c);
+                    cf[3] = mean;
+                    cf[4] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
+                    mbar_arrive(c.coef0 + 8 * b2.i);
+                }
+                if (pc.k == 0 && p.dgamma) {
+                    if (p.N == 1) {
+                        // one sample: this slab's sums ARE the gradients of its style's row
+                        const int style = load_style(p.styles, 0, p.num_styles, nullptr);
+                        for (int s = lane; s < p.num_styles; s += 32) {
+                            p.dbeta[(size_t)s * C + ch] = s == style ? S1 : 0.f;
+                            p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
+                        }
+                    } else {
+                        if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, g.epoch);
+                        if (n == (unsigned)p.N - 1) {
+                            // last sample of this channel: fold every sample's record per style, fixed order
+                            for (int s = 0; s < p.num_styles; ++s) {
+                                float ab = 0.f, ag = 0.f;
+                                for (unsigned nn = lane; nn < (unsigned)p.N; nn += 32) {
+                                    float ra, rb;
+                                    ll_wait(g.ws_slab + (size_t)nn * C + ch, g.epoch, ra, rb);
+                                    if (load_style(p.styles, nn, p.num_styles, nullptr) == s) {
+                                        ab += ra;
+                                        ag += rb;
+                                    }
+                                }
+                                ab = warp_sum(ab);
+                                ag = warp_sum(ag);
+                                if (lane == 0) {
+                                    p.dbeta[(size_t)s * C + ch] = ab;
+                                    p.dgamma[(size_t)s * C + ch] = ag;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                b2.next(NB);
+                s2r.next(g.K);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        Ring s1r{0u, 0u}, b1{0u, 0u}, s2r{0u, 0u}, b2{0u, 0u};
+        const uint32_t sb = c.stream_bytes;
+        for (unsigned step = 0; step < nj + g.L; ++step) {
+            if (step < nj) {  // P1(step)
+                const PieceId pc = piece_of(g, step * G + cta);
+                mbar_wait(c.full0 + 8 * s1r.i, s1r.ph);
+                const uint32_t base = c.data0 + s1r.i * c.slot_bytes;
+                const float* pr = c.prec + s1r.i * 4;
+                const float mean = pr[0], a = pr[1] * pr[2];
+                const float bq = sizeof(T) == 4 ? pr[3] : fmaf(-mean, a, pr[3]);
+                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 2
+                for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
+                    float xf[VN], gf[VN], of[VN];
+                    VecT<T>::unpack(lds128(base + v * 16), xf);
+                    VecT<T>::unpack(lds128(base + sb + v * 16), gf);
+                    if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(lds128(base + 2 * sb + v * 16), of);
+#pragma unroll
+                    for (int e = 0; e < VN; e += 2) {
+                        const float g0 = bwd_masked<T, EPI>(xf[e], gf[e], EPI == MICN_EPI_ADD_LRELU ? of[e] : 0.f, mean, a, bq, p.slope);
+                        const float g1 = bwd_masked<T, EPI>(xf[e + 1], gf[e + 1], EPI == MICN_EPI_ADD_LRELU ? of[e + 1] : 0.f, mean, a, bq, p.slope);
+                        s1a += g0;
+                        s1b += g1;
+                        s2a = fmaf(g0, xf[e] - mean, s2a);
+                        s2b = fmaf(g1, xf[e + 1] - mean, s2b);
+                    }
+                }
+                const float s1 = warp_sum(s1a + s1b), s2 = warp_sum(s2a + s2b);
+                if (lane == 0) {
+                    float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + warp) * 4;
+                    wp[0] = s1;
+                    wp[1] = s2;
+                    mbar_arrive(c.p1d0 + 8 * b1.i);
+                }
+                s1r.next(g.K);
+                b1.next(NB);
+            }
+            if (step >= g.L) {  // P2(step - L)
+                const PieceId pc = piece_of(g, (step - g.L) * G + cta);
+                const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
+                char* dxdst = reinterpret_cast<char*>(p.dx) + goff;
+                char* drdst = EPI == MICN_EPI_ADD_LRELU ? reinterpret_cast<char*>(p.dres) + goff : nullptr;
+                const uint32_t base = c.data0 + s2r.i * c.slot_bytes;
+                mbar_wait(c.coef0 + 8 * b2.i, b2.ph);
+                const float* cf = c.coefv + b2.i * 8;
+                const float A = cf[0], B1 = cf[1], B0 = cf[2], mean = cf[3], bq = cf[4];
+#pragma unroll 2
+                for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
+                    float xf[VN], gf[VN], of[VN];
+                    VecT<T>::unpack(lds128(base + v * 16), xf);
+                    VecT<T>::unpack(lds128(base + sb + v * 16), gf);
+                    if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(lds128(base + 2 * sb + v * 16), of);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) {
+                        const float gg = bwd_masked<T, EPI>(xf[e], gf[e], EPI == MICN_EPI_ADD_LRELU ? of[e] : 0.f, mean, A, bq, p.slope);
+                        gf[e] = gg;
+                        xf[e] = sizeof(T) == 4 ? fmaf(A, gg, fmaf(B1, xf[e] - mean, B0)) : fmaf(A, gg, fmaf(B1, xf[e], B0));
+                    }
+                    stg_stream(dxdst + (size_t)v * 16, VecT<T>::pack(xf));
+                    if (EPI == MICN_EPI_ADD_LRELU) stg_stream(drdst + (size_t)v * 16, VecT<T>::pack(gf));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.empty0 + 8 * s2r.i);
+                s2r.next(g.K);
+                b2.next(NB);
+            }
+        }
+    }
+}
+
+}  // namespace micn

@@ -26,10 +26,10 @@ _EPILOGUES = {"none": _lib.EPI_NONE, "lrelu": _lib.EPI_LRELU, "add_lrelu": _lib.
 _workspaces = {}
 
 
-def _workspace(device: torch.device, n: int, c: int, num_styles: int) -> torch.Tensor:
+def _workspace(device: torch.device, n: int, c: int, m: int, dtype_code: int, num_styles: int) -> torch.Tensor:
     """Zero-filled device workspace, one per (device, stream), grown on demand (micn.h: must be
     zero-filled once when allocated; the kernels leave it reusable)."""
-    need = int(_lib.lib().micn_workspace_bytes(n, c, num_styles))
+    need = int(_lib.lib().micn_workspace_bytes(n, c, m, dtype_code, num_styles))
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
@@ -115,7 +115,7 @@ class _InstanceCondFn(torch.autograd.Function):
             if residual is None or residual.shape != xs.shape or residual.dtype != xs.dtype:
                 raise ValueError("instance_cond: add_lrelu needs a residual of the input's shape and dtype")
             res = residual.contiguous()
-        ws = _workspace(dev, n, c, num_styles)
+        ws = _workspace(dev, n, c, m, _DTYPES[xs.dtype], num_styles)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             gp = _ptr_array(weights) if affine else None
@@ -148,7 +148,7 @@ class _InstanceCondFn(torch.autograd.Function):
         need_param_grads = affine and any(ctx.needs_input_grad[8:])
         dgamma = torch.empty((num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
         dbeta = torch.empty((num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
-        ws = _workspace(dev, n, c, num_styles)
+        ws = _workspace(dev, n, c, m, _DTYPES[xs.dtype], num_styles)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             gp = _ptr_array(weights) if affine else None

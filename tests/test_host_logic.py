@@ -37,7 +37,7 @@ def test_library_loads_and_exports_every_header_symbol():
     assert sorted(pkg._lib.SYMBOLS) == names
     assert lib.micn_version() >= 100
     assert b"dtype" in lib.micn_error_string(-2)
-    assert lib.micn_workspace_bytes(2, 48, 2) >= 64
+    assert lib.micn_workspace_bytes(2, 48, 96 ** 3, 1, 2) >= 64 + 2 * 48 * 8
     assert lib.micn_set_option(b"no_such_option", 1) != 0
 
 

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Flat-path knob sweep on the GPU box (bring-up aid; results land in gpurun_out/).
+out=${1:-gpurun_out/flat_sweep.jsonl}
+: > $out
+run() { echo "# $*" >> $out; timeout 120 tools/micn_selftest --suite one "$@" | grep '^{' >> $out; }
+for dt in bf16 fp32; do
+  run --N 1 --C 48 --S 96 --dtype $dt
+  run --N 1 --C 48 --S 96 --dtype $dt --path 1
+  for k in 4 5 8 10; do run --N 1 --C 48 --S 96 --dtype $dt --fslots $k; done
+  run --N 1 --C 48 --S 96 --dtype $dt --flag 1 --fslots 4
+  run --N 1 --C 48 --S 96 --dtype $dt --flag 1 --fslots 6
+  run --N 1 --C 48 --S 96 --dtype $dt --flag 3 --fslots 8
+  for pv in 768 1024 1536; do run --N 1 --C 48 --S 96 --dtype $dt --fpv $pv --fslots 8; done
+  run --N 1 --C 48 --S 96 --dtype $dt --fovh 0
+  run --N 1 --C 48 --S 96 --dtype $dt --fovh 1024
+done
+run --N 4 --C 96 --S 48 --dtype bf16
+run --N 4 --C 96 --S 48 --dtype fp32
+run --N 1 --C 24 --S 128 --dtype bf16
+run --N 1 --C 24 --S 128 --dtype fp32
+run --N 8 --C 192 --S 24 --dtype bf16
+run --N 1 --C 48 --S 96 --dtype bf16 --epi 1
+run --N 1 --C 48 --S 96 --dtype bf16 --epi 2
+cat $out

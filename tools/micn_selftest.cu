@@ -89,6 +89,7 @@ struct Case {
     long long pad_c = 0;      // extra elements between channel slabs of x (strided input)
     long long misalign = 0;   // element offset applied to every buffer (unaligned path)
     int cs = -1, slots = -1, max_clusters = -1, force_path = -1, tps = -1;
+    int fslots = -1, flag = -1, fpv = -1, fgrid = -1, fovh = -1;  // flat path knobs
     int num_styles = 2;
     bool affine = true;
     float mean = 1.0f, stdv = 2.0f;
@@ -130,6 +131,11 @@ static void set_opts(const Case& c) {
     micn_set_option("max_clusters", c.max_clusters);
     micn_set_option("force_path", c.force_path);
     micn_set_option("small_tps", c.tps);
+    micn_set_option("flat_slots", c.fslots);
+    micn_set_option("flat_lag", c.flag);
+    micn_set_option("flat_piece_vecs", c.fpv);
+    micn_set_option("flat_grid", c.fgrid);
+    micn_set_option("flat_ovh_vecs", c.fovh);
 }
 
 static int run_correctness(const Case& c, bool verbose) {
@@ -264,7 +270,7 @@ static int run_correctness(const Case& c, bool verbose) {
     CK(cudaMalloc(&d.dgamma, S * C * 4));
     CK(cudaMalloc(&d.dbeta, S * C * 4));
     CK(cudaMalloc(&d.styles, N * 8));
-    d.ws_bytes = micn_workspace_bytes(N, C, (int)S);
+    d.ws_bytes = micn_workspace_bytes(N, C, M, dt, (int)S);
     CK(cudaMalloc(&d.ws, d.ws_bytes));
     CK(cudaMemset(d.ws, 0, d.ws_bytes));
     CK(cudaMemcpy(d.x, hx.data(), xe * es, cudaMemcpyHostToDevice));
@@ -390,7 +396,7 @@ static PerfResult run_perf(const Case& c, int iters, int warm) {
     float *mean, *rstd, *gamma, *beta, *dgamma, *dbeta;
     int64_t* styles;
     void* ws;
-    const size_t wsb = micn_workspace_bytes(N, C, (int)S);
+    const size_t wsb = micn_workspace_bytes(N, C, M, dt, (int)S);
     CK(cudaMalloc(&mean, N * C * 4));
     CK(cudaMalloc(&rstd, N * C * 4));
     CK(cudaMalloc(&gamma, S * C * 4));
@@ -480,6 +486,7 @@ int main(int argc, char** argv) {
     double peak = 6542.1;
     long long oN = 1, oC = 48, oS = 96, oM = -1;
     int odt = MICN_BF16, oepi = MICN_EPI_NONE, ocs = -1, oslots = -1, oiters = 30, omaxcl = -1;
+    int opath = -1, ofslots = -1, oflag = -1, ofpv = -1, ofgrid = -1, ofovh = -1;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--suite") && i + 1 < argc) suite = argv[++i];
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
@@ -495,6 +502,12 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--slots") && i + 1 < argc) oslots = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--maxcl") && i + 1 < argc) omaxcl = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--iters") && i + 1 < argc) oiters = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--path") && i + 1 < argc) opath = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fslots") && i + 1 < argc) ofslots = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--flag") && i + 1 < argc) oflag = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fpv") && i + 1 < argc) ofpv = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fgrid") && i + 1 < argc) ofgrid = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fovh") && i + 1 < argc) ofovh = atoi(argv[++i]);
     }
     g_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     if (g_threads > 32) g_threads = 32;
@@ -537,6 +550,50 @@ int main(int argc, char** argv) {
             cs.push_back(s3);
         }
         // --- cluster path
+        // --- flat path (default for aligned slabs >= 32 KB)
+        for (int dt : dts)
+            for (int epi : epis) {
+                cs.push_back(mk("flat_auto_48^3", 2, 6, 110592, dt, epi));
+                cs.push_back(mk("flat_auto_96^3", 1, 3, 884736, dt, epi));
+                Case a = mk("flat_smallgrid_manyrounds", 3, 5, 65536, dt, epi);  // 7 CTAs, dozens of rounds each
+                a.fgrid = 7; a.fpv = 256;
+                cs.push_back(a);
+                Case b = mk("flat_ragged_pieces", 2, 3, 8 * (512 * 3 + 5) * 3 + 8, dt, epi);  // V not a multiple of anything
+                b.fpv = 640;
+                cs.push_back(b);
+                Case c2 = mk("flat_tinypieces_emptywarps", 2, 4, 16384, dt, epi);  // pieces < 512 vectors: idle warps
+                c2.fpv = 200; c2.force_path = 2;
+                cs.push_back(c2);
+                Case d2 = mk("flat_lag1_slots3", 2, 4, 110592, dt, epi);
+                d2.flag = 1; d2.fslots = 3;
+                cs.push_back(d2);
+                Case e2 = mk("flat_lag3_slots5_128^3", 1, 1, 2097152, dt, epi);  // a slab spanning 3+ rounds
+                e2.flag = 3; e2.fslots = 5;
+                cs.push_back(e2);
+                Case f2 = mk("flat_strided_x", 2, 3, 65536, dt, epi);
+                f2.pad_c = 64;
+                cs.push_back(f2);
+                Case g2 = mk("flat_5samples_3styles", 5, 4, 32768, dt, epi);
+                g2.num_styles = 3;
+                cs.push_back(g2);
+                Case h2 = mk("flat_40samples", 40, 2, 16384, dt, epi);  // > 32 samples: two records per lane in the style fold
+                cs.push_back(h2);
+            }
+        {
+            Case bm = mk("flat_bigmean", 1, 2, 110592, MICN_F32, MICN_EPI_NONE);
+            bm.mean = 50.f; bm.stdv = 0.1f;
+            cs.push_back(bm);
+            Case na = mk("flat_nonaffine_1style", 2, 2, 110592, MICN_BF16, MICN_EPI_NONE);
+            na.affine = false; na.num_styles = 1;
+            cs.push_back(na);
+            Case many = mk("flat_many_slabs", 2, 96, 32768, MICN_BF16, MICN_EPI_LRELU);
+            cs.push_back(many);
+            Case ns = mk("flat_north_star", 1, 48, 884736, MICN_BF16, MICN_EPI_NONE);
+            cs.push_back(ns);
+            Case f32 = mk("flat_fp32_128^3_auto", 1, 2, 2097152, MICN_F32, MICN_EPI_LRELU);
+            cs.push_back(f32);
+        }
+        const size_t first_cluster_case = cs.size();
         for (int dt : dts)
             for (int epi : epis) {
                 cs.push_back(mk("cluster_auto_48^3", 2, 6, 110592, dt, epi));
@@ -581,18 +638,22 @@ int main(int argc, char** argv) {
             Case many = mk("cluster_auto_many_slabs", 2, 96, 32768, MICN_BF16, MICN_EPI_LRELU);
             cs.push_back(many);
         }
+        for (size_t i = first_cluster_case; i < cs.size(); ++i)
+            if (cs[i].force_path < 0) cs[i].force_path = 1;  // flat is the default now: pin these to the cluster kernels
         for (const auto& c : cs) fails += run_correctness(c, verbose);
         printf("correctness: %zu cases, %d failures\n", cs.size(), fails);
     }
     if (suite == "check") {
         Case c = mk("check", oN, oC, oM > 0 ? oM : oS * oS * oS, odt, oepi);
         c.cs = ocs; c.slots = oslots; c.max_clusters = omaxcl;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh;
         fails += run_correctness(c, true);
     }
     if (suite == "one") {
         const long long M = oS * oS * oS;
         Case c = mk("one", oN, oC, M, odt, oepi);
         c.cs = ocs; c.slots = oslots; c.max_clusters = omaxcl;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh;
         PerfResult r = run_perf(c, oiters, 3);
         const double E = (double)oN * oC * M * esize(odt);
         const double fb = (oepi == MICN_EPI_ADD_LRELU ? 3 : 2) * E, bb = (oepi == MICN_EPI_ADD_LRELU ? 4 : 3) * E;
@@ -614,6 +675,7 @@ int main(int argc, char** argv) {
                 const long long M = s.S * s.S * s.S;
                 const long long slab_bytes = M * (long long)esize(s.dt);
                 if (cs > 0 && slab_bytes < 32 * 1024) continue;
+                if (cs > 1) continue;  // the cluster sweep was round-1 bring-up; -1 = auto (flat), 1 = cluster cs1
                 if (cs > 0 && slab_bytes / cs < 4096) continue;
                 Case c = mk("perf", s.N, s.C, M, s.dt, MICN_EPI_NONE);
                 c.cs = cs;
