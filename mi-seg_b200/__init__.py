@@ -6,11 +6,12 @@ interface that calls them.  The directory name carries a hyphen, so import it wi
 `importlib.import_module("mi-seg_b200")` or through the `mi_seg_b200` alias module at the repo root.
 """
 from . import _lib
+from .blocks import fuse_blocks
 from .functional import instance_cond, reset_workspaces
 from .integration import convert_module, install, uninstall
 from .norms import (FastConditionalInstanceNorm1d, FastConditionalInstanceNorm2d, FastConditionalInstanceNorm3d,
                     make_dropin_classes)
 
-__all__ = ["instance_cond", "reset_workspaces", "install", "uninstall", "convert_module",
+__all__ = ["instance_cond", "reset_workspaces", "install", "uninstall", "convert_module", "fuse_blocks",
            "FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
            "make_dropin_classes", "_lib"]

@@ -311,7 +311,7 @@ int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, con
     // (lag, slots) candidates, shallow-lag / deep-ring first; a forced pair replaces the list.  A slab of
     // P pieces spans <= ceil((P-1)/G)+1 rounds and P2 trails P1 by L rounds, so P <= L*G is required.
     struct Cand { long long lag, slots; };
-    Cand cands[4] = {{2, 6}, {2, 5}, {2, 4}, {3, 5}};
+    Cand cands[4] = {{2, 5}, {2, 4}, {3, 5}, {3, 6}};
     int ncand = 4;
     const long long fK = g_opt.flat_slots.load(), fL = g_opt.flat_lag.load();
     if (fK > 0 || fL > 0) {

@@ -15,12 +15,13 @@
 //                           warp shuffle) -> per-warp partials.  P2(j-L): normalise / epilogue /
 //                           backward formula out of the SAME shared-memory copy, 128-bit streaming
 //                           stores, then the slot goes back to the producer.  P2 trails P1 by L rounds.
-//   stats warp              publish(j): merges the 16 warp partials (Chan) and writes the piece record
-//                           to the workspace; gather(j-L): polls the P records of the piece's slab,
-//                           merges them in a fixed order (bit-identical in every CTA, no atomics),
-//                           turns them into the per-slab coefficients for P2; backward: also emits
-//                           the per-slab sums and, for the last sample of a channel, d(gamma)/d(beta)
-//                           per style in a fixed order.
+//   publish warp            merges the 16 warp partials of piece j (Chan) and writes the piece record to
+//                           the workspace as soon as P1(j) is done.
+//   gather warp             free-running: polls the P records of piece j's slab (all loads of a batch in
+//                           flight at once), merges them in a fixed order (bit-identical in every CTA, no
+//                           atomics) and turns them into the per-slab coefficients P2(j) waits for;
+//                           backward: also emits the per-slab sums and, for the last sample of a
+//                           channel, d(gamma)/d(beta) per style in a fixed order.
 //
 // Cross-CTA exchange is by 16-byte self-validating records {a, tag, b, tag} (tag = per-launch epoch):
 // no counters to reset, an aborted launch cannot poison the next one.  The planner keeps P <= L * G, so
@@ -41,8 +42,11 @@ namespace micn {
 
 constexpr int kFlatConsumerWarps = 16;
 constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512
-constexpr int kFlatThreads = kFlatConsumerThreads + 64;        // + producer warp + stats warp
-constexpr int kFlatMaxSlots = 16;
+constexpr int kFlatProducerWarp = kFlatConsumerWarps;
+constexpr int kFlatPublishWarp = kFlatConsumerWarps + 1;
+constexpr int kFlatGatherWarp = kFlatConsumerWarps + 2;
+constexpr int kFlatThreads = (kFlatConsumerWarps + 3) * 32;  // 608
+constexpr int kFlatMaxSlots = 8;
 constexpr int kFlatMaxLag = 3;
 constexpr int kFlatMaxPieces = 512;  // pieces per slab; the planner keeps P <= L * G (a slab spans <= L + 1 rounds)
 constexpr int kFlatMinPieceVecs = 128;
@@ -61,16 +65,15 @@ struct FlatGeom {
     uint4* ws_slab;        // [num_slabs] per-slab records (backward parameter gradients)
 };
 
+// per-slot control block: 4 mbarriers, 16 warp partials, P2 coefficients, slab constants
 __host__ __device__ constexpr int flat_ctl_bytes() {
-    return kFlatMaxSlots * 16 /*full+empty*/ + (kFlatMaxLag + 1) * 16 /*p1done+coef*/ +
-           (kFlatMaxLag + 1) * kFlatConsumerWarps * 16 /*warp partials*/ + (kFlatMaxLag + 1) * 32 /*coefficients*/ +
-           kFlatMaxSlots * 16 /*per-slot slab constants*/;
+    return kFlatMaxSlots * (4 * 8 + kFlatConsumerWarps * 16 + 32 + 16);
 }
 
 struct FlatCtx {
     uint32_t data0, full0, empty0, p1d0, coef0;  // shared::cta addresses
-    float* warp_part;                            // [NB][16][4]
-    float* coefv;                                // [NB][8]
+    float* warp_part;                            // [K][16][4]
+    float* coefv;                                // [K][8]
     float* prec;                                 // [K][4]
     uint32_t stream_bytes, slot_bytes;
 };
@@ -85,16 +88,14 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
     c.full0 = smem_u32(ctl);
     c.empty0 = c.full0 + kFlatMaxSlots * 8;
     c.p1d0 = c.empty0 + kFlatMaxSlots * 8;
-    c.coef0 = c.p1d0 + (kFlatMaxLag + 1) * 8;
-    c.warp_part = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 16 + (kFlatMaxLag + 1) * 16);
-    c.coefv = c.warp_part + (kFlatMaxLag + 1) * kFlatConsumerWarps * 4;
-    c.prec = c.coefv + (kFlatMaxLag + 1) * 8;
+    c.coef0 = c.p1d0 + kFlatMaxSlots * 8;
+    c.warp_part = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 32);
+    c.coefv = c.warp_part + kFlatMaxSlots * kFlatConsumerWarps * 4;
+    c.prec = c.coefv + kFlatMaxSlots * 8;
     if (threadIdx.x == 0) {
         for (unsigned i = 0; i < g.K; ++i) {
             mbar_init(c.full0 + 8 * i, 1);
             mbar_init(c.empty0 + 8 * i, kFlatConsumerWarps);
-        }
-        for (unsigned i = 0; i <= g.L; ++i) {
             mbar_init(c.p1d0 + 8 * i, kFlatConsumerWarps);
             mbar_init(c.coef0 + 8 * i, 1);
         }
@@ -119,7 +120,7 @@ __device__ __forceinline__ PieceId piece_of(const FlatGeom& g, unsigned gidx) {
     return p;
 }
 
-// ring cursor with phase parity
+// ring cursor with phase parity; every role walks the same ring of K slots, one slot per piece
 struct Ring {
     unsigned i, ph;
     __device__ __forceinline__ void next(unsigned n) {
@@ -152,8 +153,32 @@ __device__ __forceinline__ void ll_wait(const uint4* p, unsigned tag, float& a, 
     const uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (!ll_try(p, tag, a, b)) {
-        __nanosleep(64);
+        __nanosleep(32);
         if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+    }
+}
+
+// Poll the `count` records at `recs` (lane q handles records q, q+32, ...) and fold them with `fold(q, a, b)`
+// in ascending q per lane.  Up to four loads per lane are issued before the first is examined, so a
+// slab's whole record set costs one L2 round trip in the common (already published) case.
+template <typename Fold>
+__device__ __forceinline__ void ll_gather(const uint4* recs, unsigned count, unsigned tag, int lane, Fold fold) {
+    for (unsigned q0 = 0; q0 < count; q0 += 128) {
+        float a[4], b[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned q = q0 + lane + 32 * i;
+            ok[i] = q < count ? ll_try(recs + q, tag, a[i], b[i]) : true;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned q = q0 + lane + 32 * i;
+            if (q < count) {
+                if (!ok[i]) ll_wait(recs + q, tag, a[i], b[i]);
+                fold(q, a[i], b[i]);
+            }
+        }
     }
 }
 
@@ -170,12 +195,9 @@ __device__ __forceinline__ float first_elem(uint32_t smem_addr) {
     uint32_t w;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(smem_addr));
     if (sizeof(T) == 4) return __uint_as_float(w);
-    if (sizeof(T) == 2) {
-        float f[8];
-        VecT<T>::unpack(make_uint4(w, 0u, 0u, 0u), f);
-        return f[0];
-    }
-    return 0.f;
+    float f[VecT<T>::N];
+    VecT<T>::unpack(make_uint4(w, 0u, 0u, 0u), f);
+    return f[0];
 }
 
 // producer: one bulk copy per <= 32 KB chunk of each stream of the piece, all on the slot's barrier
@@ -196,92 +218,90 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
     const FlatCtx c = flat_setup<1>(smem, g);
     const unsigned cta = blockIdx.x, G = gridDim.x;
     const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
-    const unsigned NB = g.L + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned C = (unsigned)p.C;
 
-    if (warp == kFlatConsumerWarps) {
+    if (warp == kFlatProducerWarp) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
             Ring r{0u, 0u};
             for (unsigned j = 0; j < nj; ++j) {
-                if (j >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
                 const PieceId pc = piece_of(g, j * G + cta);
                 const unsigned n = pc.slab / C, ch = pc.slab - n * C;
                 const char* src = reinterpret_cast<const char*>(p.x) +
                                   ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) +
                                   (size_t)pc.k * g.PV * 16;
                 const uint32_t bytes = pc.pv * 16u, bar = c.full0 + 8 * r.i;
+                if (j >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
                 flat_issue(c.data0 + r.i * c.slot_bytes, src, bytes, bar, pol);
                 mbar_arrive_expect_tx(bar, bytes);
                 r.next(g.K);
             }
         }
-    } else if (warp == kFlatConsumerWarps + 1) {
-        // ------------------------------------------------------------------ stats warp
-        Ring b1{0u, 0u}, b2{0u, 0u};
-        for (unsigned step = 0; step < nj + g.L; ++step) {
-            if (step < nj) {  // publish(step)
-                const unsigned gidx = step * G + cta;
-                const PieceId pc = piece_of(g, gidx);
-                mbar_wait(c.p1d0 + 8 * b1.i, b1.ph);
-                Stat st{0.f, 0.f, 0.f};
-                if (lane < kFlatConsumerWarps) {
-                    const float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + lane) * 4;
-                    st = stat_from_shifted(wp[2], wp[0], wp[1], (float)(warp_vecs(pc.pv, lane) * VN));
-                }
-                st = stat_warp_reduce(st);
-                if (lane == 0) ll_store(g.ws_piece + gidx, st.mean, st.m2, g.epoch);
-                b1.next(NB);
+    } else if (warp == kFlatPublishWarp) {
+        // ------------------------------------------------------------------ publish: 16 warp partials -> piece record
+        Ring r{0u, 0u};
+        for (unsigned j = 0; j < nj; ++j) {
+            const unsigned gidx = j * G + cta;
+            const unsigned pv = piece_vecs(g, gidx % g.P);
+            const float nw = (float)(warp_vecs(pv, lane & 15) * VN);
+            mbar_wait(c.p1d0 + 8 * r.i, r.ph);
+            Stat st{0.f, 0.f, 0.f};
+            if (lane < kFlatConsumerWarps) {
+                const float4 w = *reinterpret_cast<const float4*>(c.warp_part + (r.i * kFlatConsumerWarps + lane) * 4);
+                st = stat_from_shifted(w.z, w.x, w.y, nw);
             }
-            if (step >= g.L) {  // gather(step - L)
-                const PieceId pc = piece_of(g, (step - g.L) * G + cta);
-                const unsigned n = pc.slab / C, ch = pc.slab - n * C;
-                // parameters first: their latency hides behind the polls
-                const int style = load_style(p.styles, n, p.num_styles, p.status);
-                float gamma, beta;
-                load_affine(p, style, ch, gamma, beta);
-                Stat acc{0.f, 0.f, 0.f};
-                const uint4* recs = g.ws_piece + (size_t)pc.slab * g.P;
-                for (unsigned q = lane; q < g.P; q += 32) {
-                    float a, b;
-                    ll_wait(recs + q, g.epoch, a, b);
-                    acc = stat_merge(acc, Stat{(float)(piece_vecs(g, q) * VN), a, b});
-                }
-                acc = stat_warp_reduce(acc);
+            st = stat_warp_reduce(st);
+            if (lane == 0) ll_store(g.ws_piece + gidx, st.mean, st.m2, g.epoch);
+            r.next(g.K);
+        }
+    } else if (warp == kFlatGatherWarp) {
+        // ------------------------------------------------------------------ gather: slab records -> P2 coefficients
+        Ring r{0u, 0u};
+        for (unsigned j = 0; j < nj; ++j) {
+            const PieceId pc = piece_of(g, j * G + cta);
+            const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+            // parameter loads first: their latency hides behind the polls
+            const int style = load_style(p.styles, n, p.num_styles, p.status);
+            float gamma, beta;
+            load_affine(p, style, ch, gamma, beta);
+            Stat acc{0.f, 0.f, 0.f};
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, lane, [&](unsigned q, float a, float b) {
+                acc = stat_merge(acc, Stat{(float)(piece_vecs(g, q) * VN), a, b});
+            });
+            acc = stat_warp_reduce(acc);
+            if (lane == 0) {
                 const float mean = acc.mean;
                 const float rstd = 1.f / sqrtf(acc.m2 / (float)p.M + p.eps);  // biased variance, eps inside the sqrt
-                if (lane == 0) {
-                    const float a = rstd * gamma;
-                    float* cf = c.coefv + b2.i * 8;
-                    // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element
-                    cf[0] = sizeof(T) == 4 ? mean : 0.f;
-                    cf[1] = a;
-                    cf[2] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
-                    if (pc.k == 0 && p.save_mean) {
-                        p.save_mean[pc.slab] = mean;
-                        p.save_rstd[pc.slab] = rstd;
-                    }
-                    mbar_arrive(c.coef0 + 8 * b2.i);
+                const float a = rstd * gamma;
+                // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element.
+                // The slot's previous coefficients were consumed before this piece was even loaded.
+                *reinterpret_cast<float4*>(c.coefv + r.i * 8) =
+                    make_float4(sizeof(T) == 4 ? mean : 0.f, a, sizeof(T) == 4 ? beta : fmaf(-mean, a, beta), 0.f);
+                if (pc.k == 0 && p.save_mean) {
+                    p.save_mean[pc.slab] = mean;
+                    p.save_rstd[pc.slab] = rstd;
                 }
-                __syncwarp();
-                b2.next(NB);
+                mbar_arrive(c.coef0 + 8 * r.i);
             }
+            __syncwarp();
+            r.next(g.K);
         }
     } else {
         // ------------------------------------------------------------------ consumers
-        Ring s1r{0u, 0u}, b1{0u, 0u}, s2r{0u, 0u}, b2{0u, 0u};
+        Ring r1{0u, 0u}, r2{0u, 0u};
         for (unsigned step = 0; step < nj + g.L; ++step) {
             if (step < nj) {  // P1(step): statistics
-                const PieceId pc = piece_of(g, step * G + cta);
-                mbar_wait(c.full0 + 8 * s1r.i, s1r.ph);
-                const uint32_t base = c.data0 + s1r.i * c.slot_bytes;
+                const unsigned gidx = step * G + cta;
+                const unsigned pv = piece_vecs(g, gidx % g.P);
+                mbar_wait(c.full0 + 8 * r1.i, r1.ph);
+                const uint32_t base = c.data0 + r1.i * c.slot_bytes;
                 float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, Kw = 0.f;
-                if ((unsigned)warp * 32u < pc.pv) {
+                if ((unsigned)warp * 32u < pv) {
                     Kw = first_elem<T>(base + warp * 512);  // shift = the warp's first element of the piece
 #pragma unroll 2
-                    for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
+                    for (unsigned v = tid; v < pv; v += kFlatConsumerThreads) {
                         float f[VN];
                         VecT<T>::unpack(lds128(base + v * 16), f);
 #pragma unroll
@@ -296,26 +316,23 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
                 }
                 const float s1 = warp_sum(sa + sb), s2 = warp_sum(qa + qb);
                 if (lane == 0) {
-                    float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + warp) * 4;
-                    wp[0] = s1;
-                    wp[1] = s2;
-                    wp[2] = Kw;
-                    mbar_arrive(c.p1d0 + 8 * b1.i);
+                    *reinterpret_cast<float4*>(c.warp_part + (r1.i * kFlatConsumerWarps + warp) * 4) =
+                        make_float4(s1, s2, Kw, 0.f);
+                    mbar_arrive(c.p1d0 + 8 * r1.i);
                 }
-                s1r.next(g.K);
-                b1.next(NB);
+                r1.next(g.K);
             }
             if (step >= g.L) {  // P2(step - L): normalise + epilogue out of the same shared-memory copy
                 const PieceId pc = piece_of(g, (step - g.L) * G + cta);
                 const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
                 char* ydst = reinterpret_cast<char*>(p.y) + goff;
                 const char* rsrc = EPI == MICN_EPI_ADD_LRELU ? reinterpret_cast<const char*>(p.res) + goff : nullptr;
-                const uint32_t base = c.data0 + s2r.i * c.slot_bytes;
+                const uint32_t base = c.data0 + r2.i * c.slot_bytes;
                 uint4 rv0 = make_uint4(0u, 0u, 0u, 0u);
                 if (EPI == MICN_EPI_ADD_LRELU && (unsigned)tid < pc.pv) rv0 = ldg_stream(rsrc + (size_t)tid * 16);
-                mbar_wait(c.coef0 + 8 * b2.i, b2.ph);
-                const float* cf = c.coefv + b2.i * 8;
-                const float sub = cf[0], a = cf[1], b = cf[2];
+                mbar_wait(c.coef0 + 8 * r2.i, r2.ph);
+                const float4 cf = *reinterpret_cast<const float4*>(c.coefv + r2.i * 8);
+                const float sub = cf.x, a = cf.y, b = cf.z;
 #pragma unroll 2
                 for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
                     uint4 rv = rv0;
@@ -336,9 +353,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
                     stg_stream(ydst + (size_t)v * 16, VecT<T>::pack(f));
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c.empty0 + 8 * s2r.i);
-                s2r.next(g.K);
-                b2.next(NB);
+                if (lane == 0) mbar_arrive(c.empty0 + 8 * r2.i);
+                r2.next(g.K);
             }
         }
     }
@@ -367,142 +383,135 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
     const FlatCtx c = flat_setup<NS>(smem, g);
     const unsigned cta = blockIdx.x, G = gridDim.x;
     const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
-    const unsigned NB = g.L + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned C = (unsigned)p.C;
 
-    if (warp == kFlatConsumerWarps) {
+    if (warp == kFlatProducerWarp) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
             Ring r{0u, 0u};
             for (unsigned j = 0; j < nj; ++j) {
-                if (j >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
                 const PieceId pc = piece_of(g, j * G + cta);
                 const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+                // per-slab constants for P1 / gather: loads issued before the slot wait
+                const int style = load_style(p.styles, n, p.num_styles, p.status);
+                float gamma, beta;
+                load_affine(p, style, ch, gamma, beta);
+                const float mean = __ldg(p.save_mean + pc.slab), rstd = __ldg(p.save_rstd + pc.slab);
                 const size_t poff = (size_t)pc.k * g.PV * 16;
                 const size_t doff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + poff;
                 const char* xsrc = reinterpret_cast<const char*>(p.x) +
                                    ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) + poff;
                 const uint32_t bytes = pc.pv * 16u, bar = c.full0 + 8 * r.i;
                 const uint32_t dst = c.data0 + r.i * c.slot_bytes;
+                if (j >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
                 flat_issue(dst, xsrc, bytes, bar, pol);
                 flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
                 if (NS == 3) flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(p.act_out) + doff, bytes, bar, pol);
-                // per-slab constants for P1, visible to the consumers through the barrier below
-                const int style = load_style(p.styles, n, p.num_styles, p.status);
-                float gamma, beta;
-                load_affine(p, style, ch, gamma, beta);
-                float* pr = c.prec + r.i * 4;
-                pr[0] = __ldg(p.save_mean + pc.slab);
-                pr[1] = __ldg(p.save_rstd + pc.slab);
-                pr[2] = gamma;
-                pr[3] = beta;
+                // visible to the consumers (and, through their p1done arrival, to the gather warp) via the barrier
+                *reinterpret_cast<float4*>(c.prec + r.i * 4) = make_float4(mean, rstd, gamma, beta);
                 mbar_arrive_expect_tx(bar, bytes * NS);
                 r.next(g.K);
             }
         }
-    } else if (warp == kFlatConsumerWarps + 1) {
-        // ------------------------------------------------------------------ stats warp
-        Ring b1{0u, 0u}, b2{0u, 0u}, s2r{0u, 0u};
-        const float invM = 1.f / (float)p.M;
-        for (unsigned step = 0; step < nj + g.L; ++step) {
-            if (step < nj) {  // publish(step)
-                const unsigned gidx = step * G + cta;
-                mbar_wait(c.p1d0 + 8 * b1.i, b1.ph);
-                float s1 = 0.f, s2 = 0.f;
-                if (lane < kFlatConsumerWarps) {
-                    const float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + lane) * 4;
-                    s1 = wp[0];
-                    s2 = wp[1];
-                }
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                if (lane == 0) ll_store(g.ws_piece + gidx, s1, s2, g.epoch);
-                b1.next(NB);
+    } else if (warp == kFlatPublishWarp) {
+        // ------------------------------------------------------------------ publish
+        Ring r{0u, 0u};
+        for (unsigned j = 0; j < nj; ++j) {
+            mbar_wait(c.p1d0 + 8 * r.i, r.ph);
+            float s1 = 0.f, s2 = 0.f;
+            if (lane < kFlatConsumerWarps) {
+                const float2 w = *reinterpret_cast<const float2*>(c.warp_part + (r.i * kFlatConsumerWarps + lane) * 4);
+                s1 = w.x;
+                s2 = w.y;
             }
-            if (step >= g.L) {  // gather(step - L)
-                const PieceId pc = piece_of(g, (step - g.L) * G + cta);
-                const unsigned n = pc.slab / C, ch = pc.slab - n * C;
-                // slab constants of this piece's slot (visible: its publish() came after the consumers' full
-                // wait); read BEFORE the shuffles below so every lane holds them before lane 0 lets P2 go
-                const float* pr = c.prec + s2r.i * 4;
-                const float mean = pr[0], rstd = pr[1], gamma = pr[2], beta = pr[3];
-                float S1 = 0.f, S2 = 0.f;
-                const uint4* recs = g.ws_piece + (size_t)pc.slab * g.P;
-                for (unsigned q = lane; q < g.P; q += 32) {
-                    float a, b;
-                    ll_wait(recs + q, g.epoch, a, b);
-                    S1 += a;
-                    S2 += b;
-                }
-                S1 = warp_sum(S1);
-                S2 = warp_sum(S2);
-                const float a = rstd * gamma;
-                const float S2r = S2 * rstd;  // sum g * xhat
-                if (lane == 0) {
-                    // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
-                    const float B1 = -a * S2r * invM * rstd, B0c = -a * S1 * invM;
-                    float* cf = c.coefv + b2.i * 8;
-                    cf[0] = a;
-                    cf[1] = B1;
-                    cf[2] = sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c);
-                    cf[3] = mean;
-                    cf[4] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
-                    mbar_arrive(c.coef0 + 8 * b2.i);
-                }
-                if (pc.k == 0 && p.dgamma) {
-                    if (p.N == 1) {
-                        // one sample: this slab's sums ARE the gradients of its style's row
-                        const int style = load_style(p.styles, 0, p.num_styles, nullptr);
-                        for (int s = lane; s < p.num_styles; s += 32) {
-                            p.dbeta[(size_t)s * C + ch] = s == style ? S1 : 0.f;
-                            p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
-                        }
-                    } else {
-                        if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, g.epoch);
-                        if (n == (unsigned)p.N - 1) {
-                            // last sample of this channel: fold every sample's record per style, fixed order
-                            for (int s = 0; s < p.num_styles; ++s) {
-                                float ab = 0.f, ag = 0.f;
-                                for (unsigned nn = lane; nn < (unsigned)p.N; nn += 32) {
-                                    float ra, rb;
-                                    ll_wait(g.ws_slab + (size_t)nn * C + ch, g.epoch, ra, rb);
-                                    if (load_style(p.styles, nn, p.num_styles, nullptr) == s) {
-                                        ab += ra;
-                                        ag += rb;
-                                    }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) ll_store(g.ws_piece + (j * G + cta), s1, s2, g.epoch);
+            r.next(g.K);
+        }
+    } else if (warp == kFlatGatherWarp) {
+        // ------------------------------------------------------------------ gather
+        Ring r{0u, 0u};
+        const float invM = 1.f / (float)p.M;
+        for (unsigned j = 0; j < nj; ++j) {
+            const PieceId pc = piece_of(g, j * G + cta);
+            const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+            float S1 = 0.f, S2 = 0.f;
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, lane, [&](unsigned, float a, float b) {
+                S1 += a;
+                S2 += b;
+            });
+            S1 = warp_sum(S1);
+            S2 = warp_sum(S2);
+            // the slab's records include this CTA's own piece j, so P1(j) is done: this wait returns at once
+            // and makes the producer's constants for the slot visible (full -> consumers -> p1done)
+            mbar_wait(c.p1d0 + 8 * r.i, r.ph);
+            const volatile float* pr = c.prec + r.i * 4;
+            const float mean = pr[0], rstd = pr[1], gamma = pr[2], beta = pr[3];
+            const float a = rstd * gamma;
+            const float S2r = S2 * rstd;  // sum g * xhat
+            __syncwarp();
+            if (lane == 0) {
+                // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
+                const float B1 = -a * S2r * invM * rstd, B0c = -a * S1 * invM;
+                float* cf = c.coefv + r.i * 8;
+                *reinterpret_cast<float4*>(cf) = make_float4(a, B1, sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c), mean);
+                cf[4] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
+                mbar_arrive(c.coef0 + 8 * r.i);
+            }
+            if (pc.k == 0 && p.dgamma) {
+                if (p.N == 1) {
+                    // one sample: this slab's sums ARE the gradients of its style's row
+                    const int style = load_style(p.styles, 0, p.num_styles, nullptr);
+                    for (int s = lane; s < p.num_styles; s += 32) {
+                        p.dbeta[(size_t)s * C + ch] = s == style ? S1 : 0.f;
+                        p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
+                    }
+                } else {
+                    if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, g.epoch);
+                    if (n == (unsigned)p.N - 1) {
+                        // last sample of this channel: fold every sample's record per style, fixed order
+                        for (int s = 0; s < p.num_styles; ++s) {
+                            float ab = 0.f, ag = 0.f;
+                            for (unsigned nn = lane; nn < (unsigned)p.N; nn += 32) {
+                                float ra, rb;
+                                ll_wait(g.ws_slab + (size_t)nn * C + ch, g.epoch, ra, rb);
+                                if (load_style(p.styles, nn, p.num_styles, nullptr) == s) {
+                                    ab += ra;
+                                    ag += rb;
                                 }
-                                ab = warp_sum(ab);
-                                ag = warp_sum(ag);
-                                if (lane == 0) {
-                                    p.dbeta[(size_t)s * C + ch] = ab;
-                                    p.dgamma[(size_t)s * C + ch] = ag;
-                                }
+                            }
+                            ab = warp_sum(ab);
+                            ag = warp_sum(ag);
+                            if (lane == 0) {
+                                p.dbeta[(size_t)s * C + ch] = ab;
+                                p.dgamma[(size_t)s * C + ch] = ag;
                             }
                         }
                     }
                 }
-                __syncwarp();
-                b2.next(NB);
-                s2r.next(g.K);
             }
+            __syncwarp();
+            r.next(g.K);
         }
     } else {
         // ------------------------------------------------------------------ consumers
-        Ring s1r{0u, 0u}, b1{0u, 0u}, s2r{0u, 0u}, b2{0u, 0u};
+        Ring r1{0u, 0u}, r2{0u, 0u};
         const uint32_t sb = c.stream_bytes;
         for (unsigned step = 0; step < nj + g.L; ++step) {
             if (step < nj) {  // P1(step)
-                const PieceId pc = piece_of(g, step * G + cta);
-                mbar_wait(c.full0 + 8 * s1r.i, s1r.ph);
-                const uint32_t base = c.data0 + s1r.i * c.slot_bytes;
-                const float* pr = c.prec + s1r.i * 4;
-                const float mean = pr[0], a = pr[1] * pr[2];
-                const float bq = sizeof(T) == 4 ? pr[3] : fmaf(-mean, a, pr[3]);
+                const unsigned gidx = step * G + cta;
+                const unsigned pv = piece_vecs(g, gidx % g.P);
+                mbar_wait(c.full0 + 8 * r1.i, r1.ph);
+                const uint32_t base = c.data0 + r1.i * c.slot_bytes;
+                const float4 pr = *reinterpret_cast<const float4*>(c.prec + r1.i * 4);
+                const float mean = pr.x, a = pr.y * pr.z;
+                const float bq = sizeof(T) == 4 ? pr.w : fmaf(-mean, a, pr.w);
                 float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll 2
-                for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
+                for (unsigned v = tid; v < pv; v += kFlatConsumerThreads) {
                     float xf[VN], gf[VN], of[VN];
                     VecT<T>::unpack(lds128(base + v * 16), xf);
                     VecT<T>::unpack(lds128(base + sb + v * 16), gf);
@@ -519,23 +528,21 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                 }
                 const float s1 = warp_sum(s1a + s1b), s2 = warp_sum(s2a + s2b);
                 if (lane == 0) {
-                    float* wp = c.warp_part + (b1.i * kFlatConsumerWarps + warp) * 4;
-                    wp[0] = s1;
-                    wp[1] = s2;
-                    mbar_arrive(c.p1d0 + 8 * b1.i);
+                    *reinterpret_cast<float2*>(c.warp_part + (r1.i * kFlatConsumerWarps + warp) * 4) = make_float2(s1, s2);
+                    mbar_arrive(c.p1d0 + 8 * r1.i);
                 }
-                s1r.next(g.K);
-                b1.next(NB);
+                r1.next(g.K);
             }
             if (step >= g.L) {  // P2(step - L)
                 const PieceId pc = piece_of(g, (step - g.L) * G + cta);
                 const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
                 char* dxdst = reinterpret_cast<char*>(p.dx) + goff;
                 char* drdst = EPI == MICN_EPI_ADD_LRELU ? reinterpret_cast<char*>(p.dres) + goff : nullptr;
-                const uint32_t base = c.data0 + s2r.i * c.slot_bytes;
-                mbar_wait(c.coef0 + 8 * b2.i, b2.ph);
-                const float* cf = c.coefv + b2.i * 8;
-                const float A = cf[0], B1 = cf[1], B0 = cf[2], mean = cf[3], bq = cf[4];
+                const uint32_t base = c.data0 + r2.i * c.slot_bytes;
+                mbar_wait(c.coef0 + 8 * r2.i, r2.ph);
+                const float* cf = c.coefv + r2.i * 8;
+                const float4 cq = *reinterpret_cast<const float4*>(cf);
+                const float A = cq.x, B1 = cq.y, B0 = cq.z, mean = cq.w, bq = cf[4];
 #pragma unroll 2
                 for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
                     float xf[VN], gf[VN], of[VN];
@@ -552,9 +559,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                     if (EPI == MICN_EPI_ADD_LRELU) stg_stream(drdst + (size_t)v * 16, VecT<T>::pack(gf));
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c.empty0 + 8 * s2r.i);
-                s2r.next(g.K);
-                b2.next(NB);
+                if (lane == 0) mbar_arrive(c.empty0 + 8 * r2.i);
+                r2.next(g.K);
             }
         }
     }

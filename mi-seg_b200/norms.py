@@ -79,21 +79,25 @@ class FastForwardMixin:
     """forward() shared by the stand-alone and the MI-Seg-derived classes.  Relies on the host
     class for `_check_input_dim`, `_check_input_styles`, `_get_no_batch_dim`, `norms`, `num_styles`."""
 
-    #: fused epilogue applied by forward(); set by blocks.fuse_* ("none" | "lrelu" | "add_lrelu")
-    fused_epilogue: str = "none"
-    fused_slope: float = 0.01
-
     def _params(self) -> Tuple[List[Tensor], List[Tensor]]:
         return [n.weight for n in self.norms], [n.bias for n in self.norms]
 
-    def forward(self, input: Tensor, styles: Union[List, Tensor, int], residual: Optional[Tensor] = None) -> Tensor:
+    def forward(self, input: Tensor, styles: Union[List, Tensor, int]) -> Tensor:
+        """y = IN_{styles[n]}(input[n]) for every sample: the reference's forward (:62-68)."""
+        return self.forward_fused(input, styles, "none")
+
+    def forward_fused(self, input: Tensor, styles: Union[List, Tensor, int], epilogue: str = "none",
+                      residual: Optional[Tensor] = None, slope: float = 0.01) -> Tensor:
+        """forward() with the activation / residual that follows the norm in MI-Seg's blocks fused into
+        the same kernel: "lrelu" = lrelu(norm(x)) (dynunet_block.py:107-111, 188-202), "add_lrelu" =
+        lrelu(norm(x) + residual) (:113-125).  Used by blocks.fuse_blocks()."""
         self._check_input_dim(input)
         self._check_input_styles(input, styles)
         unbatched = input.dim() == self._get_no_batch_dim()
         x = input.unsqueeze(0) if unbatched else input
         host = _host_styles(styles, self.num_styles)
         if x.shape[1] != self.norms[0].num_features:
-            # message of nn.InstanceNorm*d._check_input_dim via _get_no_batch_dim / num_features
+            # nn.InstanceNorm*d._check_input_dim's message (affine norms check the channel count)
             raise ValueError(f"expected input's size at dim=1 to match num_features "
                              f"({self.norms[0].num_features}), but got: {x.shape[1]}.")
         m = 1
@@ -107,10 +111,11 @@ class FastForwardMixin:
         else:
             styles_dev = styles.reshape(-1).to(torch.int64)
             present = None  # unknown without a device sync: absent styles get zero grads instead of None
+        if residual is not None and unbatched:
+            residual = residual.unsqueeze(0)
         w, b = self._params()
-        eps = self.norms[0].eps
-        y = instance_cond(x, styles_dev, w, b, eps=eps, epilogue=self.fused_epilogue if residual is None
-                          else "add_lrelu", residual=residual, slope=self.fused_slope, present=present)
+        y = instance_cond(x, styles_dev, w, b, eps=self.norms[0].eps, epilogue=epilogue, residual=residual,
+                          slope=slope, present=present)
         return y.squeeze(0) if unbatched else y
 
 

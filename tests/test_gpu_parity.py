@@ -261,7 +261,7 @@ def test_unbatched_and_negative_styles(pkg):
         y = mod(x, st)
         ref, _, _ = O.fwd_f64(x[None].cpu().numpy(), [1], np.full((2, 4), 2.0), np.full((2, 4), 0.5))
         assert y.shape == x.shape
-        assert rel_err(y.cpu().numpy(), ref[0]) < 1e-5
+        assert rel_err(y.detach().cpu().numpy(), ref[0]) < 1e-5
 
 
 def test_autocast_keeps_input_dtype(pkg):
@@ -388,3 +388,74 @@ def test_north_star_shape_properties_and_torch_reference(pkg, dtype):
     y2.backward((2 * dy.float()).to(dtype))
     lin = (x2.grad.float() - 2 * x.grad.float()).abs().max() / x.grad.float().abs().max()
     assert lin.item() < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ whole blocks (fused)
+class _Conv(torch.nn.Module):  # MONAI Convolution(conv_only) keeps the Conv3d under `.conv`
+    def __init__(self, cin, cout, k, stride):
+        super().__init__()
+        self.conv = torch.nn.Conv3d(cin, cout, k, stride, padding=(k - stride + 1) // 2, bias=False)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+def _make_block(pkg, kind, cin, cout, stride, num_styles):
+    class UnetResBlock(torch.nn.Module):  # same attribute names as dynunet_block.py:44-98
+        def __init__(self):
+            super().__init__()
+            self.conv1, self.conv2 = _Conv(cin, cout, 3, stride), _Conv(cout, cout, 3, 1)
+            self.lrelu = torch.nn.LeakyReLU(0.01, inplace=True)
+            self.norm1 = pkg.FastConditionalInstanceNorm3d(num_styles, cout)
+            self.norm2 = pkg.FastConditionalInstanceNorm3d(num_styles, cout)
+            if kind == "res" and (cin != cout or stride != 1):
+                self.conv3 = _Conv(cin, cout, 1, stride)
+                self.norm3 = pkg.FastConditionalInstanceNorm3d(num_styles, cout)
+
+    class UnetBasicBlock(UnetResBlock):
+        pass
+
+    return (UnetResBlock if kind == "res" else UnetBasicBlock)()
+
+
+@pytest.mark.parametrize("path", golden_files("block"), ids=os.path.basename)
+def test_fused_block_matches_reference_block_end_to_end(pkg, path):
+    """A block with MI-Seg's attribute layout, the recorded conv weights and fast norms, fused by
+    fuse_blocks(): output, input gradient and EVERY parameter gradient against the real block."""
+    g = load_golden(path)
+    kind, S = str(g["kind"]), int(g["num_styles"])
+    cin, cout, stride = g["x"].shape[1], g["out"].shape[1], int(g["stride"])
+    blk = _make_block(pkg, kind, cin, cout, stride, S).cuda()
+    with torch.no_grad():
+        for nm in ("conv1", "conv2", "conv3"):
+            if hasattr(blk, nm):
+                getattr(blk, nm).conv.weight.copy_(torch.from_numpy(g[f"{nm}_weight"]))
+        for nm in ("norm1", "norm2", "norm3"):
+            if hasattr(blk, nm):
+                for s in range(S):
+                    getattr(blk, nm).norms[s].weight.copy_(torch.from_numpy(g[f"{nm}_gamma"][s]))
+                    getattr(blk, nm).norms[s].bias.copy_(torch.from_numpy(g[f"{nm}_beta"][s]))
+    assert pkg.fuse_blocks(blk) == 1
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    st = torch.tensor(g["styles"], dtype=torch.int64)  # CPU tensor: host-visible, absent styles -> None grads
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        out = blk(x, st)
+        out.backward(torch.from_numpy(g["dout"]).cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    tol = 2e-5  # conv3d on cuDNN vs the CPU reference adds its own fp32 rounding
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < tol
+    assert rel_err(x.grad.cpu().numpy(), g["dx"]) < tol
+    for nm in ("conv1", "conv2", "conv3"):
+        if hasattr(blk, nm):
+            assert rel_err(getattr(blk, nm).conv.weight.grad.cpu().numpy(), g[f"{nm}_weight_grad"]) < 5 * tol, nm
+    for nm in ("norm1", "norm2", "norm3"):
+        if hasattr(blk, nm):
+            dg, db, present = _grads(getattr(blk, nm))
+            assert rel_err(dg, g[f"{nm}_dgamma"]) < 5 * tol, nm
+            assert rel_err(db, g[f"{nm}_dbeta"]) < 5 * tol, nm
+            assert present == list(g[f"{nm}_present"])
+    with pytest.raises(ValueError, match="Modalities must be passed"):
+        blk(x)

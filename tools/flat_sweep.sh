@@ -5,14 +5,10 @@ out=${1:-gpurun_out/flat_sweep.jsonl}
 run() { echo "# $*" >> $out; timeout 120 tools/micn_selftest --suite one "$@" | grep '^{' >> $out; }
 for dt in bf16 fp32; do
   run --N 1 --C 48 --S 96 --dtype $dt
-  run --N 1 --C 48 --S 96 --dtype $dt --path 1
-  for k in 4 5 8 10; do run --N 1 --C 48 --S 96 --dtype $dt --fslots $k; done
-  run --N 1 --C 48 --S 96 --dtype $dt --flag 1 --fslots 4
-  run --N 1 --C 48 --S 96 --dtype $dt --flag 1 --fslots 6
-  run --N 1 --C 48 --S 96 --dtype $dt --flag 3 --fslots 8
-  for pv in 768 1024 1536; do run --N 1 --C 48 --S 96 --dtype $dt --fpv $pv --fslots 8; done
-  run --N 1 --C 48 --S 96 --dtype $dt --fovh 0
-  run --N 1 --C 48 --S 96 --dtype $dt --fovh 1024
+  for k in 3 4 5 6 8; do run --N 1 --C 48 --S 96 --dtype $dt --fslots $k --flag 1; done
+  for k in 4 5 6 8; do run --N 1 --C 48 --S 96 --dtype $dt --fslots $k --flag 2; done
+  run --N 1 --C 48 --S 96 --dtype $dt --flag 3 --fslots 6
+  for pv in 1024 1536 2048; do run --N 1 --C 48 --S 96 --dtype $dt --fpv $pv --fslots 8; done
 done
 run --N 4 --C 96 --S 48 --dtype bf16
 run --N 4 --C 96 --S 48 --dtype fp32
