@@ -31,11 +31,15 @@ struct Options {
     std::atomic<long long> cluster_size{-1};  // force CS (1..16)
     std::atomic<long long> force_path{-1};    // 0 small, 1 cluster, 2 flat
     std::atomic<long long> flat_slots{-1};    // ring slots K of the flat path
-    std::atomic<long long> flat_lag{-1};      // rounds P2 trails P1
+    std::atomic<long long> flat_lag{-1};      // per consumer group, pieces P2 trails P1
+    std::atomic<long long> flat_groups{-1};   // consumer groups NG
+    std::atomic<long long> flat_poll_delay_ns{-1}, flat_poll_backoff_ns{-1};
     std::atomic<long long> flat_piece_vecs{-1};  // cap on vectors per piece
     std::atomic<long long> flat_min_bytes{-1};   // smallest slab the flat path takes
     std::atomic<long long> flat_grid{-1};     // cap on the persistent grid
     std::atomic<long long> flat_ovh_vecs{-1}; // planner: per-piece overhead in vector-equivalents
+    std::atomic<long long> flat_coop{-1};     // 0: plain launch instead of a cooperative one (experiments)
+    std::atomic<long long> flat_trace{0};     // bring-up: device pointer of a [grid][64][16] int64 trace buffer
     std::atomic<long long> slots{-1};         // force ring slots S
     std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
     std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
@@ -57,6 +61,8 @@ const OptName kOptNames[] = {
     {"launches", &g_opt.launches},         {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
+    {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace}, {"flat_groups", &g_opt.flat_groups},
+    {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
 
 // ------------------------------------------------------------------------------------------ device
@@ -308,29 +314,46 @@ int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, con
     long long ovh = g_opt.flat_ovh_vecs.load();
     if (ovh < 0) ovh = 256;
 
-    // (lag, slots) candidates, shallow-lag / deep-ring first; a forced pair replaces the list.  A slab of
-    // P pieces spans <= ceil((P-1)/G)+1 rounds and P2 trails P1 by L rounds, so P <= L*G is required.
-    struct Cand { long long lag, slots; };
-    Cand cands[4] = {{2, 5}, {2, 4}, {3, 5}, {3, 6}};
-    int ncand = 4;
-    const long long fK = g_opt.flat_slots.load(), fL = g_opt.flat_lag.load();
-    if (fK > 0 || fL > 0) {
-        long long L_ = fL > 0 ? fL : 2;
-        if (L_ > kFlatMaxLag) L_ = kFlatMaxLag;
-        long long K_ = fK > 0 ? fK : 6;
-        if (K_ < L_ + 2) K_ = L_ + 2;
-        if (K_ > kFlatMaxSlots) K_ = kFlatMaxSlots;
-        cands[0] = {L_, K_};
+    // (groups, per-group lag, slots) candidates, preferred first; forced values replace the list.
+    // Requirements (micn_flat.cuh): K a multiple of NG, K >= (Lg+1)*NG + 1, and a slab of P pieces spans R = ceil((P-1)/G)+1
+    // rounds with R - 1 <= Lg*NG and R <= K.
+    struct Cand { long long ng, lag, slots; };
+    Cand cands[4];
+    int ncand = 0;
+    if (NS == 1) {
+        cands[ncand++] = {2, 3, 12};
+        cands[ncand++] = {2, 3, 10};
+        cands[ncand++] = {2, 2, 8};
+        cands[ncand++] = {1, 4, 6};
+    } else {
+        cands[ncand++] = {2, 2, 8};
+        cands[ncand++] = {1, 4, 7};
+        cands[ncand++] = {1, 4, 6};
+        cands[ncand++] = {1, 3, 5};
+    }
+    const long long fK = g_opt.flat_slots.load(), fL = g_opt.flat_lag.load(), fG = g_opt.flat_groups.load();
+    if (fK > 0 || fL > 0 || fG > 0) {
+        long long ng = fG > 0 ? fG : cands[0].ng;
+        if (ng != 1 && ng != 2 && ng != 4 && ng != 8 && ng != 16) ng = 2;
+        long long lag = fL > 0 ? fL : cands[0].lag;
+        long long slots = fK > 0 ? fK : cands[0].slots;
+        if (slots > kFlatMaxSlots) slots = kFlatMaxSlots;
+        slots -= slots % ng;  // a slot must always belong to the same consumer group
+        if (slots < (lag + 1) * ng + 1) lag = (slots - 1) / ng - 1;
+        if (lag < 1) return 1;
+        cands[0] = {ng, lag, slots};
         ncand = 1;
     }
     for (int ci = 0; ci < ncand; ++ci) {
-        const long long L_ = cands[ci].lag, K_ = cands[ci].slots;
+        const long long NG = cands[ci].ng, Lg = cands[ci].lag, K_ = cands[ci].slots;
         const long long slot_vecs = (ring / (K_ * NS * 16)) & ~7LL;
         if (slot_vecs < kFlatMinPieceVecs) continue;
         long long pvmax = slot_vecs;
         const long long cap = g_opt.flat_piece_vecs.load();
         if (cap >= kFlatMinPieceVecs && cap < pvmax) pvmax = cap;
-        const long long pmax_hw = std::min<long long>(kFlatMaxPieces, L_ * G);
+        // R - 1 = ceil((P-1)/G) <= min(Lg*NG, K-1)
+        const long long span = std::min<long long>(Lg * NG, K_ - 1);
+        const long long pmax_hw = std::min<long long>(kFlatMaxPieces, span * G + 1);
         const long long P0 = (V + pvmax - 1) / pvmax;
         if (P0 > pmax_hw) continue;  // slab too large for this ring geometry
         const int smem = (int)(K_ * NS * slot_vecs * 16 + flat_ctl_bytes());
@@ -359,9 +382,14 @@ int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, con
         fp->g.PV = (unsigned)bestPV;
         fp->g.T = (unsigned)(slabs * bestP);
         fp->g.K = (unsigned)K_;
-        fp->g.L = (unsigned)L_;
+        fp->g.NG = (unsigned)NG;
+        fp->g.Lg = (unsigned)Lg;
         fp->g.slot_vecs = (unsigned)slot_vecs;
         fp->g.epoch = next_epoch();
+        const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
+        fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 500);
+        fp->g.poll_backoff_ns = (unsigned)(pb >= 0 ? pb : 200);
+        fp->g.trace = reinterpret_cast<long long*>(g_opt.flat_trace.load());
         fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
         fp->smem = smem;
         return 0;
@@ -380,7 +408,7 @@ int launch_flat(K kernel, const P& p, const FlatPlan& fp, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on each other's records
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_opt.flat_coop.load() == 0 ? 0 : 1;
     FlatGeom g = fp.g;
     return (int)cudaLaunchKernelEx(&cfg, kernel, p, g);
 }

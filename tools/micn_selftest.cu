@@ -89,7 +89,7 @@ struct Case {
     long long pad_c = 0;      // extra elements between channel slabs of x (strided input)
     long long misalign = 0;   // element offset applied to every buffer (unaligned path)
     int cs = -1, slots = -1, max_clusters = -1, force_path = -1, tps = -1;
-    int fslots = -1, flag = -1, fpv = -1, fgrid = -1, fovh = -1;  // flat path knobs
+    int fslots = -1, flag = -1, fpv = -1, fgrid = -1, fovh = -1, fcoop = -1, fgroups = -1, fpd = -1, fpb = -1;  // flat path knobs
     int num_styles = 2;
     bool affine = true;
     float mean = 1.0f, stdv = 2.0f;
@@ -136,6 +136,10 @@ static void set_opts(const Case& c) {
     micn_set_option("flat_piece_vecs", c.fpv);
     micn_set_option("flat_grid", c.fgrid);
     micn_set_option("flat_ovh_vecs", c.fovh);
+    micn_set_option("flat_coop", c.fcoop);
+    micn_set_option("flat_groups", c.fgroups);
+    micn_set_option("flat_poll_delay_ns", c.fpd);
+    micn_set_option("flat_poll_backoff_ns", c.fpb);
 }
 
 static int run_correctness(const Case& c, bool verbose) {
@@ -486,7 +490,7 @@ int main(int argc, char** argv) {
     double peak = 6542.1;
     long long oN = 1, oC = 48, oS = 96, oM = -1;
     int odt = MICN_BF16, oepi = MICN_EPI_NONE, ocs = -1, oslots = -1, oiters = 30, omaxcl = -1;
-    int opath = -1, ofslots = -1, oflag = -1, ofpv = -1, ofgrid = -1, ofovh = -1;
+    int opath = -1, ofslots = -1, oflag = -1, ofpv = -1, ofgrid = -1, ofovh = -1, ofcoop = -1, ofgroups = -1, ofpd = -1, ofpb = -1;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--suite") && i + 1 < argc) suite = argv[++i];
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
@@ -508,6 +512,10 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--fpv") && i + 1 < argc) ofpv = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fgrid") && i + 1 < argc) ofgrid = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fovh") && i + 1 < argc) ofovh = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fcoop") && i + 1 < argc) ofcoop = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fgroups") && i + 1 < argc) ofgroups = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fpd") && i + 1 < argc) ofpd = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fpb") && i + 1 < argc) ofpb = atoi(argv[++i]);
     }
     g_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     if (g_threads > 32) g_threads = 32;
@@ -564,11 +572,17 @@ int main(int argc, char** argv) {
                 Case c2 = mk("flat_tinypieces_emptywarps", 2, 4, 16384, dt, epi);  // pieces < 512 vectors: idle warps
                 c2.fpv = 200; c2.force_path = 2;
                 cs.push_back(c2);
-                Case d2 = mk("flat_lag1_slots3", 2, 4, 110592, dt, epi);
-                d2.flag = 1; d2.fslots = 3;
+                Case d2 = mk("flat_1group_lag1_slots3", 2, 4, 110592, dt, epi);
+                d2.flag = 1; d2.fslots = 3; d2.fgroups = 1;
                 cs.push_back(d2);
-                Case e2 = mk("flat_lag3_slots5_128^3", 1, 1, 2097152, dt, epi);  // a slab spanning 3+ rounds
-                e2.flag = 3; e2.fslots = 5;
+                Case e2 = mk("flat_4groups_128^3_multiround", 1, 1, 2097152, dt, epi);  // one slab spanning several rounds
+                e2.fgroups = 4; e2.flag = 2; e2.fslots = 16; e2.fpv = 512;
+                cs.push_back(e2);
+                e2 = mk("flat_8groups_lag1", 2, 3, 110592, dt, epi);
+                e2.fgroups = 8; e2.flag = 1; e2.fslots = 24;
+                cs.push_back(e2);
+                e2 = mk("flat_4groups_lag3", 2, 3, 65536, dt, epi);
+                e2.fgroups = 4; e2.flag = 3; e2.fslots = 20;
                 cs.push_back(e2);
                 Case f2 = mk("flat_strided_x", 2, 3, 65536, dt, epi);
                 f2.pad_c = 64;
@@ -646,14 +660,14 @@ int main(int argc, char** argv) {
     if (suite == "check") {
         Case c = mk("check", oN, oC, oM > 0 ? oM : oS * oS * oS, odt, oepi);
         c.cs = ocs; c.slots = oslots; c.max_clusters = omaxcl;
-        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fgroups = ofgroups; c.fpd = ofpd; c.fpb = ofpb;
         fails += run_correctness(c, true);
     }
     if (suite == "one") {
         const long long M = oS * oS * oS;
         Case c = mk("one", oN, oC, M, odt, oepi);
         c.cs = ocs; c.slots = oslots; c.max_clusters = omaxcl;
-        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fgroups = ofgroups; c.fpd = ofpd; c.fpb = ofpb;
         PerfResult r = run_perf(c, oiters, 3);
         const double E = (double)oN * oC * M * esize(odt);
         const double fb = (oepi == MICN_EPI_ADD_LRELU ? 3 : 2) * E, bb = (oepi == MICN_EPI_ADD_LRELU ? 4 : 3) * E;
@@ -663,6 +677,56 @@ int main(int argc, char** argv) {
                oN, oC, oS, dname(odt), oepi, r.fwd_us, r.bwd_us, fb / r.fwd_us * 1e-3, bb / r.bwd_us * 1e-3,
                (fb + bb) / (r.fwd_us + r.bwd_us) * 1e-3, (fb + bb) / (r.fwd_us + r.bwd_us) * 1e-3 / peak, r.f_cs, r.f_slots,
                r.f_grid, r.b_cs, r.b_slots, r.b_grid);
+    }
+    if (suite == "trace") {
+        // per-piece SM-clock timeline of a few CTAs of the flat forward kernel (bring-up aid)
+        const long long M = oS * oS * oS;
+        Case c = mk("trace", oN, oC, M, odt, oepi);
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fgroups = ofgroups; c.fpd = ofpd; c.fpb = ofpb;
+        const size_t tb = (size_t)prop.multiProcessorCount * 64 * 16 * sizeof(long long);
+        long long* dtrace = nullptr;
+        CK(cudaMalloc(&dtrace, tb));
+        CK(cudaMemset(dtrace, 0, tb));
+        micn_set_option("flat_trace", (long long)(uintptr_t)dtrace);
+        PerfResult r = run_perf(c, 1, 2);
+        micn_set_option("flat_trace", 0);
+        std::vector<long long> ht(tb / sizeof(long long));
+        CK(cudaMemcpy(ht.data(), dtrace, tb, cudaMemcpyDeviceToHost));
+        printf("trace fwd_us %.2f bwd_us %.2f P=%lld K=%lld\n", r.fwd_us, r.bwd_us, r.f_cs, r.f_slots);
+        const char* names[12] = {"load", "p1b", "p1e", "pubb", "pube", "gab", "gapoll", "gae", "p2wait", "p2b", "p2e", "loadwait"};
+        const int nsm = prop.multiProcessorCount;
+        long long t0 = 0;  // earliest stamp of the launch (%globaltimer is one clock for all SMs)
+        for (size_t i = 0; i < ht.size(); ++i) if (ht[i] && (!t0 || ht[i] < t0)) t0 = ht[i];
+        // per round: when was the LAST record of the round published, and when did the gathers finish
+        printf("round:  last_p1e  last_pube  first_gae  last_gae  last_p2e   (ns since first stamp, over all CTAs)\n");
+        for (int j = 0; j < 64; ++j) {
+            long long lp1 = 0, lpub = 0, fga = 0, lga = 0, lp2 = 0;
+            for (int cta = 0; cta < nsm; ++cta) {
+                const long long* t = ht.data() + ((size_t)cta * 64 + j) * 16;
+                if (!t[2]) continue;
+                lp1 = std::max(lp1, t[2] - t0); lpub = std::max(lpub, t[4] - t0); lga = std::max(lga, t[7] - t0);
+                lp2 = std::max(lp2, t[10] - t0);
+                if (t[7] && (!fga || t[7] - t0 < fga)) fga = t[7] - t0;
+            }
+            if (!lp1) break;
+            printf("%5d %9lld %9lld %9lld %9lld %9lld\n", j, lp1, lpub, fga, lga, lp2);
+        }
+        const int ctas[3] = {0, 73, nsm - 1};
+        for (int ci = 0; ci < 3; ++ci) {
+            const long long* t = ht.data() + (size_t)ctas[ci] * 64 * 16;
+            printf("cta %d (ns since the launch's first stamp)\n  j ", ctas[ci]);
+            for (int e = 0; e < 12; ++e) printf("%9s", names[e]);
+            printf("\n");
+            for (int j = 0; j < 64; ++j) {
+                bool any = false;
+                for (int e = 0; e < 12; ++e) any = any || t[j * 16 + e];
+                if (!any) break;
+                printf("%3d ", j);
+                for (int e = 0; e < 12; ++e) printf("%9lld", t[j * 16 + e] ? t[j * 16 + e] - t0 : -1);
+                printf("\n");
+            }
+        }
+        cudaFree(dtrace);
     }
     if (suite == "perf" || suite == "all") {
         FILE* fo = out.empty() ? nullptr : fopen(out.c_str(), "w");
