@@ -314,87 +314,68 @@ int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, con
     long long ovh = g_opt.flat_ovh_vecs.load();
     if (ovh < 0) ovh = 256;
 
-    // (groups, per-group lag, slots) candidates, preferred first; forced values replace the list.
-    // Requirements (micn_flat.cuh): K a multiple of NG, K >= (Lg+1)*NG + 1, and a slab of P pieces spans R = ceil((P-1)/G)+1
-    // rounds with R - 1 <= Lg*NG and R <= K.
-    struct Cand { long long ng, lag, slots; };
-    Cand cands[4];
-    int ncand = 0;
-    if (NS == 1) {
-        cands[ncand++] = {2, 3, 12};
-        cands[ncand++] = {2, 3, 10};
-        cands[ncand++] = {2, 2, 8};
-        cands[ncand++] = {1, 4, 6};
-    } else {
-        cands[ncand++] = {2, 2, 8};
-        cands[ncand++] = {1, 4, 7};
-        cands[ncand++] = {1, 4, 6};
-        cands[ncand++] = {1, 3, 5};
-    }
-    const long long fK = g_opt.flat_slots.load(), fL = g_opt.flat_lag.load(), fG = g_opt.flat_groups.load();
-    if (fK > 0 || fL > 0 || fG > 0) {
-        long long ng = fG > 0 ? fG : cands[0].ng;
-        if (ng != 1 && ng != 2 && ng != 4 && ng != 8 && ng != 16) ng = 2;
-        long long lag = fL > 0 ? fL : cands[0].lag;
-        long long slots = fK > 0 ? fK : cands[0].slots;
-        if (slots > kFlatMaxSlots) slots = kFlatMaxSlots;
-        slots -= slots % ng;  // a slot must always belong to the same consumer group
-        if (slots < (lag + 1) * ng + 1) lag = (slots - 1) / ng - 1;
-        if (lag < 1) return 1;
-        cands[0] = {ng, lag, slots};
-        ncand = 1;
-    }
-    for (int ci = 0; ci < ncand; ++ci) {
-        const long long NG = cands[ci].ng, Lg = cands[ci].lag, K_ = cands[ci].slots;
-        const long long slot_vecs = (ring / (K_ * NS * 16)) & ~7LL;
-        if (slot_vecs < kFlatMinPieceVecs) continue;
-        long long pvmax = slot_vecs;
-        const long long cap = g_opt.flat_piece_vecs.load();
-        if (cap >= kFlatMinPieceVecs && cap < pvmax) pvmax = cap;
-        // R - 1 = ceil((P-1)/G) <= min(Lg*NG, K-1)
-        const long long span = std::min<long long>(Lg * NG, K_ - 1);
-        const long long pmax_hw = std::min<long long>(kFlatMaxPieces, span * G + 1);
-        const long long P0 = (V + pvmax - 1) / pvmax;
-        if (P0 > pmax_hw) continue;  // slab too large for this ring geometry
-        const int smem = (int)(K_ * NS * slot_vecs * 16 + flat_ctl_bytes());
-        if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) continue;
-        const long long Pend =
-            std::min<long long>(pmax_hw, std::max<long long>(P0, (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs));
-        double best = 1e300;
-        long long bestP = 0, bestPV = 0;
-        for (long long P = P0; P <= Pend; ++P) {
-            const long long PV = (V + P - 1) / P;
-            const long long Pe = (V + PV - 1) / PV;
-            if (Pe != P) continue;  // same split as a smaller P: already scored
-            const long long T = slabs * Pe;
-            if (T > 0x7fffffffLL) break;
-            const long long rounds = (T + G - 1) / G;
-            const double cost = (double)rounds * (double)(PV + ovh);
-            if (cost < best * 0.9999) {
-                best = cost;
-                bestP = Pe;
-                bestPV = PV;
-            }
+    long long K_ = g_opt.flat_slots.load();
+    if (K_ <= 0) K_ = 5;
+    if (K_ < 2) K_ = 2;
+    if (K_ > kFlatMaxSlots) K_ = kFlatMaxSlots;
+    const long long slot_vecs = (ring / (K_ * NS * 16)) & ~7LL;
+    if (slot_vecs < kFlatMinPieceVecs) return 1;
+    long long pvmax = slot_vecs;
+    const long long cap = g_opt.flat_piece_vecs.load();
+    if (cap >= kFlatMinPieceVecs && cap < pvmax) pvmax = cap;
+    // a slab of P pieces spans R = ceil((P-1)/G)+1 rounds and P2 trails P1 by L >= R - 1 steps (L <= kFlatMaxLag)
+    const long long pmax_hw = std::min<long long>(kFlatMaxPieces, (long long)kFlatMaxLag * G + 1);
+    const long long P0 = (V + pvmax - 1) / pvmax;
+    if (P0 > pmax_hw) return 1;  // slab too large: not ours
+    const int smem = (int)(K_ * NS * slot_vecs * 16 + flat_ctl_bytes());
+    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) return 1;
+    const long long Pend =
+        std::min<long long>(pmax_hw, std::max<long long>(P0, (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs));
+    double best = 1e300;
+    long long bestP = 0, bestPV = 0;
+    for (long long P = P0; P <= Pend; ++P) {
+        const long long PV = (V + P - 1) / P;
+        const long long Pe = (V + PV - 1) / PV;
+        if (Pe != P) continue;  // same split as a smaller P: already scored
+        const long long T = slabs * Pe;
+        if (T > 0x7fffffffLL) break;
+        const long long rounds = (T + G - 1) / G;
+        const double cost = (double)rounds * (double)(PV + ovh);
+        if (cost < best * 0.9999) {
+            best = cost;
+            bestP = Pe;
+            bestPV = PV;
         }
-        if (!bestP) continue;
-        fp->g.V = (unsigned long long)V;
-        fp->g.P = (unsigned)bestP;
-        fp->g.PV = (unsigned)bestPV;
-        fp->g.T = (unsigned)(slabs * bestP);
-        fp->g.K = (unsigned)K_;
-        fp->g.NG = (unsigned)NG;
-        fp->g.Lg = (unsigned)Lg;
-        fp->g.slot_vecs = (unsigned)slot_vecs;
-        fp->g.epoch = next_epoch();
-        const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
-        fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 500);
-        fp->g.poll_backoff_ns = (unsigned)(pb >= 0 ? pb : 200);
-        fp->g.trace = reinterpret_cast<long long*>(g_opt.flat_trace.load());
-        fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
-        fp->smem = smem;
-        return 0;
     }
-    return 1;
+    if (!bestP) return 1;
+    // lag: long enough for the exchange (several microseconds), short enough that the L*G pieces waiting for
+    // their second touch stay well inside the 126 MB L2
+    long long L_ = g_opt.flat_lag.load();
+    if (L_ <= 0) {
+        L_ = 6;
+        const double piece_bytes = (double)bestPV * 16.0 * NS;
+        while (L_ > 2 && (double)L_ * (double)G * piece_bytes > 40e6) --L_;
+    }
+    const long long need = (bestP - 1 + G - 1) / G;  // R - 1
+    if (L_ < need) L_ = need;
+    if (L_ < 1) L_ = 1;
+    if (L_ > kFlatMaxLag) return 1;
+
+    fp->g.V = (unsigned long long)V;
+    fp->g.P = (unsigned)bestP;
+    fp->g.PV = (unsigned)bestPV;
+    fp->g.T = (unsigned)(slabs * bestP);
+    fp->g.K = (unsigned)K_;
+    fp->g.L = (unsigned)L_;
+    fp->g.slot_vecs = (unsigned)slot_vecs;
+    fp->g.epoch = next_epoch();
+    const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
+    fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 1000);
+    fp->g.poll_backoff_ns = (unsigned)(pb >= 0 ? pb : 200);
+    fp->g.trace = reinterpret_cast<long long*>(g_opt.flat_trace.load());
+    fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
+    fp->smem = smem;
+    return 0;
 }
 
 template <typename K, typename P>

@@ -5,13 +5,13 @@ out=${1:-gpurun_out/flat_sweep.jsonl}
 run() { echo "# $*" >> $out; timeout 120 tools/micn_selftest --suite one "$@" | grep '^{' >> $out; }
 for dt in bf16 fp32; do
   run --N 1 --C 48 --S 96 --dtype $dt
-  for cfg in "1 4 6" "1 6 9" "1 8 12" "2 2 8" "2 3 10" "2 3 12" "2 4 12" "2 4 16" "2 5 14" "4 1 12" "4 2 16" "4 3 20" "8 1 20" "8 1 24"; do
-    set -- $cfg
-    run --N 1 --C 48 --S 96 --dtype $dt --fgroups $1 --flag $2 --fslots $3
-  done
-  run --N 1 --C 48 --S 96 --dtype $dt --fgroups 2 --flag 3 --fslots 12 --fpd 0
-  run --N 1 --C 48 --S 96 --dtype $dt --fgroups 2 --flag 3 --fslots 12 --fpd 1500
-  run --N 1 --C 48 --S 96 --dtype $dt --fgroups 2 --flag 3 --fslots 12 --fpb 50
+  for k in 3 4 5 6 8; do run --N 1 --C 48 --S 96 --dtype $dt --fslots $k; done
+  for l in 1 2 3 4 8 12; do run --N 1 --C 48 --S 96 --dtype $dt --flag $l; done
+  run --N 1 --C 48 --S 96 --dtype $dt --fslots 4 --flag 4
+  run --N 1 --C 48 --S 96 --dtype $dt --fslots 4 --flag 8
+  run --N 1 --C 48 --S 96 --dtype $dt --fslots 8 --flag 8
+  run --N 1 --C 48 --S 96 --dtype $dt --fpd 0
+  run --N 1 --C 48 --S 96 --dtype $dt --fpd 2500
   run --N 4 --C 48 --S 96 --dtype $dt
 done
 run --N 4 --C 96 --S 48 --dtype bf16

@@ -572,17 +572,17 @@ int main(int argc, char** argv) {
                 Case c2 = mk("flat_tinypieces_emptywarps", 2, 4, 16384, dt, epi);  // pieces < 512 vectors: idle warps
                 c2.fpv = 200; c2.force_path = 2;
                 cs.push_back(c2);
-                Case d2 = mk("flat_1group_lag1_slots3", 2, 4, 110592, dt, epi);
-                d2.flag = 1; d2.fslots = 3; d2.fgroups = 1;
+                Case d2 = mk("flat_lag1_slots2", 2, 4, 110592, dt, epi);
+                d2.flag = 1; d2.fslots = 2;
                 cs.push_back(d2);
-                Case e2 = mk("flat_4groups_128^3_multiround", 1, 1, 2097152, dt, epi);  // one slab spanning several rounds
-                e2.fgroups = 4; e2.flag = 2; e2.fslots = 16; e2.fpv = 512;
+                Case e2 = mk("flat_128^3_multiround", 1, 1, 2097152, dt, epi);  // one slab spanning several rounds
+                e2.fslots = 8; e2.fpv = 512;
                 cs.push_back(e2);
-                e2 = mk("flat_8groups_lag1", 2, 3, 110592, dt, epi);
-                e2.fgroups = 8; e2.flag = 1; e2.fslots = 24;
+                e2 = mk("flat_lag12_slots8", 2, 3, 110592, dt, epi);
+                e2.flag = 12; e2.fslots = 8; e2.fpv = 300;
                 cs.push_back(e2);
-                e2 = mk("flat_4groups_lag3", 2, 3, 65536, dt, epi);
-                e2.fgroups = 4; e2.flag = 3; e2.fslots = 20;
+                e2 = mk("flat_lag3_slots3", 2, 3, 65536, dt, epi);
+                e2.flag = 3; e2.fslots = 3;
                 cs.push_back(e2);
                 Case f2 = mk("flat_strided_x", 2, 3, 65536, dt, epi);
                 f2.pad_c = 64;
