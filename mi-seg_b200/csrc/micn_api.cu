@@ -30,20 +30,24 @@ namespace {
 struct Options {
     std::atomic<long long> cluster_size{-1};  // force CS (1..16)
     std::atomic<long long> force_path{-1};    // 0 small, 1 cluster, 2 flat
-    std::atomic<long long> flat_slots{-1};    // ring slots K of the flat path
-    std::atomic<long long> flat_lag{-1};      // per consumer group, pieces P2 trails P1
-    std::atomic<long long> flat_groups{-1};   // consumer groups NG
+    std::atomic<long long> flat_slots{-1};    // ring A slots (first touch, HBM) of the flat path
+    std::atomic<long long> flat_slots_b{-1};  // ring B slots (second touch, L2)
+    std::atomic<long long> flat_lag{-1};      // steps P2 trails P1
+    std::atomic<long long> flat_l2_mb{-1};    // L2 budget (MB) the lag is sized for
+    std::atomic<long long> flat_prefer_p1{-1};  // (unused)
+    std::atomic<long long> flat_groups{-1};   // (unused; kept so old option scripts do not fail)
     std::atomic<long long> flat_poll_delay_ns{-1}, flat_poll_backoff_ns{-1};
     std::atomic<long long> flat_piece_vecs{-1};  // cap on vectors per piece
     std::atomic<long long> flat_min_bytes{-1};   // smallest slab the flat path takes
     std::atomic<long long> flat_grid{-1};     // cap on the persistent grid
     std::atomic<long long> flat_ovh_vecs{-1}; // planner: per-piece overhead in vector-equivalents
     std::atomic<long long> flat_coop{-1};     // 0: plain launch instead of a cooperative one (experiments)
+    std::atomic<long long> flat_trace_which{0};  // 0 both, 1 forward only, 2 backward only
     std::atomic<long long> flat_trace{0};     // bring-up: device pointer of a [grid][64][16] int64 trace buffer
     std::atomic<long long> slots{-1};         // force ring slots S
     std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
     std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
-    std::atomic<long long> last_path{-1}, last_cs{-1}, last_slots{-1}, last_grid{-1};  // read-back of the last plan
+    std::atomic<long long> last_path{-1}, last_cs{-1}, last_slots{-1}, last_grid{-1}, last_lag{-1};  // read-back of the last plan
     std::atomic<long long> launches{0};       // kernels launched by this library (bench "gpu_launches")
     std::atomic<long long> sm_bw_mbps{90000};   // per-SM bandwidth cap used by the planner (MB/s)
     std::atomic<long long> hbm_bw_mbps{6500000};
@@ -57,11 +61,12 @@ struct OptName {
 const OptName kOptNames[] = {
     {"cluster_size", &g_opt.cluster_size}, {"force_path", &g_opt.force_path}, {"slots", &g_opt.slots},
     {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps},   {"last_path", &g_opt.last_path},
-    {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid},
+    {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid}, {"last_lag", &g_opt.last_lag},
     {"launches", &g_opt.launches},         {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
     {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace}, {"flat_groups", &g_opt.flat_groups},
+    {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb}, {"flat_prefer_p1", &g_opt.flat_prefer_p1},
     {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
 
@@ -305,30 +310,38 @@ int flat_blocks_per_sm(K kernel, int smem, int smem_optin) {
 
 // returns 0 and fills *fp when the flat path can take the problem, 1 when it cannot, < 0 / > 0 codes on error
 template <typename KernelT>
-int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, const DeviceInfo& d, FlatPlan* fp) {
+int plan_flat(KernelT kernel, int NS, long long slabs, long long C, long long slab_bytes, const DeviceInfo& d,
+              FlatPlan* fp) {
     long long G = d.sm_count;
     const long long gcap = g_opt.flat_grid.load();
     if (gcap > 0 && gcap < G) G = gcap;
     const long long V = slab_bytes / 16;
     const long long ring = (long long)d.smem_optin - flat_ctl_bytes() - 128;
     long long ovh = g_opt.flat_ovh_vecs.load();
-    if (ovh < 0) ovh = 256;
+    if (ovh < 0) ovh = 128;
 
-    long long K_ = g_opt.flat_slots.load();
-    if (K_ <= 0) K_ = 5;
-    if (K_ < 2) K_ = 2;
-    if (K_ > kFlatMaxSlots) K_ = kFlatMaxSlots;
-    const long long slot_vecs = (ring / (K_ * NS * 16)) & ~7LL;
-    if (slot_vecs < kFlatMinPieceVecs) return 1;
-    long long pvmax = slot_vecs;
+    // ring A holds the bytes in flight from HBM: ~96 KB per SM streams at the full read rate (tools/streambw.cu),
+    // anything deeper only adds queueing delay to the record exchange; ring B re-reads from L2
+    long long KA = g_opt.flat_slots.load(), KB = g_opt.flat_slots_b.load();
+    if (KA <= 0) KA = NS == 1 ? 6 : 4;
+    if (KB <= 0) KB = NS == 1 ? 3 : 2;
+    KA = std::min<long long>(std::max<long long>(KA, 2), kFlatMaxSlots);
+    KB = std::min<long long>(std::max<long long>(KB, 2), kFlatMaxSlots);
+    long long pvmax = NS == 1 ? 1024 : (NS == 2 ? 1024 : 512);  // 16 KB / 32 KB / 24 KB per slot
     const long long cap = g_opt.flat_piece_vecs.load();
-    if (cap >= kFlatMinPieceVecs && cap < pvmax) pvmax = cap;
-    // a slab of P pieces spans R = ceil((P-1)/G)+1 rounds and P2 trails P1 by L >= R - 1 steps (L <= kFlatMaxLag)
-    const long long pmax_hw = std::min<long long>(kFlatMaxPieces, (long long)kFlatMaxLag * G + 1);
+    if (cap >= kFlatMinPieceVecs) pvmax = cap;
+    const long long fit = (ring / ((KA + KB) * NS * 16)) & ~7LL;
+    if (pvmax > fit) pvmax = fit;
+    if (pvmax > V) pvmax = V;
+    if (pvmax < kFlatMinPieceVecs) return 1;
+    const long long slot_vecs = (pvmax + 7) & ~7LL;
+    const int smem = (int)((KA + KB) * NS * slot_vecs * 16 + flat_ctl_bytes());
+    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) return 1;
+
+    // a slab of P pieces spans R = ceil((P-1)/G)+1 rounds; P2 trails P1 by L >= R steps (L <= kFlatMaxLag)
+    const long long pmax_hw = std::min<long long>(kFlatMaxPieces, (long long)(kFlatMaxLag - 1) * G + 1);
     const long long P0 = (V + pvmax - 1) / pvmax;
     if (P0 > pmax_hw) return 1;  // slab too large: not ours
-    const int smem = (int)(K_ * NS * slot_vecs * 16 + flat_ctl_bytes());
-    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) return 1;
     const long long Pend =
         std::min<long long>(pmax_hw, std::max<long long>(P0, (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs));
     double best = 1e300;
@@ -340,37 +353,45 @@ int plan_flat(KernelT kernel, int NS, long long slabs, long long slab_bytes, con
         const long long T = slabs * Pe;
         if (T > 0x7fffffffLL) break;
         const long long rounds = (T + G - 1) / G;
-        const double cost = (double)rounds * (double)(PV + ovh);
+        // bytes cost what they are; the consumer loops cost whole 512-vector sweeps
+        const long long sweep = (PV + kFlatConsumerThreads - 1) / kFlatConsumerThreads * kFlatConsumerThreads;
+        const double cost = (double)rounds * (0.5 * (double)PV + 0.5 * (double)sweep + (double)ovh);
         if (cost < best * 0.9999) {
             best = cost;
             bestP = Pe;
             bestPV = PV;
         }
+        if (PV * 3 < pvmax) break;  // far past the useful range
     }
     if (!bestP) return 1;
-    // lag: long enough for the exchange (several microseconds), short enough that the L*G pieces waiting for
-    // their second touch stay well inside the 126 MB L2
+    // lag: long enough to cover the exchange at launch and at the tail (several microseconds of HBM time),
+    // short enough that the L*G pieces waiting for their second touch stay well inside the 126 MB L2
     long long L_ = g_opt.flat_lag.load();
     if (L_ <= 0) {
-        L_ = 6;
+        long long l2mb = g_opt.flat_l2_mb.load();
+        if (l2mb <= 0) l2mb = 40;
         const double piece_bytes = (double)bestPV * 16.0 * NS;
-        while (L_ > 2 && (double)L_ * (double)G * piece_bytes > 40e6) --L_;
+        L_ = (long long)((double)l2mb * 1e6 / ((double)G * piece_bytes));
+        if (L_ < 3) L_ = 3;
     }
-    const long long need = (bestP - 1 + G - 1) / G;  // R - 1
+    const long long need = (bestP - 1 + G - 1) / G + 1;  // R
     if (L_ < need) L_ = need;
-    if (L_ < 1) L_ = 1;
-    if (L_ > kFlatMaxLag) return 1;
+    if (L_ > kFlatMaxLag) L_ = kFlatMaxLag;
+    if (L_ < need) return 1;
 
     fp->g.V = (unsigned long long)V;
     fp->g.P = (unsigned)bestP;
     fp->g.PV = (unsigned)bestPV;
     fp->g.T = (unsigned)(slabs * bestP);
-    fp->g.K = (unsigned)K_;
+    fp->g.KA = (unsigned)KA;
+    fp->g.KB = (unsigned)KB;
     fp->g.L = (unsigned)L_;
     fp->g.slot_vecs = (unsigned)slot_vecs;
     fp->g.epoch = next_epoch();
+    fp->g.divP = fastdiv_make((unsigned)bestP);
+    fp->g.divC = fastdiv_make((unsigned)C);
     const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
-    fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 1000);
+    fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 500);
     fp->g.poll_backoff_ns = (unsigned)(pb >= 0 ? pb : 200);
     fp->g.trace = reinterpret_cast<long long*>(g_opt.flat_trace.load());
     fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
@@ -397,7 +418,8 @@ int launch_flat(K kernel, const P& p, const FlatPlan& fp, cudaStream_t st) {
 void record_flat(const FlatPlan& fp) {
     g_opt.last_path.store(2);
     g_opt.last_cs.store(fp.g.P);
-    g_opt.last_slots.store(fp.g.K);
+    g_opt.last_slots.store(fp.g.KA);
+    g_opt.last_lag.store(fp.g.L);
     g_opt.last_grid.store(fp.grid);
     g_opt.launches.fetch_add(1);
 }
@@ -419,8 +441,9 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         auto kernel = micn_fwd_flat_kernel<T, EPI>;
         FlatPlan fpl = {};
-        const int rc = plan_flat(kernel, 1, slabs, slab_bytes, d, &fpl);
+        const int rc = plan_flat(kernel, 1, slabs, p.C, slab_bytes, d, &fpl);
         if (rc == 0) {
+            if (g_opt.flat_trace_which.load() == 2) fpl.g.trace = nullptr;
             fpl.g.ws_piece = ws_flat->piece;
             fpl.g.ws_slab = ws_flat->slab;
             record_flat(fpl);
@@ -466,8 +489,9 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         auto kernel = micn_bwd_flat_kernel<T, EPI>;
         FlatPlan fpl = {};
-        const int rc = plan_flat(kernel, NS, slabs, slab_bytes, d, &fpl);
+        const int rc = plan_flat(kernel, NS, slabs, p.C, slab_bytes, d, &fpl);
         if (rc == 0) {
+            if (g_opt.flat_trace_which.load() == 1) fpl.g.trace = nullptr;
             fpl.g.ws_piece = ws_flat->piece;
             fpl.g.ws_slab = ws_flat->slab;
             record_flat(fpl);

@@ -283,6 +283,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the warp for a system-defined time; a warp choosing between two
+// rings must not)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -316,6 +331,49 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     while (!mbar_try_wait_cluster(bar, parity)) {
         if (((++spins) & 0x3ffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
     }
+}
+
+// Waits of helper warps and of consumers that have nothing else to do: try_wait with a suspend-time hint parks
+// the warp in hardware until the phase completes (or the hint expires) instead of spinning on issue slots the
+// working warps need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (((++spins) & 0x3fu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+    }
+}
+
+// x / d for x < 2^31 with a precomputed multiplier (host: fastdiv_make)
+struct FastDiv {
+    unsigned mul, shr;
+};
+__device__ __forceinline__ unsigned fastdiv(unsigned x, const FastDiv& d) {
+    return d.mul ? __umulhi(x, d.mul) >> d.shr : x;
+}
+inline FastDiv fastdiv_make(unsigned d) {
+    FastDiv f{0u, 0u};
+    if (d <= 1u) return f;  // mul == 0 marks the identity
+    unsigned lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const unsigned p = 31u + lg;
+    f.mul = (unsigned)(((1ull << p) + d - 1ull) / d);
+    f.shr = p - 32u;
+    return f;
 }
 
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {

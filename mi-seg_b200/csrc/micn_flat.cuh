@@ -1,38 +1,48 @@
 // micn_flat.cuh - flat-partition instance_cond forward / backward (sm_100a): the default large-slab path.
 //
-// Measured on B200 (tools/l2bw.cu, profiles/): HBM copy 6.5 TB/s, HBM read 7.3 TB/s, but reads that hit the
-// 126 MB L2 stream at 18-19 TB/s.  So the budget is HBM bytes, not L2<->SM bytes: a voxel should cross HBM
-// once per tensor, while a second look at it is cheap as long as it is still in L2.  Two designs were
-// built and measured before this one: cluster-per-slab (cannot balance 48 slabs on 148 SMs)
-// and a shared-memory-resident flat partition (the ~5-10 us cross-CTA exchange of the statistics cannot be
-// hidden behind 220 KB of shared memory per SM).
+// Measured on B200 (tools/l2bw.cu, tools/streambw.cu, profiles/): HBM copy 6.5 TB/s, HBM read 7.1-7.3 TB/s, reads
+// that hit the 126 MB L2 18-19 TB/s.  So the budget is HBM bytes, not L2<->SM bytes: a voxel should cross HBM
+// once per tensor, while a second look at it is cheap as long as it is still in L2.  A ring of 1-D TMA bulk
+// copies streams at the full HBM read rate from one persistent CTA per SM once 96 KB are in flight per SM
+// (6 slots x 16 KB: 7.1 TB/s; 3 x 8 KB: 3.8 TB/s) and costs the consumer warps no issue slots.  What the
+// earlier designs taught: cluster-per-slab cannot balance 48 slabs on 148 SMs;
+// shared-memory-resident pieces cannot hide the cross-CTA exchange; a 220 KB-deep prefetch turns the memory
+// system into a 5 us FIFO that every record store and poll queues in; helper warps that spin on mbarriers
+// steal the issue slots the bf16 math needs; a kernel that outgrows the instruction cache loses everything.
 //
 // How: every (n, c) slab is cut into P pieces of <= PV 16-byte vectors; piece g = slab*P + k belongs to
 // CTA g % G in its round g / G (G = one persistent CTA per SM, launched cooperatively so all are
 // co-resident): every SM carries the same share whatever N*C is.  A CTA walks its pieces j = 0, 1, ... in
-// steps; step s runs two TASKS, each a TMA load of a piece into a shared-memory slot plus a pass over it:
+// steps; step s runs two tasks, each fed by its own ring of shared-memory slots and its own TMA producer lane:
 //
-//     P1(s)      statistics of piece s            (first touch: HBM -> L2 -> SM, L2 evict_last)
-//     P2(s - L)  normalise / epilogue / backward formula of piece s - L, 128-bit streaming stores
-//                                                 (second touch L steps later: served by L2, evict_first)
+//     ring A: P1(s)      statistics of piece s          (first touch: HBM -> L2 -> SM, L2 evict_last)
+//     ring B: P2(s - L)  normalise / epilogue / backward formula of piece s - L, 128-bit streaming stores
+//                                                       (second touch L steps later: served by L2, evict_first)
 //
-// Between the two, the piece lives in L2 (L*G pieces, a few tens of MB), not in shared memory, so the lag L
-// can be as long as the exchange needs while all K slots keep prefetching.  Roles inside a CTA:
+// Between the two the piece lives in L2 (L*G pieces, a few tens of MB), not in shared memory.  At launch the
+// CTAs therefore read at full HBM speed for L steps while the first statistics are exchanged, and at the end
+// the backlog of L P2 tasks hides the last exchange.  Roles inside a CTA:
 //
-//   producer warp (1 lane)  issues the tasks' 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) in
-//                           order, up to K tasks ahead of the consumers.
-//   16 consumer warps       run the tasks in order out of shared memory (fp32 shifted sums + warp shuffle in
-//                           P1; FMA + pack + st.global.v4 in P2) and hand each slot straight back.
-//   2 publish warps         merge the 16 warp partials of a piece (Chan) and write the piece record to the
-//                           workspace as soon as its P1 is done; never wait on another CTA.
+//   producer A / B (1 lane each)  1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), KA / KB slots ahead;
+//                           B issues P2(j)'s copy as soon as P1(j) is through, so it is in the slot long before use.
+//   16 consumer warps       each warp owns a fixed 1/16 of every piece: fp32 shifted sums + warp shuffle in P1;
+//                           FMA + pack + st.global.v4 in P2.  Every wait parks the warp (try_wait + suspend hint).
+//   2 publish warps         fold the 16 warp partials of a piece and write the piece record to the workspace as
+//                           soon as its P1 is done; never wait on another CTA.
 //   8 gather warps          poll the P records of the piece's slab (batches of loads in flight, re-polled in
-//                           parallel), merge them in a fixed order (bit-identical in every CTA, no atomics)
+//                           parallel), fold them in a fixed order (bit-identical in every CTA, no atomics)
 //                           and publish the per-slab coefficients P2 needs; backward: also the per-slab
 //                           sums and, for the last sample of a channel, d(gamma)/d(beta) per style.
 //
+// Statistics are folded without a chain of divisions: partials (n, mean, M2) are summed about a common
+// reference `ref` (the first partial's mean - itself a mean, never an outlier) as
+//     A = sum n_q (mean_q - ref),  B = sum [M2_q + n_q (mean_q - ref)^2]   ->   mean = ref + A/N,  M2 = B - A^2/N
+// which is exact algebra, well conditioned because |mean_q - ref| is of the order of the spread, and uses one
+// division per fold.
+//
 // Cross-CTA exchange is by 16-byte self-validating records {a, tag, b, tag} (tag = per-launch epoch): no
 // counters to reset, an aborted launch cannot poison the next one.  Deadlock freedom: a slab of P pieces
-// spans R <= ceil((P-1)/G)+1 rounds and the planner keeps L >= R - 1, so every P1 a record depends on runs
+// spans R <= ceil((P-1)/G)+1 rounds and the planner keeps L >= R, so every P1 a record depends on runs
 // before anyone can block in a P2; publishes never block.  Every wait is bounded and traps instead of hanging.
 //
 // HBM traffic: forward reads x once and writes y once (2*E*s); backward reads x, dy [, act_out] once and
@@ -49,15 +59,16 @@ namespace micn {
 
 constexpr int kFlatConsumerWarps = 16;
 constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512
-constexpr int kFlatProducerWarp = kFlatConsumerWarps;
-constexpr int kFlatPublishWarp0 = kFlatConsumerWarps + 1;
+constexpr int kFlatProducerWarpA = kFlatConsumerWarps;
+constexpr int kFlatProducerWarpB = kFlatConsumerWarps + 1;
+constexpr int kFlatPublishWarp0 = kFlatConsumerWarps + 2;
 constexpr int kFlatPublishWarps = 2;
 constexpr int kFlatGatherWarp0 = kFlatPublishWarp0 + kFlatPublishWarps;
 constexpr int kFlatGatherWarps = 8;  // a gather is a multi-microsecond latency chain: keep several in flight
-constexpr int kFlatThreads = (kFlatConsumerWarps + 1 + kFlatPublishWarps + kFlatGatherWarps) * 32;  // 864
-constexpr int kFlatMaxSlots = 8;
-constexpr int kFlatNB = 16;          // per-piece control ring (partials, coefficients): piece j -> entry j % 16
-constexpr int kFlatMaxLag = 12;      // L <= kFlatNB - 4 (entry reuse needs NB > L plus the producer's run-ahead)
+constexpr int kFlatThreads = (kFlatConsumerWarps + 2 + kFlatPublishWarps + kFlatGatherWarps) * 32;  // 896
+constexpr int kFlatMaxSlots = 8;     // per ring
+constexpr int kFlatNB = 32;          // per-piece control ring (partials, coefficients): piece j -> entry j % 32
+constexpr int kFlatMaxLag = 30;      // L <= kFlatNB - 1: an entry is recycled only after its piece's P2 is done
 constexpr int kFlatMaxPieces = 1024; // pieces per slab (workspace sizing); the planner enforces the round bound
 constexpr int kFlatMinPieceVecs = 128;
 constexpr uint32_t kFlatTmaChunk = 32768;
@@ -67,11 +78,12 @@ struct FlatGeom {
     unsigned T;            // total pieces = num_slabs * P
     unsigned P;            // pieces per slab
     unsigned PV;           // vectors per piece (the last piece of a slab may be shorter)
-    unsigned K;            // shared-memory slots (TMA landing buffers)
+    unsigned KA, KB;       // shared-memory slots of ring A (P1) and ring B (P2)
     unsigned L;            // steps P2 trails P1
     unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
     unsigned epoch;        // per-launch tag of the workspace records (never 0)
     unsigned poll_delay_ns, poll_backoff_ns;
+    FastDiv divP, divC;    // piece index -> slab, slab -> sample
     uint4* ws_piece;       // [T] piece records
     uint4* ws_slab;        // [num_slabs] per-slab records (backward parameter gradients)
     long long* trace;      // bring-up only: [grid][kFlatTraceSteps][16] %globaltimer stamps (ns) per piece, or null
@@ -85,17 +97,16 @@ __device__ __forceinline__ void flat_trace(const FlatGeom& g, unsigned j, int ev
         g.trace[((size_t)blockIdx.x * kFlatTraceSteps + j) * 16 + ev] = (long long)globaltimer_ns();
 }
 
-// control block: slot barriers + the per-piece ring
+// control block: slot barriers of both rings + the per-piece ring
 __host__ __device__ constexpr int flat_ctl_bytes() {
-    return kFlatMaxSlots * (2 * 8 + 16) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 32 + 16);
+    return kFlatMaxSlots * (4 * 8 + 16) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 32);
 }
 
 struct FlatCtx {
-    uint32_t data0, full0, empty0, p1d0, coef0;  // shared::cta addresses
-    float* slot_prec;                            // [K][4]   slab constants of the task in the slot (backward)
+    uint32_t dataA, dataB, fullA, emptyA, fullB, emptyB, p1d0, coef0;  // shared::cta addresses
+    float* slot_prec;                            // [KA][4]  slab constants of the piece in the A slot (backward)
     float* warp_part;                            // [NB][16][4]
     float* coefv;                                // [NB][8]
-    float* prec;                                 // [NB][4]  slab constants of the piece (backward, for the gather)
     uint32_t stream_bytes, slot_bytes;
 };
 
@@ -104,21 +115,27 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
     FlatCtx c;
     c.stream_bytes = g.slot_vecs * 16u;
     c.slot_bytes = c.stream_bytes * NS;
-    c.data0 = smem_u32(smem);
-    unsigned char* ctl = smem + (size_t)g.K * c.slot_bytes;
-    c.full0 = smem_u32(ctl);
-    c.empty0 = c.full0 + kFlatMaxSlots * 8;
-    c.p1d0 = c.empty0 + kFlatMaxSlots * 8;
+    c.dataA = smem_u32(smem);
+    c.dataB = c.dataA + g.KA * c.slot_bytes;
+    unsigned char* ctl = smem + (size_t)(g.KA + g.KB) * c.slot_bytes;
+    c.fullA = smem_u32(ctl);
+    c.emptyA = c.fullA + kFlatMaxSlots * 8;
+    c.fullB = c.emptyA + kFlatMaxSlots * 8;
+    c.emptyB = c.fullB + kFlatMaxSlots * 8;
+    c.p1d0 = c.emptyB + kFlatMaxSlots * 8;
     c.coef0 = c.p1d0 + kFlatNB * 8;
-    float* f = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 16 + kFlatNB * 16);
+    float* f = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 32 + kFlatNB * 16);
     c.slot_prec = f;
     c.warp_part = c.slot_prec + kFlatMaxSlots * 4;
     c.coefv = c.warp_part + kFlatNB * kFlatConsumerWarps * 4;
-    c.prec = c.coefv + kFlatNB * 8;
     if (threadIdx.x == 0) {
-        for (unsigned i = 0; i < g.K; ++i) {
-            mbar_init(c.full0 + 8 * i, 1);
-            mbar_init(c.empty0 + 8 * i, kFlatConsumerWarps);
+        for (unsigned i = 0; i < g.KA; ++i) {
+            mbar_init(c.fullA + 8 * i, 1);
+            mbar_init(c.emptyA + 8 * i, kFlatConsumerWarps);
+        }
+        for (unsigned i = 0; i < g.KB; ++i) {
+            mbar_init(c.fullB + 8 * i, 1);
+            mbar_init(c.emptyB + 8 * i, kFlatConsumerWarps);
         }
         for (unsigned i = 0; i < kFlatNB; ++i) {
             mbar_init(c.p1d0 + 8 * i, kFlatConsumerWarps);
@@ -139,13 +156,13 @@ __device__ __forceinline__ unsigned piece_vecs(const FlatGeom& g, unsigned k) {
 }
 __device__ __forceinline__ PieceId piece_of(const FlatGeom& g, unsigned gidx) {
     PieceId p;
-    p.slab = gidx / g.P;
+    p.slab = fastdiv(gidx, g.divP);
     p.k = gidx - p.slab * g.P;
     p.pv = piece_vecs(g, p.k);
     return p;
 }
 
-// ring cursors with phase parity: slots advance once per TASK, piece-ring entries once per PIECE
+// ring cursors with phase parity: slots advance once per task of their ring, piece-ring entries once per PIECE
 struct Ring {
     unsigned i, ph;
     __device__ __forceinline__ void next(unsigned n) {
@@ -176,11 +193,11 @@ __device__ __forceinline__ bool ll_try(const uint4* p, unsigned tag, float& a, f
 }
 
 // Poll the `count` records at `recs` (lane q handles records q, q+32, ...) and fold them with `fold(q, a, b)`
-// in ascending q per lane.  A batch of up to four loads per lane is in flight at once and the missing ones
+// in ascending q per lane; `first(a0, b0)` sees record 0 (the common reference) before any fold.  A batch of up to four loads per lane is in flight at once and the missing ones
 // are re-polled together, so a slab's record set costs one L2 round trip once everything is published.
-template <typename Fold>
+template <typename First, typename Fold>
 __device__ __forceinline__ void ll_gather(const uint4* recs, unsigned count, unsigned tag, unsigned backoff_ns, int lane,
-                                          Fold fold) {
+                                          First first, Fold fold) {
     for (unsigned q0 = 0; q0 < count; q0 += 128) {
         float a[4], b[4];
         bool ok[4];
@@ -200,6 +217,7 @@ __device__ __forceinline__ void ll_gather(const uint4* recs, unsigned count, uns
                 if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
             } while (!(ok[0] && ok[1] && ok[2] && ok[3]));
         }
+        if (q0 == 0) first(__shfl_sync(0xffffffffu, a[0], 0), __shfl_sync(0xffffffffu, b[0], 0));  // record 0
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const unsigned q = q0 + lane + 32 * i;
@@ -256,73 +274,87 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned C = (unsigned)p.C;
 
-    if (warp == kFlatProducerWarp) {
-        // ------------------------------------------------------------------ producer: tasks P1(s), P2(s-L) in order
+    if (warp == kFlatProducerWarpA || warp == kFlatProducerWarpB) {
+        // ------------------------------------------------------------------ producers (A: first touch, B: second touch)
         if (lane == 0) {
-            const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
+            const bool isA = warp == kFlatProducerWarpA;
+            const uint64_t pol = isA ? l2_policy_evict_last() : l2_policy_evict_first();
+            const unsigned K = isA ? g.KA : g.KB;
+            const uint32_t full0 = isA ? c.fullA : c.fullB, empty0 = isA ? c.emptyA : c.emptyB;
+            const uint32_t data0 = isA ? c.dataA : c.dataB;
             Ring r{0u, 0u};
-            unsigned t = 0;  // task counter
-            for (unsigned s = 0; s < nj + g.L; ++s) {
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (pass == 0 ? s >= nj : s < g.L) continue;
-                    const unsigned j = pass == 0 ? s : s - g.L;
-                    const PieceId pc = piece_of(g, j * G + cta);
-                    const unsigned n = pc.slab / C, ch = pc.slab - n * C;
-                    const char* src = reinterpret_cast<const char*>(p.x) +
-                                      ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) +
-                                      (size_t)pc.k * g.PV * 16;
-                    const uint32_t bytes = pc.pv * 16u, bar = c.full0 + 8 * r.i;
-                    if (t >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
-                    flat_trace(g, j, pass == 0 ? TR_LOAD : TR_LOAD2);
-                    flat_issue(c.data0 + r.i * c.slot_bytes, src, bytes, bar, pass == 0 ? pol_keep : pol_done);
-                    mbar_arrive_expect_tx(bar, bytes);
-                    r.next(g.K);
-                    ++t;
+            for (unsigned j = 0; j < nj; ++j) {
+                const PieceId pc = piece_of(g, j * G + cta);
+                const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+                const char* src = reinterpret_cast<const char*>(p.x) +
+                                  ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) +
+                                  (size_t)pc.k * g.PV * 16;
+                const uint32_t bytes = pc.pv * 16u, bar = full0 + 8 * r.i;
+                if (!isA) {  // the second touch must find the piece in L2: not before its first touch is through
+                    const Ring e = entry_of(j);
+                    mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
                 }
+                if (j >= K) mbar_wait_park(empty0 + 8 * r.i, r.ph ^ 1u);
+                flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
+                flat_issue(data0 + r.i * c.slot_bytes, src, bytes, bar, pol);
+                mbar_arrive_expect_tx(bar, bytes);
+                r.next(K);
             }
         }
-    } else if (warp > kFlatProducerWarp && warp < kFlatGatherWarp0) {
+    } else if (warp >= kFlatPublishWarp0 && warp < kFlatGatherWarp0) {
         // ------------------------------------------------------------------ publish: warp partials -> piece record
         for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
             const Ring e = entry_of(j);
             const unsigned gidx = j * G + cta;
-            const unsigned pv = piece_vecs(g, gidx % g.P);
-            const float nw = (float)(warp_vecs(pv, lane & 15) * VN);
-            mbar_wait(c.p1d0 + 8 * e.i, e.ph);
+            const unsigned k = gidx - fastdiv(gidx, g.divP) * g.P;
+            const unsigned pv = piece_vecs(g, k);
+            const float nw = lane < kFlatConsumerWarps ? (float)(warp_vecs(pv, lane) * VN) : 0.f;
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
             Stat st{0.f, 0.f, 0.f};
             if (lane < kFlatConsumerWarps) {
                 const float4 w = *reinterpret_cast<const float4*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
                 st = stat_from_shifted(w.z, w.x, w.y, nw);
             }
-            st = stat_warp_reduce(st);
-            if (lane == 0) ll_store(g.ws_piece + gidx, st.mean, st.m2, g.epoch);
+            // fold about the first warp's mean (see the file header)
+            const float ref = __shfl_sync(0xffffffffu, st.mean, 0);
+            const float d = st.n > 0.f ? st.mean - ref : 0.f;
+            const float A = warp_sum(st.n * d), B = warp_sum(fmaf(st.n * d, d, st.m2));
+            const float N = (float)(pv * VN);
+            const float m = A / N;
+            if (lane == 0) ll_store(g.ws_piece + gidx, ref + m, fmaxf(B - A * m, 0.f), g.epoch);
             if (lane == 0) flat_trace(g, j, TR_PUB_END);
         }
     } else if (warp >= kFlatGatherWarp0) {
         // ------------------------------------------------------------------ gather: slab records -> coefficients for P2
         for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
-            const Ring e = entry_of(j);  // kFlatNB is a multiple of both warp counts: an entry keeps its warps
+            const Ring e = entry_of(j);
             const PieceId pc = piece_of(g, j * G + cta);
-            const unsigned n = pc.slab / C, ch = pc.slab - n * C;
+            const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
             // parameter loads first: their latency hides behind everything below
             const int style = load_style(p.styles, n, p.num_styles, p.status);
             float gamma, beta;
             load_affine(p, style, ch, gamma, beta);
             // no polling before this CTA's own piece is through P1: the other CTAs are at the same point
-            mbar_wait(c.p1d0 + 8 * e.i, e.ph);
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             __nanosleep(g.poll_delay_ns);  // ... and let their record stores land
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
-            Stat acc{0.f, 0.f, 0.f};
+            float ref = 0.f, A = 0.f, B = 0.f;
             ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane,
+                      [&](float a0, float) { ref = a0; },
                       [&](unsigned q, float a, float b) {
-                          acc = stat_merge(acc, Stat{(float)(piece_vecs(g, q) * VN), a, b});
+                          const float nq = (float)(piece_vecs(g, q) * VN), d = a - ref;
+                          A = fmaf(nq, d, A);
+                          B += fmaf(nq * d, d, b);
                       });
             if (lane == 0) flat_trace(g, j, TR_GA_POLLED);
-            acc = stat_warp_reduce(acc);
+            A = warp_sum(A);
+            B = warp_sum(B);
             if (lane == 0) {
-                const float mean = acc.mean;
-                const float rstd = 1.f / sqrtf(acc.m2 / (float)p.M + p.eps);  // biased variance, eps inside the sqrt
+                const float invM = 1.f / (float)p.M;
+                const float m = A * invM;
+                const float mean = ref + m;
+                const float rstd = 1.f / sqrtf(fmaxf(B - A * m, 0.f) * invM + p.eps);  // biased variance, eps inside the sqrt
                 const float a = rstd * gamma;
                 // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element.
                 *reinterpret_cast<float4*>(c.coefv + e.i * 8) =
@@ -337,34 +369,47 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ consumers: the tasks, in the producer's order
-        Ring r{0u, 0u};
+        // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
+        Ring ra{0u, 0u}, rb{0u, 0u};
         for (unsigned s = 0; s < nj + g.L; ++s) {
-            if (s < nj) {  // P1(s): statistics; the slot goes straight back, the piece stays in L2
+            if (s < nj) {
+                // ---- P1(s): statistics; the slot goes straight back, the piece stays in L2
                 const Ring e = entry_of(s);
-                const unsigned pv = piece_vecs(g, (s * G + cta) % g.P);
-                mbar_wait(c.full0 + 8 * r.i, r.ph);
+                const unsigned gidx = s * G + cta;
+                const unsigned pv = piece_vecs(g, gidx - fastdiv(gidx, g.divP) * g.P);
+                mbar_wait_park(c.fullA + 8 * ra.i, ra.ph);
                 if (tid == 0) flat_trace(g, s, TR_P1_BEGIN);
-                const uint32_t base = c.data0 + r.i * c.slot_bytes;
+                const uint32_t base = c.dataA + ra.i * c.slot_bytes;
                 float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, Kw = 0.f;
                 if ((unsigned)warp * 32u < pv) {
                     Kw = first_elem<T>(base + warp * 512);  // shift = the warp's first element of the piece
-#pragma unroll 2
-                    for (unsigned v = tid; v < pv; v += kFlatConsumerThreads) {
-                        float f[VN];
-                        VecT<T>::unpack(lds128(base + v * 16), f);
+                    for (unsigned v0 = tid; v0 < pv; v0 += 4 * kFlatConsumerThreads) {
+                        uint4 q[4];
 #pragma unroll
-                        for (int k = 0; k < VN; k += 2) {
-                            const float d0 = f[k] - Kw, d1 = f[k + 1] - Kw;
-                            sa += d0;
-                            sb += d1;
-                            qa = fmaf(d0, d0, qa);
-                            qb = fmaf(d1, d1, qb);
+                        for (int i = 0; i < 4; ++i) {
+                            const unsigned v = v0 + i * kFlatConsumerThreads;
+                            if (v < pv) q[i] = lds128(base + v * 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const unsigned v = v0 + i * kFlatConsumerThreads;
+                            if (v < pv) {
+                                float f[VN];
+                                VecT<T>::unpack(q[i], f);
+#pragma unroll
+                                for (int k = 0; k < VN; k += 2) {
+                                    const float d0 = f[k] - Kw, d1 = f[k + 1] - Kw;
+                                    sa += d0;
+                                    sb += d1;
+                                    qa = fmaf(d0, d0, qa);
+                                    qb = fmaf(d1, d1, qb);
+                                }
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c.empty0 + 8 * r.i);
+                if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
                 const float s1 = warp_sum(sa + sb), s2 = warp_sum(qa + qb);
                 if (lane == 0) {
                     *reinterpret_cast<float4*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) =
@@ -372,47 +417,65 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
                     mbar_arrive(c.p1d0 + 8 * e.i);
                 }
                 if (tid == 0) flat_trace(g, s, TR_P1_END);
-                r.next(g.K);
+                ra.next(g.KA);
             }
-            if (s >= g.L) {  // P2(s - L): normalise + epilogue from the piece's second (L2-served) copy
+            if (s >= g.L) {
+                // ---- P2(s - L): normalise + epilogue from the piece's second (L2-served) copy
                 const unsigned j = s - g.L;
                 const Ring e = entry_of(j);
                 const PieceId pc = piece_of(g, j * G + cta);
                 const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
                 char* ydst = reinterpret_cast<char*>(p.y) + goff;
                 const char* rsrc = EPI == MICN_EPI_ADD_LRELU ? reinterpret_cast<const char*>(p.res) + goff : nullptr;
-                const uint32_t base = c.data0 + r.i * c.slot_bytes;
-                uint4 rv0 = make_uint4(0u, 0u, 0u, 0u);
-                if (EPI == MICN_EPI_ADD_LRELU && (unsigned)tid < pc.pv) rv0 = ldg_stream(rsrc + (size_t)tid * 16);
-                if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
-                mbar_wait(c.coef0 + 8 * e.i, e.ph);
-                const float4 cf = *reinterpret_cast<const float4*>(c.coefv + e.i * 8);
-                const float sub = cf.x, a = cf.y, b = cf.z;
-                mbar_wait(c.full0 + 8 * r.i, r.ph);
-                if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
-#pragma unroll 2
-                for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
-                    uint4 rv = rv0;
-                    if (EPI == MICN_EPI_ADD_LRELU) {  // residual straight from HBM, next one in flight
-                        const unsigned vn = v + kFlatConsumerThreads;
-                        if (vn < pc.pv) rv0 = ldg_stream(rsrc + (size_t)vn * 16);
-                    }
-                    float f[VN], rr[VN];
-                    VecT<T>::unpack(lds128(base + v * 16), f);
-                    if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(rv, rr);
+                const uint32_t base = c.dataB + rb.i * c.slot_bytes;
+                uint4 rv[2];
+                if (EPI == MICN_EPI_ADD_LRELU) {  // the first residual vectors: in flight while we wait below
 #pragma unroll
-                    for (int k = 0; k < VN; ++k) {
-                        float o = sizeof(T) == 4 ? fmaf(f[k] - sub, a, b) : fmaf(f[k], a, b);
-                        if (EPI == MICN_EPI_ADD_LRELU) o += rr[k];
-                        if (EPI != MICN_EPI_NONE) o = o > 0.f ? o : o * p.slope;
-                        f[k] = o;
+                    for (int i = 0; i < 2; ++i) {
+                        const unsigned v = tid + i * kFlatConsumerThreads;
+                        if (v < pc.pv) rv[i] = ldg_stream(rsrc + (size_t)v * 16);
                     }
-                    stg_stream(ydst + (size_t)v * 16, VecT<T>::pack(f));
+                }
+                if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
+                mbar_wait_park(c.coef0 + 8 * e.i, e.ph);
+                const float4 cf = *reinterpret_cast<const float4*>(c.coefv + e.i * 8);
+                const float sub = cf.x, ca = cf.y, cb = cf.z;
+                mbar_wait_park(c.fullB + 8 * rb.i, rb.ph);
+                if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
+                for (unsigned v0 = tid; v0 < pc.pv; v0 += 2 * kFlatConsumerThreads) {
+                    uint4 q[2], rc[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const unsigned v = v0 + i * kFlatConsumerThreads;
+                        if (v < pc.pv) q[i] = lds128(base + v * 16);
+                        if (EPI == MICN_EPI_ADD_LRELU) {  // this batch's residual; the next batch's goes in flight
+                            rc[i] = rv[i];
+                            const unsigned vn = v + 2 * kFlatConsumerThreads;
+                            if (vn < pc.pv) rv[i] = ldg_stream(rsrc + (size_t)vn * 16);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const unsigned v = v0 + i * kFlatConsumerThreads;
+                        if (v < pc.pv) {
+                            float f[VN], rr[VN];
+                            VecT<T>::unpack(q[i], f);
+                            if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(rc[i], rr);
+#pragma unroll
+                            for (int k = 0; k < VN; ++k) {
+                                float o = sizeof(T) == 4 ? fmaf(f[k] - sub, ca, cb) : fmaf(f[k], ca, cb);
+                                if (EPI == MICN_EPI_ADD_LRELU) o += rr[k];
+                                if (EPI != MICN_EPI_NONE) o = o > 0.f ? o : o * p.slope;
+                                f[k] = o;
+                            }
+                            stg_stream(ydst + (size_t)v * 16, VecT<T>::pack(f));
+                        }
+                    }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c.empty0 + 8 * r.i);
+                if (lane == 0) mbar_arrive(c.emptyB + 8 * rb.i);
                 if (tid == 0) flat_trace(g, j, TR_P2_END);
-                r.next(g.K);
+                rb.next(g.KB);
             }
         }
     }
@@ -433,10 +496,20 @@ __device__ __forceinline__ float bwd_masked(float x, float gy, float o, float me
     return gy;
 }
 
+// (mean, rstd, gamma, beta) of a slab
+template <typename P>
+__device__ __forceinline__ float4 slab_consts(const P& p, unsigned slab, unsigned n, unsigned ch) {
+    const int style = load_style(p.styles, n, p.num_styles, p.status);
+    float gamma, beta;
+    load_affine(p, style, ch, gamma, beta);
+    return make_float4(__ldg(p.save_mean + slab), __ldg(p.save_rstd + slab), gamma, beta);
+}
+
 template <typename T, int EPI>
 __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
     constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
     constexpr int VN = VecT<T>::N;
+    constexpr int U = NS == 3 ? 1 : 2;  // vectors per thread in flight per stream (register budget: 72)
     extern __shared__ __align__(128) unsigned char smem[];
     const FlatCtx c = flat_setup<NS>(smem, g);
     const unsigned cta = blockIdx.x, G = gridDim.x;
@@ -444,48 +517,47 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned C = (unsigned)p.C;
 
-    if (warp == kFlatProducerWarp) {
-        // ------------------------------------------------------------------ producer
+    if (warp == kFlatProducerWarpA || warp == kFlatProducerWarpB) {
+        // ------------------------------------------------------------------ producers (A: first touch, B: second touch)
         if (lane == 0) {
-            const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
+            const bool isA = warp == kFlatProducerWarpA;
+            const uint64_t pol = isA ? l2_policy_evict_last() : l2_policy_evict_first();
+            const unsigned K = isA ? g.KA : g.KB;
+            const uint32_t full0 = isA ? c.fullA : c.fullB, empty0 = isA ? c.emptyA : c.emptyB;
+            const uint32_t data0 = isA ? c.dataA : c.dataB;
             Ring r{0u, 0u};
-            unsigned t = 0;
-            for (unsigned s = 0; s < nj + g.L; ++s) {
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (pass == 0 ? s >= nj : s < g.L) continue;
-                    const unsigned j = pass == 0 ? s : s - g.L;
-                    const PieceId pc = piece_of(g, j * G + cta);
-                    const unsigned n = pc.slab / C, ch = pc.slab - n * C;
-                    float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (pass == 0) {  // per-slab constants for P1 and the gather: loads issued before the slot wait
-                        const int style = load_style(p.styles, n, p.num_styles, p.status);
-                        float gamma, beta;
-                        load_affine(p, style, ch, gamma, beta);
-                        pr = make_float4(__ldg(p.save_mean + pc.slab), __ldg(p.save_rstd + pc.slab), gamma, beta);
-                    }
-                    const size_t poff = (size_t)pc.k * g.PV * 16;
-                    const size_t doff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + poff;
-                    const char* xsrc = reinterpret_cast<const char*>(p.x) +
-                                       ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) + poff;
-                    const uint32_t bytes = pc.pv * 16u, bar = c.full0 + 8 * r.i;
-                    const uint32_t dst = c.data0 + r.i * c.slot_bytes;
-                    const uint64_t pol = pass == 0 ? pol_keep : pol_done;
-                    if (t >= g.K) mbar_wait(c.empty0 + 8 * r.i, r.ph ^ 1u);
-                    flat_issue(dst, xsrc, bytes, bar, pol);
-                    flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
-                    if (NS == 3) flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(p.act_out) + doff, bytes, bar, pol);
-                    if (pass == 0) *reinterpret_cast<float4*>(c.slot_prec + r.i * 4) = pr;  // visible through the barrier
-                    mbar_arrive_expect_tx(bar, bytes * NS);
-                    r.next(g.K);
-                    ++t;
+            for (unsigned j = 0; j < nj; ++j) {
+                const PieceId pc = piece_of(g, j * G + cta);
+                const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+                float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (isA) pr = slab_consts(p, pc.slab, n, ch);  // for P1: loads issued before the waits
+                const size_t poff = (size_t)pc.k * g.PV * 16;
+                const size_t doff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + poff;
+                const char* xsrc = reinterpret_cast<const char*>(p.x) +
+                                   ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) + poff;
+                const uint32_t bytes = pc.pv * 16u, bar = full0 + 8 * r.i;
+                const uint32_t dst = data0 + r.i * c.slot_bytes;
+                if (!isA) {
+                    const Ring e = entry_of(j);
+                    mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
                 }
+                if (j >= K) mbar_wait_park(empty0 + 8 * r.i, r.ph ^ 1u);
+                flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
+                flat_issue(dst, xsrc, bytes, bar, pol);
+                flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
+                if (NS == 3)
+                    flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(p.act_out) + doff, bytes, bar, pol);
+                if (isA) *reinterpret_cast<float4*>(c.slot_prec + r.i * 4) = pr;  // visible through the barrier
+                mbar_arrive_expect_tx(bar, bytes * NS);
+                r.next(K);
             }
         }
-    } else if (warp > kFlatProducerWarp && warp < kFlatGatherWarp0) {
+    } else if (warp >= kFlatPublishWarp0 && warp < kFlatGatherWarp0) {
         // ------------------------------------------------------------------ publish
         for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
             const Ring e = entry_of(j);
-            mbar_wait(c.p1d0 + 8 * e.i, e.ph);
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
+            if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
             float s1 = 0.f, s2 = 0.f;
             if (lane < kFlatConsumerWarps) {
                 const float2 w = *reinterpret_cast<const float2*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
@@ -495,6 +567,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
             if (lane == 0) ll_store(g.ws_piece + (j * G + cta), s1, s2, g.epoch);
+            if (lane == 0) flat_trace(g, j, TR_PUB_END);
         }
     } else if (warp >= kFlatGatherWarp0) {
         // ------------------------------------------------------------------ gather
@@ -502,19 +575,20 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
         for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
             const Ring e = entry_of(j);
             const PieceId pc = piece_of(g, j * G + cta);
-            const unsigned n = pc.slab / C, ch = pc.slab - n * C;
-            // no polling before this CTA's own piece is through P1 (the others are at the same point); the wait
-            // also makes the piece's slab constants (copied by consumer thread 0) visible
-            mbar_wait(c.p1d0 + 8 * e.i, e.ph);
-            const volatile float* pr = c.prec + e.i * 4;
-            const float mean = pr[0], rstd = pr[1], gamma = pr[2], beta = pr[3];
+            const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+            const float4 pr = slab_consts(p, pc.slab, n, ch);  // latency hides behind the wait below
+            const float mean = pr.x, rstd = pr.y, gamma = pr.z, beta = pr.w;
+            // no polling before this CTA's own piece is through P1 (the others are at the same point)
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             __nanosleep(g.poll_delay_ns);  // let the record stores land
+            if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float S1 = 0.f, S2 = 0.f;
-            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane,
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane, [](float, float) {},
                       [&](unsigned, float a, float b) {
                           S1 += a;
                           S2 += b;
                       });
+            if (lane == 0) flat_trace(g, j, TR_GA_POLLED);
             S1 = warp_sum(S1);
             S2 = warp_sum(S2);
             const float a = rstd * gamma;
@@ -526,6 +600,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                 *reinterpret_cast<float4*>(cf) = make_float4(a, B1, sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c), mean);
                 cf[4] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
                 mbar_arrive(c.coef0 + 8 * e.i);
+                flat_trace(g, j, TR_GA_END);
             }
             if (pc.k == 0 && p.dgamma) {
                 if (p.N == 1) {
@@ -562,76 +637,113 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ consumers
-        Ring r{0u, 0u};
+        // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
+        Ring ra{0u, 0u}, rb{0u, 0u};
         const uint32_t sb = c.stream_bytes;
         for (unsigned s = 0; s < nj + g.L; ++s) {
-            if (s < nj) {  // P1(s)
+            if (s < nj) {
+                // ---- P1(s)
                 const Ring e = entry_of(s);
-                const unsigned pv = piece_vecs(g, (s * G + cta) % g.P);
-                mbar_wait(c.full0 + 8 * r.i, r.ph);
-                const uint32_t base = c.data0 + r.i * c.slot_bytes;
-                const float4 pr = *reinterpret_cast<const float4*>(c.slot_prec + r.i * 4);
-                if (tid == 0) *reinterpret_cast<float4*>(c.prec + e.i * 4) = pr;  // for the gather, past the slot's life
-                const float mean = pr.x, a = pr.y * pr.z;
-                const float bq = sizeof(T) == 4 ? pr.w : fmaf(-mean, a, pr.w);
+                const unsigned gidx = s * G + cta;
+                const unsigned pv = piece_vecs(g, gidx - fastdiv(gidx, g.divP) * g.P);
+                mbar_wait_park(c.fullA + 8 * ra.i, ra.ph);
+                if (tid == 0) flat_trace(g, s, TR_P1_BEGIN);
+                const uint32_t base = c.dataA + ra.i * c.slot_bytes;
+                const float4 pr = *reinterpret_cast<const float4*>(c.slot_prec + ra.i * 4);
+                const float mean = pr.x, ca = pr.y * pr.z;
+                const float bq = sizeof(T) == 4 ? pr.w : fmaf(-mean, ca, pr.w);
                 float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll 2
-                for (unsigned v = tid; v < pv; v += kFlatConsumerThreads) {
-                    float xf[VN], gf[VN], of[VN];
-                    VecT<T>::unpack(lds128(base + v * 16), xf);
-                    VecT<T>::unpack(lds128(base + sb + v * 16), gf);
-                    if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(lds128(base + 2 * sb + v * 16), of);
+                for (unsigned v0 = tid; v0 < pv; v0 += U * kFlatConsumerThreads) {
+                    uint4 qx[U], qg[U], qo[U];
 #pragma unroll
-                    for (int k = 0; k < VN; k += 2) {
-                        const float g0 = bwd_masked<T, EPI>(xf[k], gf[k], EPI == MICN_EPI_ADD_LRELU ? of[k] : 0.f, mean, a, bq, p.slope);
-                        const float g1 = bwd_masked<T, EPI>(xf[k + 1], gf[k + 1], EPI == MICN_EPI_ADD_LRELU ? of[k + 1] : 0.f, mean, a, bq, p.slope);
-                        s1a += g0;
-                        s1b += g1;
-                        s2a = fmaf(g0, xf[k] - mean, s2a);
-                        s2b = fmaf(g1, xf[k + 1] - mean, s2b);
+                    for (int i = 0; i < U; ++i) {
+                        const unsigned v = v0 + i * kFlatConsumerThreads;
+                        if (v < pv) {
+                            qx[i] = lds128(base + v * 16);
+                            qg[i] = lds128(base + sb + v * 16);
+                            if (NS == 3) qo[i] = lds128(base + 2 * sb + v * 16);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < U; ++i) {
+                        const unsigned v = v0 + i * kFlatConsumerThreads;
+                        if (v < pv) {
+                            float xf[VN], gf[VN], of[VN];
+                            VecT<T>::unpack(qx[i], xf);
+                            VecT<T>::unpack(qg[i], gf);
+                            if (NS == 3) VecT<T>::unpack(qo[i], of);
+#pragma unroll
+                            for (int k = 0; k < VN; k += 2) {
+                                const float g0 = bwd_masked<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0.f, mean, ca, bq, p.slope);
+                                const float g1 = bwd_masked<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0.f, mean, ca, bq, p.slope);
+                                s1a += g0;
+                                s1b += g1;
+                                s2a = fmaf(g0, xf[k] - mean, s2a);
+                                s2b = fmaf(g1, xf[k + 1] - mean, s2b);
+                            }
+                        }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c.empty0 + 8 * r.i);
+                if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
                 const float s1 = warp_sum(s1a + s1b), s2 = warp_sum(s2a + s2b);
                 if (lane == 0) {
                     *reinterpret_cast<float2*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) = make_float2(s1, s2);
                     mbar_arrive(c.p1d0 + 8 * e.i);
                 }
-                r.next(g.K);
+                if (tid == 0) flat_trace(g, s, TR_P1_END);
+                ra.next(g.KA);
             }
-            if (s >= g.L) {  // P2(s - L)
+            if (s >= g.L) {
+                // ---- P2(s - L)
                 const unsigned j = s - g.L;
                 const Ring e = entry_of(j);
                 const PieceId pc = piece_of(g, j * G + cta);
                 const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
                 char* dxdst = reinterpret_cast<char*>(p.dx) + goff;
-                char* drdst = EPI == MICN_EPI_ADD_LRELU ? reinterpret_cast<char*>(p.dres) + goff : nullptr;
-                const uint32_t base = c.data0 + r.i * c.slot_bytes;
-                mbar_wait(c.coef0 + 8 * e.i, e.ph);
+                char* drdst = NS == 3 ? reinterpret_cast<char*>(p.dres) + goff : nullptr;
+                const uint32_t base = c.dataB + rb.i * c.slot_bytes;
+                if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
+                mbar_wait_park(c.coef0 + 8 * e.i, e.ph);
                 const float* cf = c.coefv + e.i * 8;
                 const float4 cq = *reinterpret_cast<const float4*>(cf);
                 const float A = cq.x, B1 = cq.y, B0 = cq.z, mean = cq.w, bq = cf[4];
-                mbar_wait(c.full0 + 8 * r.i, r.ph);
-#pragma unroll 2
-                for (unsigned v = tid; v < pc.pv; v += kFlatConsumerThreads) {
-                    float xf[VN], gf[VN], of[VN];
-                    VecT<T>::unpack(lds128(base + v * 16), xf);
-                    VecT<T>::unpack(lds128(base + sb + v * 16), gf);
-                    if (EPI == MICN_EPI_ADD_LRELU) VecT<T>::unpack(lds128(base + 2 * sb + v * 16), of);
+                mbar_wait_park(c.fullB + 8 * rb.i, rb.ph);
+                if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
+                for (unsigned v0 = tid; v0 < pc.pv; v0 += U * kFlatConsumerThreads) {
+                    uint4 qx[U], qg[U], qo[U];
 #pragma unroll
-                    for (int k = 0; k < VN; ++k) {
-                        const float gg = bwd_masked<T, EPI>(xf[k], gf[k], EPI == MICN_EPI_ADD_LRELU ? of[k] : 0.f, mean, A, bq, p.slope);
-                        gf[k] = gg;
-                        xf[k] = sizeof(T) == 4 ? fmaf(A, gg, fmaf(B1, xf[k] - mean, B0)) : fmaf(A, gg, fmaf(B1, xf[k], B0));
+                    for (int i = 0; i < U; ++i) {
+                        const unsigned v = v0 + i * kFlatConsumerThreads;
+                        if (v < pc.pv) {
+                            qx[i] = lds128(base + v * 16);
+                            qg[i] = lds128(base + sb + v * 16);
+                            if (NS == 3) qo[i] = lds128(base + 2 * sb + v * 16);
+                        }
                     }
-                    stg_stream(dxdst + (size_t)v * 16, VecT<T>::pack(xf));
-                    if (EPI == MICN_EPI_ADD_LRELU) stg_stream(drdst + (size_t)v * 16, VecT<T>::pack(gf));
+#pragma unroll
+                    for (int i = 0; i < U; ++i) {
+                        const unsigned v = v0 + i * kFlatConsumerThreads;
+                        if (v < pc.pv) {
+                            float xf[VN], gf[VN], of[VN];
+                            VecT<T>::unpack(qx[i], xf);
+                            VecT<T>::unpack(qg[i], gf);
+                            if (NS == 3) VecT<T>::unpack(qo[i], of);
+#pragma unroll
+                            for (int k = 0; k < VN; ++k) {
+                                const float gg = bwd_masked<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0.f, mean, A, bq, p.slope);
+                                gf[k] = gg;
+                                xf[k] = sizeof(T) == 4 ? fmaf(A, gg, fmaf(B1, xf[k] - mean, B0)) : fmaf(A, gg, fmaf(B1, xf[k], B0));
+                            }
+                            stg_stream(dxdst + (size_t)v * 16, VecT<T>::pack(xf));
+                            if (NS == 3) stg_stream(drdst + (size_t)v * 16, VecT<T>::pack(gf));
+                        }
+                    }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c.empty0 + 8 * r.i);
-                r.next(g.K);
+                if (lane == 0) mbar_arrive(c.emptyB + 8 * rb.i);
+                if (tid == 0) flat_trace(g, j, TR_P2_END);
+                rb.next(g.KB);
             }
         }
     }

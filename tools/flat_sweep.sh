@@ -3,21 +3,20 @@
 out=${1:-gpurun_out/flat_sweep.jsonl}
 : > $out
 run() { echo "# $*" >> $out; timeout 120 tools/micn_selftest --suite one "$@" | grep '^{' >> $out; }
+H="--N 1 --C 48 --S 96"
 for dt in bf16 fp32; do
-  run --N 1 --C 48 --S 96 --dtype $dt
-  for k in 3 4 5 6 8; do run --N 1 --C 48 --S 96 --dtype $dt --fslots $k; done
-  for l in 1 2 3 4 8 12; do run --N 1 --C 48 --S 96 --dtype $dt --flag $l; done
-  run --N 1 --C 48 --S 96 --dtype $dt --fslots 4 --flag 4
-  run --N 1 --C 48 --S 96 --dtype $dt --fslots 4 --flag 8
-  run --N 1 --C 48 --S 96 --dtype $dt --fslots 8 --flag 8
-  run --N 1 --C 48 --S 96 --dtype $dt --fpd 0
-  run --N 1 --C 48 --S 96 --dtype $dt --fpd 2500
+  run $H --dtype $dt
+  for k in 3 4 8; do run $H --dtype $dt --fslots $k; done
+  for k in 2 4; do run $H --dtype $dt --opt flat_slots_b=$k; done
+  for v in 512 768 1536 2048 3072; do run $H --dtype $dt --fpv $v; done
+  for m in 20 60 80; do run $H --dtype $dt --opt flat_l2_mb=$m; done
+  for d in 0 1500; do run $H --dtype $dt --fpd $d; done
   run --N 4 --C 48 --S 96 --dtype $dt
 done
 run --N 4 --C 96 --S 48 --dtype bf16
 run --N 4 --C 96 --S 48 --dtype fp32
 run --N 1 --C 24 --S 128 --dtype bf16
 run --N 1 --C 24 --S 128 --dtype fp32
-run --N 1 --C 48 --S 96 --dtype bf16 --epi 1
-run --N 1 --C 48 --S 96 --dtype bf16 --epi 2
+run $H --dtype bf16 --epi 1
+run $H --dtype bf16 --epi 2
 cat $out

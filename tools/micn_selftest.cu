@@ -125,6 +125,9 @@ static double relerr_f(const std::vector<double>& ref, const float* got, size_t 
     return mx / (den > 0 ? den : 1.0);
 }
 
+// generic library knobs from the command line (--opt name=value), applied after the per-case ones
+static std::vector<std::pair<std::string, long long>> g_extra_opts;
+
 static void set_opts(const Case& c) {
     micn_set_option("cluster_size", c.cs);
     micn_set_option("slots", c.slots);
@@ -140,6 +143,7 @@ static void set_opts(const Case& c) {
     micn_set_option("flat_groups", c.fgroups);
     micn_set_option("flat_poll_delay_ns", c.fpd);
     micn_set_option("flat_poll_backoff_ns", c.fpb);
+    for (auto& o : g_extra_opts) micn_set_option(o.first.c_str(), o.second);
 }
 
 static int run_correctness(const Case& c, bool verbose) {
@@ -516,6 +520,11 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--fgroups") && i + 1 < argc) ofgroups = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fpd") && i + 1 < argc) ofpd = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fpb") && i + 1 < argc) ofpb = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--opt") && i + 1 < argc) {
+            std::string kv = argv[++i];
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos) g_extra_opts.emplace_back(kv.substr(0, eq), atoll(kv.c_str() + eq + 1));
+        }
     }
     g_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     if (g_threads > 32) g_threads = 32;
@@ -688,11 +697,12 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&dtrace, tb));
         CK(cudaMemset(dtrace, 0, tb));
         micn_set_option("flat_trace", (long long)(uintptr_t)dtrace);
+        micn_set_option("flat_trace_which", 1);  // forward unless --opt flat_trace_which=2 says otherwise
         PerfResult r = run_perf(c, 1, 2);
         micn_set_option("flat_trace", 0);
         std::vector<long long> ht(tb / sizeof(long long));
         CK(cudaMemcpy(ht.data(), dtrace, tb, cudaMemcpyDeviceToHost));
-        printf("trace fwd_us %.2f bwd_us %.2f P=%lld K=%lld\n", r.fwd_us, r.bwd_us, r.f_cs, r.f_slots);
+        printf("trace fwd_us %.2f bwd_us %.2f P=%lld KA=%lld L=%lld\n", r.fwd_us, r.bwd_us, r.f_cs, r.f_slots, micn_get_option("last_lag"));
         const char* names[12] = {"load", "p1b", "p1e", "pubb", "pube", "gab", "gapoll", "gae", "p2wait", "p2b", "p2e", "loadwait"};
         const int nsm = prop.multiProcessorCount;
         long long t0 = 0;  // earliest stamp of the launch (%globaltimer is one clock for all SMs)
