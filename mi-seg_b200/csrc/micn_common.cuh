@@ -244,6 +244,19 @@ __device__ __forceinline__ void load_affine(const P& p, int s, long long c, floa
     }
 }
 
+// the same for a __grid_constant__ parameter block: the pointer tables stay in the constant bank and are
+// indexed there (no local copy, no scan)
+template <typename P>
+__device__ __forceinline__ void load_affine_gc(const P& p, int s, long long c, float& g, float& b) {
+    if (p.affine) {
+        g = __ldg(p.gamma[s] + c);
+        b = __ldg(p.beta[s] + c);
+    } else {
+        g = 1.f;
+        b = 0.f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PTX: shared addresses, mbarrier, TMA bulk copies, cluster
 // ---------------------------------------------------------------------------------------------

@@ -6,11 +6,10 @@ run() { echo "# $*" >> $out; timeout 120 tools/micn_selftest --suite one "$@" | 
 H="--N 1 --C 48 --S 96"
 for dt in bf16 fp32; do
   run $H --dtype $dt
-  for k in 3 4 8; do run $H --dtype $dt --fslots $k; done
-  for k in 2 4; do run $H --dtype $dt --opt flat_slots_b=$k; done
-  for v in 512 768 1536 2048 3072; do run $H --dtype $dt --fpv $v; done
-  for m in 20 60 80; do run $H --dtype $dt --opt flat_l2_mb=$m; done
-  for d in 0 1500; do run $H --dtype $dt --fpd $d; done
+  for l in 3 4; do run $H --dtype $dt --flag $l; done
+  for v in 128 256 384 512 1024 1536 2048; do run $H --dtype $dt --fpv $v; done
+  for m in 30 80 110; do run $H --dtype $dt --opt flat_l2_mb=$m; done
+  run $H --dtype $dt --fpb 50
   run --N 4 --C 48 --S 96 --dtype $dt
 done
 run --N 4 --C 96 --S 48 --dtype bf16
