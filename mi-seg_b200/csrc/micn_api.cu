@@ -308,41 +308,46 @@ int flat_blocks_per_sm(K kernel, int smem, int smem_optin) {
     return nb;
 }
 
-// returns 0 and fills *fp when the flat path can take the problem, 1 when it cannot, < 0 / > 0 codes on error.
-// NS = input streams that wait in L2 between their first and second touch.
+// returns 0 and fills *fp when the flat path can take the problem, 1 when it cannot, < 0 / > 0 codes on error
+// NS = streams of a ring A slot (and, in L2, of a piece between its two touches); NSB = streams of a ring B slot
 template <typename KernelT>
-int plan_flat(KernelT kernel, int NS, long long slabs, long long C, long long slab_bytes, const DeviceInfo& d,
+int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, long long slab_bytes, const DeviceInfo& d,
               FlatPlan* fp) {
     long long G = d.sm_count;
     const long long gcap = g_opt.flat_grid.load();
     if (gcap > 0 && gcap < G) G = gcap;
-    if (flat_blocks_per_sm(kernel, 0, d.smem_optin) < 1) return 1;
     const long long V = slab_bytes / 16;
-    const long long W = G * kFlatWarps;  // workers (warps) of the persistent grid
+    const long long ring = (long long)d.smem_optin - flat_ctl_bytes() - 128;
     long long ovh = g_opt.flat_ovh_vecs.load();
-    if (ovh < 0) ovh = 96;
+    if (ovh < 0) ovh = 128;
 
-    // lag: P2 trails P1 by L steps of a worker; the L*W pieces in between wait in L2, so the piece size is what
-    // keeps them well inside the 126 MB (a step of a 12 KB piece is ~9 us of a worker's HBM share: two steps
-    // cover the exchange many times over)
-    long long L_ = g_opt.flat_lag.load();
-    if (L_ <= 0) L_ = 3;
-    L_ = std::min<long long>(std::max<long long>(L_, 2), kFlatMaxLag);
-    // a piece is one batch of a worker: kFlatLoadsPerLane 128-bit loads per lane over all streams (6 KB); the
-    // (L+1)*W pieces between first and second touch then take ~45 MB of the 126 MB L2
-    long long pvmax = 32LL * (kFlatLoadsPerLane / NS);
-    long long l2mb = g_opt.flat_l2_mb.load();
-    if (l2mb > 0) pvmax = ((long long)((double)l2mb * 1e6 / (16.0 * NS * (double)W * (double)(L_ + 1)))) & ~31LL;
+    // ring A holds the bytes in flight from HBM (~100 KB per SM streams at the full read rate, tools/streambw.cu;
+    // anything much deeper only adds queueing delay to the record exchange); ring B re-reads from L2
+    long long KA = g_opt.flat_slots.load(), KB = g_opt.flat_slots_b.load();
+    if (KA <= 0) KA = 2;
+    if (KB <= 0) KB = 2;
+    KA = std::min<long long>(std::max<long long>(KA, 1), kFlatMaxSlots);
+    KB = std::min<long long>(std::max<long long>(KB, 1), kFlatMaxSlots);
+    // pieces as large as the rings allow (2 + 2 slots of ~56 KB): the 16 consumer warps of a CTA work on one
+    // piece in lock step, so every per-piece latency chain (barrier wake-up, shuffles, hand-offs) is paid by
+    // the whole SM and only amortises over large pieces (measured: 56 KB slots 0.69, 24 KB slots 0.58 of peak)
+    long long pvmax = 1LL << 20;
     const long long cap = g_opt.flat_piece_vecs.load();
     if (cap >= kFlatMinPieceVecs) pvmax = cap;
-    pvmax = std::max<long long>(pvmax, (V + kFlatMaxPieces - 1) / kFlatMaxPieces);  // huge slabs: P is capped
-    pvmax = std::max<long long>(pvmax, kFlatMinPieceVecs);
+    const long long fit = (ring / ((KA * NS + KB * NSB) * 16)) & ~7LL;
+    if (pvmax > fit) pvmax = fit;
     if (pvmax > V) pvmax = V;
+    if (pvmax < kFlatMinPieceVecs) return 1;
+    const long long slot_vecs = (pvmax + 7) & ~7LL;
+    const int smem = (int)((KA * NS + KB * NSB) * slot_vecs * 16 + flat_ctl_bytes());
+    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) return 1;
 
+    // a slab of P pieces spans R = ceil((P-1)/G)+1 rounds; P2 trails P1 by L >= R steps (L <= kFlatMaxLag)
+    const long long pmax_hw = std::min<long long>(kFlatMaxPieces, (long long)(kFlatMaxLag - 1) * G + 1);
     const long long P0 = (V + pvmax - 1) / pvmax;
+    if (P0 > pmax_hw) return 1;  // slab too large: not ours
     const long long Pend =
-        std::min<long long>(kFlatMaxPieces, std::max<long long>(P0, (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs));
-    if (P0 > Pend) return 1;
+        std::min<long long>(pmax_hw, std::max<long long>(P0, (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs));
     double best = 1e300;
     long long bestP = 0, bestPV = 0;
     for (long long P = P0; P <= Pend; ++P) {
@@ -351,34 +356,50 @@ int plan_flat(KernelT kernel, int NS, long long slabs, long long C, long long sl
         if (Pe != P) continue;  // same split as a smaller P: already scored
         const long long T = slabs * Pe;
         if (T > 0x7fffffffLL) break;
-        const long long rounds = (T + W - 1) / W;
-        // bytes cost what they are; every batch costs one memory latency whatever it holds
-        const long long bv = 32LL * (kFlatLoadsPerLane / NS);
-        const long long batches = (PV + bv - 1) / bv;
-        const double cost = (double)rounds * ((double)PV + (double)batches * (double)ovh);
+        const long long rounds = (T + G - 1) / G;
+        // bytes cost what they are; the consumer loops cost whole 512-vector sweeps
+        const long long sweep = (PV + kFlatConsumerThreads - 1) / kFlatConsumerThreads * kFlatConsumerThreads;
+        const double cost = (double)rounds * (0.5 * (double)PV + 0.5 * (double)sweep + (double)ovh);
         if (cost < best * 0.9999) {
             best = cost;
             bestP = Pe;
             bestPV = PV;
         }
-        if (PV * 4 < pvmax) break;  // far past the useful range
+        if (PV * 3 < pvmax) break;  // far past the useful range
     }
     if (!bestP) return 1;
+    // lag: long enough to cover the exchange at launch and at the tail (several microseconds of HBM time),
+    // short enough that the L*G pieces waiting for their second touch stay well inside the 126 MB L2
+    long long L_ = g_opt.flat_lag.load();
+    if (L_ <= 0) {
+        long long l2mb = g_opt.flat_l2_mb.load();
+        if (l2mb <= 0) l2mb = 32;
+        const double piece_bytes = (double)bestPV * 16.0 * NS;
+        L_ = (long long)((double)l2mb * 1e6 / ((double)G * piece_bytes));
+        if (L_ < 3) L_ = 3;
+    }
+    const long long need = (bestP - 1 + G - 1) / G + 1;  // R
+    if (L_ < need) L_ = need;
+    if (L_ > kFlatMaxLag) L_ = kFlatMaxLag;
+    if (L_ < need) return 1;
 
     fp->g.V = (unsigned long long)V;
     fp->g.P = (unsigned)bestP;
     fp->g.PV = (unsigned)bestPV;
-    fp->g.PVlast = (unsigned)(V - (bestP - 1) * bestPV);
     fp->g.T = (unsigned)(slabs * bestP);
+    fp->g.KA = (unsigned)KA;
+    fp->g.KB = (unsigned)KB;
     fp->g.L = (unsigned)L_;
+    fp->g.slot_vecs = (unsigned)slot_vecs;
     fp->g.epoch = next_epoch();
     fp->g.divP = fastdiv_make((unsigned)bestP);
     fp->g.divC = fastdiv_make((unsigned)C);
-    const long long pb = g_opt.flat_poll_backoff_ns.load();
+    const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
+    fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 2000);
     fp->g.poll_backoff_ns = (unsigned)(pb >= 0 ? pb : 200);
     fp->g.trace = reinterpret_cast<long long*>(g_opt.flat_trace.load());
     fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
-    fp->smem = 0;
+    fp->smem = smem;
     return 0;
 }
 
@@ -401,7 +422,7 @@ int launch_flat(K kernel, const P& p, const FlatPlan& fp, cudaStream_t st) {
 void record_flat(const FlatPlan& fp) {
     g_opt.last_path.store(2);
     g_opt.last_cs.store(fp.g.P);
-    g_opt.last_slots.store(fp.g.PV);
+    g_opt.last_slots.store(fp.g.KA);
     g_opt.last_lag.store(fp.g.L);
     g_opt.last_grid.store(fp.grid);
     g_opt.launches.fetch_add(1);
@@ -424,7 +445,7 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         auto kernel = micn_fwd_flat_kernel<T, EPI>;
         FlatPlan fpl = {};
-        const int rc = plan_flat(kernel, 1, slabs, p.C, slab_bytes, d, &fpl);
+        const int rc = plan_flat(kernel, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, p.C, slab_bytes, d, &fpl);
         if (rc == 0) {
             if (g_opt.flat_trace_which.load() == 2) fpl.g.trace = nullptr;
             fpl.g.ws_piece = ws_flat->piece;
@@ -472,7 +493,7 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         auto kernel = micn_bwd_flat_kernel<T, EPI>;
         FlatPlan fpl = {};
-        const int rc = plan_flat(kernel, NS, slabs, p.C, slab_bytes, d, &fpl);
+        const int rc = plan_flat(kernel, NS, NS, slabs, p.C, slab_bytes, d, &fpl);
         if (rc == 0) {
             if (g_opt.flat_trace_which.load() == 1) fpl.g.trace = nullptr;
             fpl.g.ws_piece = ws_flat->piece;

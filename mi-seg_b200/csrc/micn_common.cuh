@@ -63,6 +63,47 @@ struct BwdParams {
 };
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two fp32 operations per issued instruction).
+// The hot loops are bound by instruction issue, not by the fp32 pipe, so halving the arithmetic
+// instruction count is what counts.  A pair lives in one 64-bit register.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_bits(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_make(v, v); }
+__device__ __forceinline__ void f2_split(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float f2_hsum(f32x2 v) {
+    float lo, hi;
+    f2_split(v, lo, hi);
+    return lo + hi;
+}
+
+// ---------------------------------------------------------------------------------------------
 // element / vector traits: one 16-byte vector per thread per access
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -71,6 +112,7 @@ struct VecT;
 template <>
 struct VecT<float> {
     static constexpr int N = 4;
+    static constexpr bool kWideExponent = true;
     __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
         f[0] = __uint_as_float(v.x);
         f[1] = __uint_as_float(v.y);
@@ -80,6 +122,16 @@ struct VecT<float> {
     __device__ __forceinline__ static uint4 pack(const float* f) {
         return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
     }
+    __device__ __forceinline__ static void unpack2(const uint4& v, f32x2* f) {
+        f[0] = f2_bits(v.x, v.y);
+        f[1] = f2_bits(v.z, v.w);
+    }
+    __device__ __forceinline__ static uint4 pack2v(const f32x2* f) {
+        float a, b, c, d;
+        f2_split(f[0], a, b);
+        f2_split(f[1], c, d);
+        return make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
+    }
     __device__ __forceinline__ static float load1(const float* p) { return *p; }
     __device__ __forceinline__ static void store1(float* p, float v) { *p = v; }
 };
@@ -87,6 +139,7 @@ struct VecT<float> {
 template <>
 struct VecT<__nv_bfloat16> {
     static constexpr int N = 8;
+    static constexpr bool kWideExponent = true;  // same exponent range as fp32
     __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
         // bf16 -> fp32 is a 16-bit shift: no conversion instruction needed
         f[0] = __uint_as_float(v.x << 16);
@@ -105,6 +158,20 @@ struct VecT<__nv_bfloat16> {
     __device__ __forceinline__ static uint4 pack(const float* f) {
         return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     }
+    __device__ __forceinline__ static void unpack2(const uint4& v, f32x2* f) {
+        f[0] = f2_bits(v.x << 16, v.x & 0xffff0000u);
+        f[1] = f2_bits(v.y << 16, v.y & 0xffff0000u);
+        f[2] = f2_bits(v.z << 16, v.z & 0xffff0000u);
+        f[3] = f2_bits(v.w << 16, v.w & 0xffff0000u);
+    }
+    __device__ __forceinline__ static uint32_t packp(f32x2 p) {
+        float lo, hi;
+        f2_split(p, lo, hi);
+        return pack2(lo, hi);
+    }
+    __device__ __forceinline__ static uint4 pack2v(const f32x2* f) {
+        return make_uint4(packp(f[0]), packp(f[1]), packp(f[2]), packp(f[3]));
+    }
     __device__ __forceinline__ static float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     __device__ __forceinline__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
@@ -112,6 +179,7 @@ struct VecT<__nv_bfloat16> {
 template <>
 struct VecT<__half> {
     static constexpr int N = 8;
+    static constexpr bool kWideExponent = false;
     __device__ __forceinline__ static void unpack2(uint32_t u, float& lo, float& hi) {
         float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
         lo = f.x;
@@ -129,6 +197,25 @@ struct VecT<__half> {
     }
     __device__ __forceinline__ static uint4 pack(const float* f) {
         return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+    __device__ __forceinline__ static f32x2 unpackp(uint32_t u) {
+        float lo, hi;
+        unpack2(u, lo, hi);
+        return f2_make(lo, hi);
+    }
+    __device__ __forceinline__ static void unpack2(const uint4& v, f32x2* f) {
+        f[0] = unpackp(v.x);
+        f[1] = unpackp(v.y);
+        f[2] = unpackp(v.z);
+        f[3] = unpackp(v.w);
+    }
+    __device__ __forceinline__ static uint32_t packp(f32x2 p) {
+        float lo, hi;
+        f2_split(p, lo, hi);
+        return pack2(lo, hi);
+    }
+    __device__ __forceinline__ static uint4 pack2v(const f32x2* f) {
+        return make_uint4(packp(f[0]), packp(f[1]), packp(f[2]), packp(f[3]));
     }
     __device__ __forceinline__ static float load1(const __half* p) { return __half2float(*p); }
     __device__ __forceinline__ static void store1(__half* p, float v) { *p = __float2half_rn(v); }

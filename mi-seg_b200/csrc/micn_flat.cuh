@@ -2,38 +2,37 @@
 //
 // Measured on B200 (tools/l2bw.cu, tools/streambw.cu, profiles/): HBM copy 6.5 TB/s, HBM read 7.1-7.3 TB/s, reads
 // that hit the 126 MB L2 18-19 TB/s.  So the budget is HBM bytes, not L2<->SM bytes: a voxel should cross HBM
-// once per tensor, while a second look at it is cheap as long as it is still in L2.  What the earlier designs
-// of this file taught: cluster-per-slab cannot balance 48 slabs on 148 SMs; shared-memory-resident
-// pieces cannot hide the cross-CTA exchange; whenever the 16 warps of a CTA work on ONE piece in lock step
-// (TMA ring + mbarriers) every per-piece latency chain - barrier wake-up, shuffles, the partial hand-off - is
-// paid by the whole SM at once, ~1 us per piece; helper warps that spin steal the issue slots the bf16 math
-// needs; a kernel that outgrows the instruction cache loses everything.
+// once per tensor, while a second look at it is cheap as long as it is still in L2.  A ring of 1-D TMA bulk
+// copies streams at the full HBM read rate from one persistent CTA per SM once 96 KB are in flight per SM
+// (6 slots x 16 KB: 7.1 TB/s; 3 x 8 KB: 3.8 TB/s) and costs the consumer warps no issue slots.  What the
+// earlier designs taught: cluster-per-slab cannot balance 48 slabs on 148 SMs;
+// shared-memory-resident pieces cannot hide the cross-CTA exchange; a 220 KB-deep prefetch turns the memory
+// system into a 5 us FIFO that every record store and poll queues in; helper warps that spin on mbarriers
+// steal the issue slots the bf16 math needs; a kernel that outgrows the instruction cache loses everything.
 //
-// How: every (n, c) slab is cut into P pieces of <= PV 16-byte vectors and every WARP of the persistent grid
-// (one 16-warp CTA per SM, launched cooperatively so all are co-resident) is an independent worker: piece
-// g = slab*P + k belongs to worker g % W in its step g / W, W = 16*G workers, worker = warp*G + cta so that
-// neighbouring pieces sit on different SMs.  No shared memory, no block-wide barrier, no TMA: a piece is ONE
-// batch of 128-bit loads per lane, issued a task ahead of its use, so a worker always has its next first-touch
-// batch (HBM) or this step's second-touch batch (L2) in flight while it computes on the other (~64 KB in flight
-// per SM, which tools/streambw.cu shows is enough for the full HBM read rate), and the 16 workers of an SM are
-// out of phase by construction, so one worker's reduction / exchange latency is hidden by the streaming of the
-// others.  Step s of a worker:
+// How: every (n, c) slab is cut into P pieces of <= PV 16-byte vectors; piece g = slab*P + k belongs to
+// CTA g % G in its round g / G (G = one persistent CTA per SM, launched cooperatively so all are
+// co-resident): every SM carries the same share whatever N*C is.  A CTA walks its pieces j = 0, 1, ... in
+// steps; step s runs two tasks, each fed by its own ring of shared-memory slots and its own TMA producer lane:
 //
-//     issue      second-touch batch of piece s-L (L2, evict_first)
-//     P1(s)      statistics of its piece of step s (fp32 shifted sums, warp shuffle) -> piece record
-//                                                 (first touch: HBM -> L2 -> SM, L2 evict_last)
-//     issue      first-touch batch of piece s+1 (HBM)
-//     fold       if it owns piece 0 of a slab whose pieces are at step s-1: poll the slab's P piece records
-//                (batches of loads in flight), fold them in a fixed order (bit-identical whoever folds, no
-//                atomics) -> slab record; backward: also d(gamma)/d(beta) for the last sample of a channel
-//     P2(s - L)  poll the slab record (published a whole step ago; if its owner is late, fold it oneself: same
-//                records, same order, same bits), then normalise / epilogue / backward formula of its piece of
-//                step s-L with 128-bit streaming stores
-//                                                 (second touch L steps later: served by L2, evict_first)
+//     ring A: P1(s)      statistics of piece s          (first touch: HBM -> L2 -> SM, L2 evict_last)
+//     ring B: P2(s - L)  normalise / epilogue / backward formula of piece s - L, 128-bit streaming stores
+//                                                       (second touch L steps later: served by L2, evict_first)
 //
-// Between the two touches the piece lives in L2 (L*W pieces, a few tens of MB).  At launch the workers
-// therefore read at full HBM speed for L steps while the first statistics are exchanged, and at the end the
-// backlog of L P2 steps hides the last exchange.
+// Between the two the piece lives in L2 (L*G pieces, a few tens of MB), not in shared memory.  At launch the
+// CTAs therefore read at full HBM speed for L steps while the first statistics are exchanged, and at the end
+// the backlog of L P2 tasks hides the last exchange.  Roles inside a CTA:
+//
+//   producer A / B (1 lane each)  1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), KA / KB slots ahead;
+//                           B issues P2(j)'s copy as soon as P1(j) is through, so it is in the slot long before use.
+//   16 consumer warps       each warp owns a fixed 1/16 of every piece: fp32 shifted sums + warp shuffle in P1;
+//                           FMA + pack + st.global.v4 in P2.  Every wait parks the warp (try_wait + suspend hint).
+//   1 publish warp          folds the 16 warp partials of a piece and write the piece record to the workspace as
+//                           soon as its P1 is done; never wait on another CTA.
+//   4 gather warps          poll the P records of the piece's slab (batches of loads in flight, re-polled in
+//                           parallel), fold them in a fixed order (bit-identical in every CTA, no atomics)
+//                           and publish the per-slab coefficients P2 needs; backward: also the per-slab
+//                           sums and, for the last sample of a channel, d(gamma)/d(beta) per style.
 //
 // Statistics are folded without a chain of divisions: partials (n, mean, M2) are summed about a common
 // reference `ref` (the first partial's mean - itself a mean, never an outlier) as
@@ -41,10 +40,10 @@
 // which is exact algebra, well conditioned because |mean_q - ref| is of the order of the spread, and uses one
 // division per fold.
 //
-// Cross-worker exchange is by 16-byte self-validating records {a, tag, b, tag} (tag = per-launch epoch): no
-// counters to reset, an aborted launch cannot poison the next one.  Deadlock freedom (L >= 2): P1 never waits;
-// a fold at step s needs P1 records of steps <= s (a slab may straddle two steps), all written before any fold
-// of step s starts; a P2 at step s needs a fold of step s-L+1 <= s-1 (or folds for itself).  Every wait is bounded and traps instead of hanging.
+// Cross-CTA exchange is by 16-byte self-validating records {a, tag, b, tag} (tag = per-launch epoch): no
+// counters to reset, an aborted launch cannot poison the next one.  Deadlock freedom: a slab of P pieces
+// spans R <= ceil((P-1)/G)+1 rounds and the planner keeps L >= R, so every P1 a record depends on runs
+// before anyone can block in a P2; publishes never block.  Every wait is bounded and traps instead of hanging.
 //
 // HBM traffic: forward reads x once and writes y once (2*E*s); backward reads x, dy [, act_out] once and
 // writes dx [, dresidual] once (3*E*s / 5*E*s) - the algorithmic minimum; L2<->SM carries
@@ -58,29 +57,36 @@
 
 namespace micn {
 
-constexpr int kFlatWarps = 16;                 // workers per CTA
-constexpr int kFlatThreads = kFlatWarps * 32;  // 512: one CTA per SM, up to 128 registers per thread
-constexpr int kFlatMaxLag = 8;
-constexpr int kFlatMaxPieces = 1024;  // pieces per slab (workspace sizing)
+constexpr int kFlatConsumerWarps = 16;
+constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512
+constexpr int kFlatProducerWarpA = kFlatConsumerWarps;
+constexpr int kFlatProducerWarpB = kFlatConsumerWarps + 1;
+constexpr int kFlatPublishWarp0 = kFlatConsumerWarps + 2;
+constexpr int kFlatPublishWarps = 1;
+constexpr int kFlatGatherWarp0 = kFlatPublishWarp0 + kFlatPublishWarps;
+constexpr int kFlatGatherWarps = 4;  // a gather is a multi-microsecond latency chain: keep several in flight
+constexpr int kFlatThreads = (kFlatConsumerWarps + 2 + kFlatPublishWarps + kFlatGatherWarps) * 32;  // 736 -> 88 registers
+constexpr int kFlatMaxSlots = 8;     // per ring
+constexpr int kFlatNB = 32;          // per-piece control ring (partials, coefficients): piece j -> entry j % 32
+constexpr int kFlatMaxLag = 30;      // L <= kFlatNB - 1: an entry is recycled only after its piece's P2 is done
+constexpr int kFlatMaxPieces = 1024; // pieces per slab (workspace sizing); the planner enforces the round bound
 constexpr int kFlatMinPieceVecs = 128;
-#ifndef MICN_FLAT_LPL
-#define MICN_FLAT_LPL 8
-#endif
-constexpr int kFlatLoadsPerLane = MICN_FLAT_LPL;  // 128-bit loads a lane has in flight per batch, over all streams
+constexpr uint32_t kFlatTmaChunk = 32768;
 
 struct FlatGeom {
     unsigned long long V;  // 16-byte vectors per slab
     unsigned T;            // total pieces = num_slabs * P
     unsigned P;            // pieces per slab
-    unsigned PV;           // vectors per piece ...
-    unsigned PVlast;       // ... except the last piece of a slab
-    unsigned L;            // steps P2 trails P1 (>= 2)
+    unsigned PV;           // vectors per piece (the last piece of a slab may be shorter)
+    unsigned KA, KB;       // shared-memory slots of ring A (P1) and ring B (P2)
+    unsigned L;            // steps P2 trails P1
+    unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
     unsigned epoch;        // per-launch tag of the workspace records (never 0)
-    unsigned poll_backoff_ns;
+    unsigned poll_delay_ns, poll_backoff_ns;
     FastDiv divP, divC;    // piece index -> slab, slab -> sample
     uint4* ws_piece;       // [T] piece records
-    uint4* ws_slab;        // [num_slabs] slab records (forward: mean, rstd; backward: sum g, sum g*xhat)
-    long long* trace;      // bring-up only: [grid][kFlatTraceSteps][16] %globaltimer stamps (ns) of warp 0, or null
+    uint4* ws_slab;        // [num_slabs] per-slab records (backward parameter gradients)
+    long long* trace;      // bring-up only: [grid][kFlatTraceSteps][16] %globaltimer stamps (ns) per piece, or null
 };
 
 constexpr int kFlatTraceSteps = 64;
@@ -91,10 +97,64 @@ __device__ __forceinline__ void flat_trace(const FlatGeom& g, unsigned j, int ev
         g.trace[((size_t)blockIdx.x * kFlatTraceSteps + j) * 16 + ev] = (long long)globaltimer_ns();
 }
 
+// control block: slot barriers of both rings + the per-piece ring
+__host__ __device__ constexpr int flat_ctl_bytes() {
+    return kFlatMaxSlots * (4 * 8 + 16) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 32);
+}
+
+struct FlatCtx {
+    uint32_t dataA, dataB, fullA, emptyA, fullB, emptyB, p1d0, coef0;  // shared::cta addresses
+    float* slot_prec;                            // [KA][4]  slab constants of the piece in the A slot (backward)
+    float* warp_part;                            // [NB][16][4]
+    float* coefv;                                // [NB][8]
+    uint32_t stream_bytes, slot_bytes, slot_bytes_b;  // one stream of a slot; a ring A slot; a ring B slot
+};
+
+template <int NSA, int NSB>
+__device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeom& g) {
+    FlatCtx c;
+    c.stream_bytes = g.slot_vecs * 16u;
+    c.slot_bytes = c.stream_bytes * NSA;
+    c.slot_bytes_b = c.stream_bytes * NSB;
+    c.dataA = smem_u32(smem);
+    c.dataB = c.dataA + g.KA * c.slot_bytes;
+    unsigned char* ctl = smem + (size_t)g.KA * c.slot_bytes + (size_t)g.KB * c.slot_bytes_b;
+    c.fullA = smem_u32(ctl);
+    c.emptyA = c.fullA + kFlatMaxSlots * 8;
+    c.fullB = c.emptyA + kFlatMaxSlots * 8;
+    c.emptyB = c.fullB + kFlatMaxSlots * 8;
+    c.p1d0 = c.emptyB + kFlatMaxSlots * 8;
+    c.coef0 = c.p1d0 + kFlatNB * 8;
+    float* f = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 32 + kFlatNB * 16);
+    c.slot_prec = f;
+    c.warp_part = c.slot_prec + kFlatMaxSlots * 4;
+    c.coefv = c.warp_part + kFlatNB * kFlatConsumerWarps * 4;
+    if (threadIdx.x == 0) {
+        for (unsigned i = 0; i < g.KA; ++i) {
+            mbar_init(c.fullA + 8 * i, 1);
+            mbar_init(c.emptyA + 8 * i, kFlatConsumerWarps);
+        }
+        for (unsigned i = 0; i < g.KB; ++i) {
+            mbar_init(c.fullB + 8 * i, 1);
+            mbar_init(c.emptyB + 8 * i, kFlatConsumerWarps);
+        }
+        for (unsigned i = 0; i < kFlatNB; ++i) {
+            mbar_init(c.p1d0 + 8 * i, kFlatConsumerWarps);
+            mbar_init(c.coef0 + 8 * i, 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    return c;
+}
+
 struct PieceId {
     unsigned slab, k, pv;  // slab index, piece index inside the slab, vectors in this piece
 };
-__device__ __forceinline__ unsigned piece_vecs(const FlatGeom& g, unsigned k) { return k + 1 == g.P ? g.PVlast : g.PV; }
+__device__ __forceinline__ unsigned piece_vecs(const FlatGeom& g, unsigned k) {
+    const unsigned long long left = g.V - (unsigned long long)k * g.PV;
+    return left < g.PV ? (unsigned)left : g.PV;
+}
 __device__ __forceinline__ PieceId piece_of(const FlatGeom& g, unsigned gidx) {
     PieceId p;
     p.slab = fastdiv(gidx, g.divP);
@@ -103,14 +163,17 @@ __device__ __forceinline__ PieceId piece_of(const FlatGeom& g, unsigned gidx) {
     return p;
 }
 
-// 128-bit streaming loads with an L2 eviction-priority hint (first touch: keep; second touch: done with it)
-__device__ __forceinline__ uint4 ldg_hint(const void* p, uint64_t pol) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-}
+// ring cursors with phase parity: slots advance once per task of their ring, piece-ring entries once per PIECE
+struct Ring {
+    unsigned i, ph;
+    __device__ __forceinline__ void next(unsigned n) {
+        if (++i == n) {
+            i = 0;
+            ph ^= 1u;
+        }
+    }
+};
+__device__ __forceinline__ Ring entry_of(unsigned j) { return Ring{j % kFlatNB, (j / kFlatNB) & 1u}; }
 
 // ---- self-validating workspace records {a, tag, b, tag}: each 8-byte half carries its own tag, so a
 //      torn 16-byte access can never be mistaken for a complete record
@@ -136,33 +199,28 @@ __device__ __forceinline__ bool ll_try(const uint4* p, unsigned tag, float& a, f
 template <typename First, typename Fold>
 __device__ __forceinline__ void ll_gather(const uint4* recs, unsigned count, unsigned tag, unsigned backoff_ns, int lane,
                                           First first, Fold fold) {
-    constexpr int R = 8;  // records per lane in flight: a slab of <= 256 pieces costs one L2 round trip
-    for (unsigned q0 = 0; q0 < count; q0 += 32 * R) {
-        float a[R], b[R];
-        bool ok[R], all = true;
+    for (unsigned q0 = 0; q0 < count; q0 += 128) {
+        float a[4], b[4];
+        bool ok[4];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const unsigned q = q0 + lane + 32 * i;
             ok[i] = q < count ? ll_try(recs + q, tag, a[i], b[i]) : true;
-            all = all && ok[i];
         }
-        if (!all) {
+        if (!(ok[0] && ok[1] && ok[2] && ok[3])) {
             const uint64_t t0 = globaltimer_ns();
             uint32_t spins = 0;
             do {
                 __nanosleep(backoff_ns);
-                all = true;
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
+                for (int i = 0; i < 4; ++i)
                     if (!ok[i]) ok[i] = ll_try(recs + q0 + lane + 32 * i, tag, a[i], b[i]);
-                    all = all && ok[i];
-                }
                 if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
-            } while (!all);
+            } while (!(ok[0] && ok[1] && ok[2] && ok[3]));
         }
         if (q0 == 0) first(__shfl_sync(0xffffffffu, a[0], 0), __shfl_sync(0xffffffffu, b[0], 0));  // record 0
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const unsigned q = q0 + lane + 32 * i;
             if (q < count) fold(q, a[i], b[i]);
         }
@@ -178,219 +236,258 @@ __device__ __forceinline__ void ll_wait1(const uint4* p, unsigned tag, unsigned 
     } while (!ll_try(p, tag, a, b));
 }
 
-
-// ---- a worker's walk over its piece: lane handles vectors lane + 32*(b*U + i).  A whole batch of U vectors per
-//      lane per stream is in flight at once; the planner sizes pieces to ONE batch (U*32 vectors), and the step
-//      loop below issues a task's batch well before it is used, so a worker always has an HBM batch (next P1)
-//      or an L2 batch (this step's P2) in flight while it computes on the other.
-template <int NS, int U>
-struct Batch {
-    uint4 q[NS][U];
-};
-
-// one task of a worker: a piece and where its lane-0.. vectors live
-struct FlatTask {
-    unsigned gidx, slab, pv;
-    unsigned long long xoff;  // bytes: this lane's vector 0 of the piece inside x (strided) ...
-    unsigned long long doff;  // ... and inside the dense [N, C, M] tensors
-    unsigned n, ch;
-};
-__device__ __forceinline__ FlatTask flat_task(const FlatGeom& g, unsigned gidx, unsigned C, long long x_sN, long long x_sC,
-                                              long long M, unsigned es, int lane) {
-    FlatTask t;
-    const PieceId pc = piece_of(g, gidx);
-    t.gidx = gidx;
-    t.slab = pc.slab;
-    t.pv = pc.pv;
-    t.n = fastdiv(pc.slab, g.divC);
-    t.ch = pc.slab - t.n * C;
-    const unsigned long long poff = (unsigned long long)pc.k * g.PV * 16ull + (unsigned long long)lane * 16ull;
-    t.xoff = (unsigned long long)(((long long)t.n * x_sN + (long long)t.ch * x_sC) * (long long)es) + poff;
-    t.doff = (unsigned long long)pc.slab * (unsigned long long)M * es + poff;
-    return t;
+// vectors of a piece (pv vectors, strided over the 512 consumer threads) that land in consumer warp w
+__device__ __forceinline__ unsigned warp_vecs(unsigned pv, unsigned w) {
+    const unsigned full = pv / kFlatConsumerThreads, rem = pv % kFlatConsumerThreads;
+    int r = (int)rem - 32 * (int)w;
+    r = r < 0 ? 0 : (r > 32 ? 32 : r);
+    return 32u * full + (unsigned)r;
 }
 
-// fold of a slab's piece statistics about record 0's mean (see the file header); every lane returns the totals
-struct SlabStat {
-    float mean, m2;
-};
-template <int VN>
-__device__ __noinline__ SlabStat fold_slab_stats(const FlatGeom& g, unsigned slab, float M, int lane) {
-    float ref = 0.f, A = 0.f, B = 0.f;
-    ll_gather(g.ws_piece + (size_t)slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane, [&](float a0, float) { ref = a0; },
-              [&](unsigned q, float a, float b) {
-                  const float nq = (float)(piece_vecs(g, q) * VN), d = a - ref;
-                  A = fmaf(nq, d, A);
-                  B += fmaf(nq * d, d, b);
-              });
-    A = warp_sum(A);
-    B = warp_sum(B);
-    const float m = A / M;
-    return SlabStat{ref + m, fmaxf(B - A * m, 0.f)};
+template <typename T>
+__device__ __forceinline__ float first_elem(uint32_t smem_addr) {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(smem_addr));
+    if (sizeof(T) == 4) return __uint_as_float(w);
+    float f[VecT<T>::N];
+    VecT<T>::unpack(make_uint4(w, 0u, 0u, 0u), f);
+    return f[0];
 }
 
-// a few polls of a slab record; false if its owner has not folded yet (the caller then folds for itself: same
-// records, same order, same bits)
-__device__ __forceinline__ bool ll_poll_short(const uint4* p, unsigned tag, unsigned backoff_ns, float& a, float& b) {
-    for (int i = 0; i < 6; ++i) {
-        if (ll_try(p, tag, a, b)) return true;
-        __nanosleep(backoff_ns);
+// producer: one bulk copy per <= 32 KB chunk of each stream of the piece, all on the slot's barrier
+__device__ __forceinline__ void flat_issue(uint32_t dst, const char* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    for (uint32_t off = 0; off < bytes; off += kFlatTmaChunk) {
+        const uint32_t n = bytes - off < kFlatTmaChunk ? bytes - off : kFlatTmaChunk;
+        tma_load_1d(dst + off, src + off, n, bar, pol);
     }
-    return ll_try(p, tag, a, b);
+}
+
+// A consumer thread's walk over the pv vectors of a piece, U vectors at a time (vector v = tid + 512*m).  The
+// full batches run without a single bounds check or index recomputation; only the ragged tail is predicated.
+template <int U, typename Load, typename Use>
+__device__ __forceinline__ void piece_sweep(unsigned pv, unsigned tid, Load load, Use use) {
+    constexpr unsigned kStep = U * kFlatConsumerThreads;
+    const unsigned full = pv / kStep * kStep;
+    unsigned v0 = tid;
+    for (; v0 < full; v0 += kStep) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) load(i, v0 + i * kFlatConsumerThreads);
+#pragma unroll
+        for (int i = 0; i < U; ++i) use(i, v0 + i * kFlatConsumerThreads);
+    }
+    if (v0 < pv) {
+#pragma unroll
+        for (int i = 0; i < U; ++i)
+            if (v0 + i * kFlatConsumerThreads < pv) load(i, v0 + i * kFlatConsumerThreads);
+#pragma unroll
+        for (int i = 0; i < U; ++i)
+            if (v0 + i * kFlatConsumerThreads < pv) use(i, v0 + i * kFlatConsumerThreads);
+    }
 }
 
 // =================================================================================================
 // forward
 // =================================================================================================
 template <typename T, int EPI>
-__global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ FlatGeom g) {
+__global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const FwdParams p, const FlatGeom g) {
+    extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VN = VecT<T>::N;
-    constexpr int NS = EPI == MICN_EPI_ADD_LRELU ? 2 : 1;  // P2: x [, residual]
-    constexpr int U = kFlatLoadsPerLane / NS;              // vectors per lane per stream per batch (P1 and P2 alike)
-    const unsigned G = gridDim.x, W = G * kFlatWarps;
-    const int lane = threadIdx.x & 31;
-    const unsigned worker = (threadIdx.x >> 5) * G + blockIdx.x;
-    const unsigned nj = worker < g.T ? (g.T - worker + W - 1) / W : 0;
+    constexpr int NSB = EPI == MICN_EPI_ADD_LRELU ? 2 : 1;  // ring B: x [, residual]
+    const FlatCtx c = flat_setup<1, NSB>(smem, g);
+    const unsigned cta = blockIdx.x, G = gridDim.x;
+    const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned C = (unsigned)p.C;
-    const bool tr = threadIdx.x == 0;
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
-    const float Mf = (float)p.M;
-    const char* xb = reinterpret_cast<const char*>(p.x);
-    const char* rb = reinterpret_cast<const char*>(p.res);
-    char* yb = reinterpret_cast<char*>(p.y);
 
-    auto loadA = [&](const FlatTask& t, unsigned b, Batch<1, U>& A) {
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const unsigned v = lane + 32u * (b * U + i);
-            A.q[0][i] = make_uint4(0u, 0u, 0u, 0u);
-            if (v < t.pv) A.q[0][i] = ldg_hint(xb + t.xoff + (size_t)(b * U + i) * 512, pol_keep);
-        }
-    };
-    auto loadB = [&](const FlatTask& t, unsigned b, Batch<NS, U>& B) {
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const unsigned v = lane + 32u * (b * U + i);
-            if (v < t.pv) {
-                B.q[0][i] = ldg_hint(xb + t.xoff + (size_t)(b * U + i) * 512, pol_done);
-                if (NS == 2) B.q[NS - 1][i] = ldg_hint(rb + t.doff + (size_t)(b * U + i) * 512, pol_done);
+    if (warp == kFlatProducerWarpA || warp == kFlatProducerWarpB) {
+        // ------------------------------------------------------------------ producers (A: first touch, B: second touch)
+        if (lane == 0) {
+            const bool isA = warp == kFlatProducerWarpA;
+            const uint64_t pol = isA ? l2_policy_evict_last() : l2_policy_evict_first();
+            const unsigned K = isA ? g.KA : g.KB;
+            const uint32_t full0 = isA ? c.fullA : c.fullB, empty0 = isA ? c.emptyA : c.emptyB;
+            const uint32_t data0 = isA ? c.dataA : c.dataB;
+            Ring r{0u, 0u};
+            for (unsigned j = 0; j < nj; ++j) {
+                const PieceId pc = piece_of(g, j * G + cta);
+                const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+                const char* src = reinterpret_cast<const char*>(p.x) +
+                                  ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) +
+                                  (size_t)pc.k * g.PV * 16;
+                const uint32_t bytes = pc.pv * 16u, bar = full0 + 8 * r.i;
+                if (!isA) {  // the second touch must find the piece in L2: not before its first touch is through
+                    const Ring e = entry_of(j);
+                    mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
+                }
+                if (j >= K) mbar_wait_park(empty0 + 8 * r.i, r.ph ^ 1u);
+                flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
+                const uint32_t dst = data0 + r.i * (isA ? c.slot_bytes : c.slot_bytes_b);
+                flat_issue(dst, src, bytes, bar, pol);
+                if (NSB == 2 && !isA) {  // the residual rides in the same slot (read once, from HBM)
+                    const char* rsrc = reinterpret_cast<const char*>(p.res) + ((size_t)pc.slab * (size_t)p.M) * sizeof(T) +
+                                       (size_t)pc.k * g.PV * 16;
+                    flat_issue(dst + c.stream_bytes, rsrc, bytes, bar, pol);
+                }
+                mbar_arrive_expect_tx(bar, (NSB == 2 && !isA) ? 2 * bytes : bytes);
+                r.next(K);
             }
         }
-    };
-
-    FlatTask ta, tb;
-    Batch<1, U> A;
-    Batch<NS, U> B;
-    if (nj) {
-        ta = flat_task(g, worker, C, p.x_sN, p.x_sC, p.M, sizeof(T), lane);
-        loadA(ta, 0, A);
-    }
-    for (unsigned s = 0; s < nj + g.L; ++s) {
-        const bool hasB = s >= g.L;
-        float gamma = 1.f, beta = 0.f;
-        if (hasB) {
-            // ---- second touch of piece s-L: its batch (L2) and parameters go in flight now, used at the end of the step
-            tb = flat_task(g, (s - g.L) * W + worker, C, p.x_sN, p.x_sC, p.M, sizeof(T), lane);
-            loadB(tb, 0, B);
-            const int style = load_style(p.styles, tb.n, p.num_styles, p.status);
-            load_affine_gc(p, style, tb.ch, gamma, beta);
-        }
-        if (s < nj) {
-            // ---- P1(s): statistics of this worker's piece (its first batch was issued a step ago) -> piece record
-            if (tr) flat_trace(g, s, TR_P1_BEGIN);
-            float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, K = 0.f;
-            const unsigned pv = ta.pv, nb = (pv + 32 * U - 1) / (32 * U);
-            for (unsigned b = 0; b < nb; ++b) {
-                if (b) loadA(ta, b, A);
-                if (b == 0) {  // shift = the piece's first element
-                    float f0[VN];
-                    VecT<T>::unpack(A.q[0][0], f0);
-                    K = __shfl_sync(0xffffffffu, f0[0], 0);
-                }
-#pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    const unsigned v = lane + 32u * (b * U + i);
-                    if (v < pv) {
-                        float f[VN];
-                        VecT<T>::unpack(A.q[0][i], f);
-#pragma unroll
-                        for (int k = 0; k < VN; k += 2) {
-                            const float d0 = f[k] - K, d1 = f[k + 1] - K;
-                            sa += d0;
-                            sb += d1;
-                            qa = fmaf(d0, d0, qa);
-                            qb = fmaf(d1, d1, qb);
-                        }
-                    }
-                }
+    } else if (warp >= kFlatPublishWarp0 && warp < kFlatGatherWarp0) {
+        // ------------------------------------------------------------------ publish: warp partials -> piece record
+        for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
+            const Ring e = entry_of(j);
+            const unsigned gidx = j * G + cta;
+            const unsigned k = gidx - fastdiv(gidx, g.divP) * g.P;
+            const unsigned pv = piece_vecs(g, k);
+            const float nw = lane < kFlatConsumerWarps ? (float)(warp_vecs(pv, lane) * VN) : 0.f;
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
+            if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
+            Stat st{0.f, 0.f, 0.f};
+            if (lane < kFlatConsumerWarps) {
+                const float4 w = *reinterpret_cast<const float4*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
+                st = stat_from_shifted(w.z, w.x, w.y, nw);
             }
-            const float s1 = warp_sum(sa + sb), s2 = warp_sum(qa + qb);
+            // fold about the first warp's mean (see the file header)
+            const float ref = __shfl_sync(0xffffffffu, st.mean, 0);
+            const float d = st.n > 0.f ? st.mean - ref : 0.f;
+            const float A = warp_sum(st.n * d), B = warp_sum(fmaf(st.n * d, d, st.m2));
+            const float N = (float)(pv * VN);
+            const float m = A / N;
+            if (lane == 0) ll_store(g.ws_piece + gidx, ref + m, fmaxf(B - A * m, 0.f), g.epoch);
+            if (lane == 0) flat_trace(g, j, TR_PUB_END);
+        }
+    } else if (warp >= kFlatGatherWarp0) {
+        // ------------------------------------------------------------------ gather: slab records -> coefficients for P2
+        for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
+            const Ring e = entry_of(j);
+            const PieceId pc = piece_of(g, j * G + cta);
+            const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+            // parameter loads first: their latency hides behind everything below
+            const int style = load_style(p.styles, n, p.num_styles, p.status);
+            float gamma, beta;
+            load_affine(p, style, ch, gamma, beta);
+            // no polling before this CTA's own piece is through P1: the other CTAs are at the same point
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
+            __nanosleep(g.poll_delay_ns);  // ... and let their record stores land
+            if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
+            float ref = 0.f, A = 0.f, B = 0.f;
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane,
+                      [&](float a0, float) { ref = a0; },
+                      [&](unsigned q, float a, float b) {
+                          const float nq = (float)(piece_vecs(g, q) * VN), d = a - ref;
+                          A = fmaf(nq, d, A);
+                          B += fmaf(nq * d, d, b);
+                      });
+            if (lane == 0) flat_trace(g, j, TR_GA_POLLED);
+            A = warp_sum(A);
+            B = warp_sum(B);
             if (lane == 0) {
-                const float m = s1 / (float)(pv * VN);
-                ll_store(g.ws_piece + ta.gidx, K + m, fmaxf(s2 - s1 * m, 0.f), g.epoch);
-            }
-            if (tr) flat_trace(g, s, TR_P1_END);
-            // ---- first touch of piece s+1 goes in flight (HBM) while this step folds and normalises
-            if (s + 1 < nj) {
-                ta = flat_task(g, (s + 1) * W + worker, C, p.x_sN, p.x_sC, p.M, sizeof(T), lane);
-                loadA(ta, 0, A);
-            }
-        }
-        if (s >= 1 && s - 1 < nj) {
-            // ---- fold: the owner of a slab's piece 0 turns the slab's piece records (all written a step ago)
-            //      into the slab record, L - 1 steps before anyone needs it
-            const unsigned gidx = (s - 1) * W + worker;
-            const unsigned slab = fastdiv(gidx, g.divP);
-            if (gidx == slab * g.P) {
-                if (tr) flat_trace(g, s - 1, TR_GA_BEGIN);
-                const SlabStat st = fold_slab_stats<VN>(g, slab, Mf, lane);
-                if (lane == 0) {
-                    const float rstd = 1.f / sqrtf(st.m2 / Mf + p.eps);  // biased variance, eps inside the sqrt
-                    ll_store(g.ws_slab + slab, st.mean, rstd, g.epoch);
-                    if (p.save_mean) {
-                        p.save_mean[slab] = st.mean;
-                        p.save_rstd[slab] = rstd;
-                    }
+                const float invM = 1.f / (float)p.M;
+                const float m = A * invM;
+                const float mean = ref + m;
+                const float rstd = 1.f / sqrtf(fmaxf(B - A * m, 0.f) * invM + p.eps);  // biased variance, eps inside the sqrt
+                const float a = rstd * gamma;
+                // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element.
+                *reinterpret_cast<float4*>(c.coefv + e.i * 8) =
+                    make_float4(sizeof(T) == 4 ? mean : 0.f, a, sizeof(T) == 4 ? beta : fmaf(-mean, a, beta), 0.f);
+                if (pc.k == 0 && p.save_mean) {
+                    p.save_mean[pc.slab] = mean;
+                    p.save_rstd[pc.slab] = rstd;
                 }
-                if (tr) flat_trace(g, s - 1, TR_GA_END);
+                mbar_arrive(c.coef0 + 8 * e.i);
+                flat_trace(g, j, TR_GA_END);
             }
+            __syncwarp();
         }
-        if (hasB) {
-            // ---- P2(s - L): normalise + epilogue from the piece's second (L2-served) copy
-            const unsigned j = s - g.L;
-            if (tr) flat_trace(g, j, TR_P2_WAIT);
-            float mean, rstd;
-            if (!ll_poll_short(g.ws_slab + tb.slab, g.epoch, g.poll_backoff_ns, mean, rstd)) {
-                const SlabStat st = fold_slab_stats<VN>(g, tb.slab, Mf, lane);  // the owner is late: same fold, same bits
-                mean = st.mean;
-                rstd = 1.f / sqrtf(st.m2 / Mf + p.eps);
+    } else {
+        // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
+        Ring ra{0u, 0u}, rb{0u, 0u};
+        for (unsigned s = 0; s < nj + g.L; ++s) {
+            if (s < nj) {
+                // ---- P1(s): statistics; the slot goes straight back, the piece stays in L2
+                const Ring e = entry_of(s);
+                const unsigned gidx = s * G + cta;
+                const unsigned pv = piece_vecs(g, gidx - fastdiv(gidx, g.divP) * g.P);
+                mbar_wait_park(c.fullA + 8 * ra.i, ra.ph);
+                if (tid == 0) flat_trace(g, s, TR_P1_BEGIN);
+                const uint32_t base = c.dataA + ra.i * c.slot_bytes;
+                float Kw = 0.f;
+                f32x2 sacc = f2_splat(0.f), qacc = f2_splat(0.f), sacc2 = sacc, qacc2 = sacc;
+                if ((unsigned)warp * 32u < pv) {
+                    Kw = first_elem<T>(base + warp * 512);  // shift = the warp's first element of the piece
+                    const f32x2 K2 = f2_splat(Kw);
+                    uint4 q[4];
+                    piece_sweep<4>(
+                        pv, tid, [&](int i, unsigned v) { q[i] = lds128(base + v * 16); },
+                        [&](int i, unsigned) {
+                            f32x2 f[VN / 2];
+                            VecT<T>::unpack2(q[i], f);
+#pragma unroll
+                            for (int k = 0; k < VN / 2; k += 2) {  // two independent accumulator pairs
+                                const f32x2 d0 = f2_sub(f[k], K2), d1 = f2_sub(f[k + 1], K2);
+                                sacc = f2_add(sacc, d0);
+                                sacc2 = f2_add(sacc2, d1);
+                                qacc = f2_fma(d0, d0, qacc);
+                                qacc2 = f2_fma(d1, d1, qacc2);
+                            }
+                        });
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
+                const float s1 = warp_sum(f2_hsum(f2_add(sacc, sacc2))), s2 = warp_sum(f2_hsum(f2_add(qacc, qacc2)));
+                if (lane == 0) {
+                    *reinterpret_cast<float4*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) =
+                        make_float4(s1, s2, Kw, 0.f);
+                    mbar_arrive(c.p1d0 + 8 * e.i);
+                }
+                if (tid == 0) flat_trace(g, s, TR_P1_END);
+                ra.next(g.KA);
             }
-            const float ca = rstd * gamma;
-            // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element.
-            const float sub = sizeof(T) == 4 ? mean : 0.f, cb = sizeof(T) == 4 ? beta : fmaf(-mean, ca, beta);
-            if (tr) flat_trace(g, j, TR_P2_BEGIN);
-            const unsigned pv = tb.pv, nb = (pv + 32 * U - 1) / (32 * U);
-            for (unsigned b = 0; b < nb; ++b) {
-                if (b) loadB(tb, b, B);
+            if (s >= g.L) {
+                // ---- P2(s - L): normalise + epilogue from the piece's second (L2-served) copy
+                const unsigned j = s - g.L;
+                const Ring e = entry_of(j);
+                const PieceId pc = piece_of(g, j * G + cta);
+                const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
+                char* ydst = reinterpret_cast<char*>(p.y) + goff;
+                const uint32_t base = c.dataB + rb.i * c.slot_bytes_b;
+                if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
+                mbar_wait_park(c.coef0 + 8 * e.i, e.ph);
+                const float4 cf = *reinterpret_cast<const float4*>(c.coefv + e.i * 8);
+                const f32x2 sub2 = f2_splat(cf.x), ca2 = f2_splat(cf.y), cb2 = f2_splat(cf.z);
+                mbar_wait_park(c.fullB + 8 * rb.i, rb.ph);
+                if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
+                uint4 q[2], rq[2];
+                piece_sweep<2>(
+                    pc.pv, tid,
+                    [&](int i, unsigned v) {
+                        q[i] = lds128(base + v * 16);
+                        if (NSB == 2) rq[i] = lds128(base + c.stream_bytes + v * 16);
+                    },
+                    [&](int i, unsigned v) {
+                        f32x2 f[VN / 2], rr[VN / 2];
+                        VecT<T>::unpack2(q[i], f);
+                        if (NSB == 2) VecT<T>::unpack2(rq[i], rr);
 #pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    const unsigned v = lane + 32u * (b * U + i);
-                    if (v < pv) {
-                        float f[VN], rr[VN];
-                        VecT<T>::unpack(B.q[0][i], f);
-                        if (NS == 2) VecT<T>::unpack(B.q[NS - 1][i], rr);
-#pragma unroll
-                        for (int k = 0; k < VN; ++k) {
-                            float o = sizeof(T) == 4 ? fmaf(f[k] - sub, ca, cb) : fmaf(f[k], ca, cb);
-                            if (NS == 2) o += rr[k];
-                            if (EPI != MICN_EPI_NONE) o = o > 0.f ? o : o * p.slope;
+                        for (int k = 0; k < VN / 2; ++k) {
+                            f32x2 o = sizeof(T) == 4 ? f2_fma(f2_sub(f[k], sub2), ca2, cb2) : f2_fma(f[k], ca2, cb2);
+                            if (NSB == 2) o = f2_add(o, rr[k]);
+                            if (EPI != MICN_EPI_NONE) {
+                                float lo, hi;
+                                f2_split(o, lo, hi);
+                                lo = lo > 0.f ? lo : lo * p.slope;
+                                hi = hi > 0.f ? hi : hi * p.slope;
+                                o = f2_make(lo, hi);
+                            }
                             f[k] = o;
                         }
-                        stg_stream(yb + tb.doff + (size_t)(b * U + i) * 512, VecT<T>::pack(f));
-                    }
-                }
+                        stg_stream(ydst + (size_t)v * 16, VecT<T>::pack2v(f));
+                    });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.emptyB + 8 * rb.i);
+                if (tid == 0) flat_trace(g, j, TR_P2_END);
+                rb.next(g.KB);
             }
-            if (tr) flat_trace(g, j, TR_P2_END);
         }
     }
 }
@@ -410,141 +507,144 @@ __device__ __forceinline__ float bwd_masked(float x, float gy, float o, float me
     return gy;
 }
 
+// the same on a packed pair (FFMA2 evaluates each half exactly like the scalar fmaf of the forward)
+template <typename T, int EPI>
+__device__ __forceinline__ f32x2 bwd_masked2(f32x2 x, f32x2 gy, f32x2 o, f32x2 mean2, f32x2 a2, f32x2 bq2, float slope) {
+    if (EPI == MICN_EPI_NONE) return gy;
+    const f32x2 pre = EPI == MICN_EPI_ADD_LRELU ? o : (sizeof(T) == 4 ? f2_fma(f2_sub(x, mean2), a2, bq2) : f2_fma(x, a2, bq2));
+    // the reference masks on the ROUNDED output (in-place LeakyReLU on the norm's 16-bit result): an fp16 value in
+    // (0, 2^-25] rounds to +0 and counts as "not positive"; bf16 and fp32 share fp32's exponent range
+    const float zero = (EPI == MICN_EPI_LRELU && sizeof(T) == 2 && !VecT<T>::kWideExponent) ? 2.98023224e-8f : 0.f;
+    float p0, p1, g0, g1;
+    f2_split(pre, p0, p1);
+    f2_split(gy, g0, g1);
+    return f2_make(p0 > zero ? g0 : g0 * slope, p1 > zero ? g1 : g1 * slope);
+}
+
 // (mean, rstd, gamma, beta) of a slab
 template <typename P>
 __device__ __forceinline__ float4 slab_consts(const P& p, unsigned slab, unsigned n, unsigned ch) {
     const int style = load_style(p.styles, n, p.num_styles, p.status);
     float gamma, beta;
-    load_affine_gc(p, style, ch, gamma, beta);
+    load_affine(p, style, ch, gamma, beta);
     return make_float4(__ldg(p.save_mean + slab), __ldg(p.save_rstd + slab), gamma, beta);
 }
 
-// sum of a slab's piece records (sum g, sum g*(x-mean)); every lane returns the totals
-__device__ __noinline__ float2 fold_slab_sums(const FlatGeom& g, unsigned slab, int lane) {
-    float S1 = 0.f, S2 = 0.f;
-    ll_gather(g.ws_piece + (size_t)slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane, [](float, float) {},
-              [&](unsigned, float a, float b) {
-                  S1 += a;
-                  S2 += b;
-              });
-    return make_float2(warp_sum(S1), warp_sum(S2));
-}
-
 template <typename T, int EPI>
-__global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ FlatGeom g) {
+__global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
     constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
     constexpr int VN = VecT<T>::N;
-    constexpr int U = kFlatLoadsPerLane / NS;  // vectors per lane per stream per batch
-    const unsigned G = gridDim.x, W = G * kFlatWarps;
-    const int lane = threadIdx.x & 31;
-    const unsigned worker = (threadIdx.x >> 5) * G + blockIdx.x;
-    const unsigned nj = worker < g.T ? (g.T - worker + W - 1) / W : 0;
+    constexpr int U = NS == 3 ? 1 : 2;  // vectors per thread in flight per stream (register budget: 72)
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FlatCtx c = flat_setup<NS, NS>(smem, g);
+    const unsigned cta = blockIdx.x, G = gridDim.x;
+    const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned C = (unsigned)p.C;
-    const bool tr = threadIdx.x == 0;
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
-    const float invM = 1.f / (float)p.M;
-    const char* xb = reinterpret_cast<const char*>(p.x);
-    const char* gb = reinterpret_cast<const char*>(p.dy);
-    const char* ob = reinterpret_cast<const char*>(p.act_out);
-    char* dxb = reinterpret_cast<char*>(p.dx);
-    char* drb = reinterpret_cast<char*>(p.dres);
 
-    auto load = [&](const FlatTask& t, unsigned b, Batch<NS, U>& Q, uint64_t pol) {
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const unsigned v = lane + 32u * (b * U + i);
-            if (v < t.pv) {
-                const size_t o = (size_t)(b * U + i) * 512;
-                Q.q[0][i] = ldg_hint(xb + t.xoff + o, pol);
-                Q.q[1][i] = ldg_hint(gb + t.doff + o, pol);
-                if (NS == 3) Q.q[NS - 1][i] = ldg_hint(ob + t.doff + o, pol);
-            }
-        }
-    };
-
-    FlatTask ta, tb;
-    Batch<NS, U> A, B;
-    float4 pra = make_float4(0.f, 0.f, 0.f, 0.f), prb = pra;
-    if (nj) {
-        ta = flat_task(g, worker, C, p.x_sN, p.x_sC, p.M, sizeof(T), lane);
-        load(ta, 0, A, pol_keep);
-        pra = slab_consts(p, ta.slab, ta.n, ta.ch);
-    }
-    for (unsigned s = 0; s < nj + g.L; ++s) {
-        const bool hasB = s >= g.L;
-        if (hasB) {
-            // ---- second touch of piece s-L: its batch (L2) and constants go in flight now
-            tb = flat_task(g, (s - g.L) * W + worker, C, p.x_sN, p.x_sC, p.M, sizeof(T), lane);
-            load(tb, 0, B, pol_done);
-            prb = slab_consts(p, tb.slab, tb.n, tb.ch);
-        }
-        if (s < nj) {
-            // ---- P1(s): sum g, sum g*(x - mean) of this worker's piece -> piece record
-            if (tr) flat_trace(g, s, TR_P1_BEGIN);
-            const float mean = pra.x, ca = pra.y * pra.z;
-            const float bq = sizeof(T) == 4 ? pra.w : fmaf(-mean, ca, pra.w);
-            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-            const unsigned pv = ta.pv, nb = (pv + 32 * U - 1) / (32 * U);
-            for (unsigned b = 0; b < nb; ++b) {
-                if (b) load(ta, b, A, pol_keep);
-#pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    const unsigned v = lane + 32u * (b * U + i);
-                    if (v < pv) {
-                        float xf[VN], gf[VN], of[VN];
-                        VecT<T>::unpack(A.q[0][i], xf);
-                        VecT<T>::unpack(A.q[1][i], gf);
-                        if (NS == 3) VecT<T>::unpack(A.q[NS - 1][i], of);
-#pragma unroll
-                        for (int k = 0; k < VN; k += 2) {
-                            const float g0 = bwd_masked<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0.f, mean, ca, bq, p.slope);
-                            const float g1 = bwd_masked<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0.f, mean, ca, bq, p.slope);
-                            s1a += g0;
-                            s1b += g1;
-                            s2a = fmaf(g0, xf[k] - mean, s2a);
-                            s2b = fmaf(g1, xf[k + 1] - mean, s2b);
-                        }
-                    }
+    if (warp == kFlatProducerWarpA || warp == kFlatProducerWarpB) {
+        // ------------------------------------------------------------------ producers (A: first touch, B: second touch)
+        if (lane == 0) {
+            const bool isA = warp == kFlatProducerWarpA;
+            const uint64_t pol = isA ? l2_policy_evict_last() : l2_policy_evict_first();
+            const unsigned K = isA ? g.KA : g.KB;
+            const uint32_t full0 = isA ? c.fullA : c.fullB, empty0 = isA ? c.emptyA : c.emptyB;
+            const uint32_t data0 = isA ? c.dataA : c.dataB;
+            Ring r{0u, 0u};
+            for (unsigned j = 0; j < nj; ++j) {
+                const PieceId pc = piece_of(g, j * G + cta);
+                const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+                float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (isA) pr = slab_consts(p, pc.slab, n, ch);  // for P1: loads issued before the waits
+                const size_t poff = (size_t)pc.k * g.PV * 16;
+                const size_t doff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + poff;
+                const char* xsrc = reinterpret_cast<const char*>(p.x) +
+                                   ((long long)n * p.x_sN + (long long)ch * p.x_sC) * (long long)sizeof(T) + poff;
+                const uint32_t bytes = pc.pv * 16u, bar = full0 + 8 * r.i;
+                const uint32_t dst = data0 + r.i * c.slot_bytes;
+                if (!isA) {
+                    const Ring e = entry_of(j);
+                    mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
                 }
-            }
-            const float s1 = warp_sum(s1a + s1b), s2 = warp_sum(s2a + s2b);
-            if (lane == 0) ll_store(g.ws_piece + ta.gidx, s1, s2, g.epoch);
-            if (tr) flat_trace(g, s, TR_P1_END);
-            // ---- first touch of piece s+1 goes in flight (HBM) while this step folds and writes dx
-            if (s + 1 < nj) {
-                ta = flat_task(g, (s + 1) * W + worker, C, p.x_sN, p.x_sC, p.M, sizeof(T), lane);
-                load(ta, 0, A, pol_keep);
-                pra = slab_consts(p, ta.slab, ta.n, ta.ch);
+                if (j >= K) mbar_wait_park(empty0 + 8 * r.i, r.ph ^ 1u);
+                flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
+                flat_issue(dst, xsrc, bytes, bar, pol);
+                flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
+                if (NS == 3)
+                    flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(p.act_out) + doff, bytes, bar, pol);
+                if (isA) *reinterpret_cast<float4*>(c.slot_prec + r.i * 4) = pr;  // visible through the barrier
+                mbar_arrive_expect_tx(bar, bytes * NS);
+                r.next(K);
             }
         }
-        if (s >= 1 && s - 1 < nj) {
-            // ---- fold: the owner of a slab's piece 0 sums the slab's piece records (all written a step ago)
-            //      into the slab record, L - 1 steps before anyone needs it
-            const unsigned gidx = (s - 1) * W + worker;
-            const unsigned slab = fastdiv(gidx, g.divP);
-            if (gidx == slab * g.P) {
-                const unsigned n = fastdiv(slab, g.divC), ch = slab - n * C;
-                const float rstd = __ldg(p.save_rstd + slab);
-                if (tr) flat_trace(g, s - 1, TR_GA_BEGIN);
-                const float2 S = fold_slab_sums(g, slab, lane);
-                const float S1 = S.x, S2r = S.y * rstd;  // sum g, sum g * xhat
-                if (lane == 0) ll_store(g.ws_slab + slab, S1, S2r, g.epoch);
-                if (p.dgamma) {
-                    if (p.N == 1) {
-                        // one sample: this slab's sums ARE the gradients of its style's row
-                        const int style = load_style(p.styles, 0, p.num_styles, nullptr);
-                        for (int st = lane; st < p.num_styles; st += 32) {
-                            p.dbeta[(size_t)st * C + ch] = st == style ? S1 : 0.f;
-                            p.dgamma[(size_t)st * C + ch] = st == style ? S2r : 0.f;
-                        }
-                    } else if (n == (unsigned)p.N - 1) {
-                        // last sample of this channel: fold every sample's slab record per style, fixed order
-                        for (int st = 0; st < p.num_styles; ++st) {
+    } else if (warp >= kFlatPublishWarp0 && warp < kFlatGatherWarp0) {
+        // ------------------------------------------------------------------ publish
+        for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
+            const Ring e = entry_of(j);
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
+            if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
+            float s1 = 0.f, s2 = 0.f;
+            if (lane < kFlatConsumerWarps) {
+                const float2 w = *reinterpret_cast<const float2*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
+                s1 = w.x;
+                s2 = w.y;
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) ll_store(g.ws_piece + (j * G + cta), s1, s2, g.epoch);
+            if (lane == 0) flat_trace(g, j, TR_PUB_END);
+        }
+    } else if (warp >= kFlatGatherWarp0) {
+        // ------------------------------------------------------------------ gather
+        const float invM = 1.f / (float)p.M;
+        for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
+            const Ring e = entry_of(j);
+            const PieceId pc = piece_of(g, j * G + cta);
+            const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
+            const float4 pr = slab_consts(p, pc.slab, n, ch);  // latency hides behind the wait below
+            const float mean = pr.x, rstd = pr.y, gamma = pr.z, beta = pr.w;
+            // no polling before this CTA's own piece is through P1 (the others are at the same point)
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
+            __nanosleep(g.poll_delay_ns);  // let the record stores land
+            if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
+            float S1 = 0.f, S2 = 0.f;
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane, [](float, float) {},
+                      [&](unsigned, float a, float b) {
+                          S1 += a;
+                          S2 += b;
+                      });
+            if (lane == 0) flat_trace(g, j, TR_GA_POLLED);
+            S1 = warp_sum(S1);
+            S2 = warp_sum(S2);
+            const float a = rstd * gamma;
+            const float S2r = S2 * rstd;  // sum g * xhat
+            if (lane == 0) {
+                // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
+                const float B1 = -a * S2r * invM * rstd, B0c = -a * S1 * invM;
+                float* cf = c.coefv + e.i * 8;
+                *reinterpret_cast<float4*>(cf) = make_float4(a, B1, sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c), mean);
+                cf[4] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
+                mbar_arrive(c.coef0 + 8 * e.i);
+                flat_trace(g, j, TR_GA_END);
+            }
+            if (pc.k == 0 && p.dgamma) {
+                if (p.N == 1) {
+                    // one sample: this slab's sums ARE the gradients of its style's row
+                    const int style = load_style(p.styles, 0, p.num_styles, nullptr);
+                    for (int s = lane; s < p.num_styles; s += 32) {
+                        p.dbeta[(size_t)s * C + ch] = s == style ? S1 : 0.f;
+                        p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
+                    }
+                } else {
+                    if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, g.epoch);
+                    if (n == (unsigned)p.N - 1) {
+                        // last sample of this channel: fold every sample's record per style, fixed order
+                        for (int s = 0; s < p.num_styles; ++s) {
                             float ab = 0.f, ag = 0.f;
                             for (unsigned nn = lane; nn < (unsigned)p.N; nn += 32) {
                                 float ra, rb;
                                 ll_wait1(g.ws_slab + (size_t)nn * C + ch, g.epoch, g.poll_backoff_ns, ra, rb);
-                                if (load_style(p.styles, nn, p.num_styles, nullptr) == st) {
+                                if (load_style(p.styles, nn, p.num_styles, nullptr) == s) {
                                     ab += ra;
                                     ag += rb;
                                 }
@@ -552,55 +652,110 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const __
                             ab = warp_sum(ab);
                             ag = warp_sum(ag);
                             if (lane == 0) {
-                                p.dbeta[(size_t)st * C + ch] = ab;
-                                p.dgamma[(size_t)st * C + ch] = ag;
+                                p.dbeta[(size_t)s * C + ch] = ab;
+                                p.dgamma[(size_t)s * C + ch] = ag;
                             }
                         }
                     }
                 }
-                if (tr) flat_trace(g, s - 1, TR_GA_END);
             }
+            __syncwarp();
         }
-        if (hasB) {
-            // ---- P2(s - L)
-            const unsigned j = s - g.L;
-            if (tr) flat_trace(g, j, TR_P2_WAIT);
-            const float mean = prb.x, rstd = prb.y, Ac = rstd * prb.z;
-            float S1, S2r;
-            if (!ll_poll_short(g.ws_slab + tb.slab, g.epoch, g.poll_backoff_ns, S1, S2r)) {
-                const float2 S = fold_slab_sums(g, tb.slab, lane);  // the owner is late: same fold, same bits
-                S1 = S.x;
-                S2r = S.y * rstd;
-            }
-            // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
-            const float B1 = -Ac * S2r * invM * rstd, B0c = -Ac * S1 * invM;
-            const float B0 = sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c);
-            const float bq = sizeof(T) == 4 ? prb.w : fmaf(-mean, Ac, prb.w);
-            if (tr) flat_trace(g, j, TR_P2_BEGIN);
-            const unsigned pv = tb.pv, nb = (pv + 32 * U - 1) / (32 * U);
-            for (unsigned b = 0; b < nb; ++b) {
-                if (b) load(tb, b, B, pol_done);
+    } else {
+        // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
+        Ring ra{0u, 0u}, rb{0u, 0u};
+        const uint32_t sb = c.stream_bytes;
+        for (unsigned s = 0; s < nj + g.L; ++s) {
+            if (s < nj) {
+                // ---- P1(s)
+                const Ring e = entry_of(s);
+                const unsigned gidx = s * G + cta;
+                const unsigned pv = piece_vecs(g, gidx - fastdiv(gidx, g.divP) * g.P);
+                mbar_wait_park(c.fullA + 8 * ra.i, ra.ph);
+                if (tid == 0) flat_trace(g, s, TR_P1_BEGIN);
+                const uint32_t base = c.dataA + ra.i * c.slot_bytes;
+                const float4 pr = *reinterpret_cast<const float4*>(c.slot_prec + ra.i * 4);
+                const float mean = pr.x, ca = pr.y * pr.z;
+                const float bq = sizeof(T) == 4 ? pr.w : fmaf(-mean, ca, pr.w);
+                const f32x2 mean2 = f2_splat(mean), ca2 = f2_splat(ca), bq2 = f2_splat(bq);
+                f32x2 s1a = f2_splat(0.f), s1b = s1a, s2a = s1a, s2b = s1a;
+                uint4 qx[U], qg[U], qo[U];
+                piece_sweep<U>(
+                    pv, tid,
+                    [&](int i, unsigned v) {
+                        qx[i] = lds128(base + v * 16);
+                        qg[i] = lds128(base + sb + v * 16);
+                        if (NS == 3) qo[i] = lds128(base + 2 * sb + v * 16);
+                    },
+                    [&](int i, unsigned) {
+                        f32x2 xf[VN / 2], gf[VN / 2], of[VN / 2];
+                        VecT<T>::unpack2(qx[i], xf);
+                        VecT<T>::unpack2(qg[i], gf);
+                        if (NS == 3) VecT<T>::unpack2(qo[i], of);
 #pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    const unsigned v = lane + 32u * (b * U + i);
-                    if (v < pv) {
-                        float xf[VN], gf[VN], of[VN];
-                        VecT<T>::unpack(B.q[0][i], xf);
-                        VecT<T>::unpack(B.q[1][i], gf);
-                        if (NS == 3) VecT<T>::unpack(B.q[NS - 1][i], of);
-#pragma unroll
-                        for (int k = 0; k < VN; ++k) {
-                            const float gg = bwd_masked<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0.f, mean, Ac, bq, p.slope);
-                            gf[k] = gg;
-                            xf[k] = sizeof(T) == 4 ? fmaf(Ac, gg, fmaf(B1, xf[k] - mean, B0)) : fmaf(Ac, gg, fmaf(B1, xf[k], B0));
+                        for (int k = 0; k < VN / 2; k += 2) {
+                            const f32x2 g0 = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, ca2, bq2, p.slope);
+                            const f32x2 g1 = bwd_masked2<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0ull, mean2, ca2, bq2, p.slope);
+                            s1a = f2_add(s1a, g0);
+                            s1b = f2_add(s1b, g1);
+                            s2a = f2_fma(g0, f2_sub(xf[k], mean2), s2a);
+                            s2b = f2_fma(g1, f2_sub(xf[k + 1], mean2), s2b);
                         }
-                        const size_t o = (size_t)(b * U + i) * 512;
-                        stg_stream(dxb + tb.doff + o, VecT<T>::pack(xf));
-                        if (NS == 3) stg_stream(drb + tb.doff + o, VecT<T>::pack(gf));
-                    }
+                    });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
+                const float s1 = warp_sum(f2_hsum(f2_add(s1a, s1b))), s2 = warp_sum(f2_hsum(f2_add(s2a, s2b)));
+                if (lane == 0) {
+                    *reinterpret_cast<float2*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) = make_float2(s1, s2);
+                    mbar_arrive(c.p1d0 + 8 * e.i);
                 }
+                if (tid == 0) flat_trace(g, s, TR_P1_END);
+                ra.next(g.KA);
             }
-            if (tr) flat_trace(g, j, TR_P2_END);
+            if (s >= g.L) {
+                // ---- P2(s - L)
+                const unsigned j = s - g.L;
+                const Ring e = entry_of(j);
+                const PieceId pc = piece_of(g, j * G + cta);
+                const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
+                char* dxdst = reinterpret_cast<char*>(p.dx) + goff;
+                char* drdst = NS == 3 ? reinterpret_cast<char*>(p.dres) + goff : nullptr;
+                const uint32_t base = c.dataB + rb.i * c.slot_bytes;
+                if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
+                mbar_wait_park(c.coef0 + 8 * e.i, e.ph);
+                const float* cf = c.coefv + e.i * 8;
+                const float4 cq = *reinterpret_cast<const float4*>(cf);
+                const f32x2 A2 = f2_splat(cq.x), B12 = f2_splat(cq.y), B02 = f2_splat(cq.z), mean2 = f2_splat(cq.w),
+                            bq2 = f2_splat(cf[4]);
+                mbar_wait_park(c.fullB + 8 * rb.i, rb.ph);
+                if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
+                uint4 qx[U], qg[U], qo[U];
+                piece_sweep<U>(
+                    pc.pv, tid,
+                    [&](int i, unsigned v) {
+                        qx[i] = lds128(base + v * 16);
+                        qg[i] = lds128(base + sb + v * 16);
+                        if (NS == 3) qo[i] = lds128(base + 2 * sb + v * 16);
+                    },
+                    [&](int i, unsigned v) {
+                        f32x2 xf[VN / 2], gf[VN / 2], of[VN / 2];
+                        VecT<T>::unpack2(qx[i], xf);
+                        VecT<T>::unpack2(qg[i], gf);
+                        if (NS == 3) VecT<T>::unpack2(qo[i], of);
+#pragma unroll
+                        for (int k = 0; k < VN / 2; ++k) {
+                            const f32x2 gg = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, A2, bq2, p.slope);
+                            gf[k] = gg;
+                            xf[k] = f2_fma(A2, gg, f2_fma(B12, sizeof(T) == 4 ? f2_sub(xf[k], mean2) : xf[k], B02));
+                        }
+                        stg_stream(dxdst + (size_t)v * 16, VecT<T>::pack2v(xf));
+                        if (NS == 3) stg_stream(drdst + (size_t)v * 16, VecT<T>::pack2v(gf));
+                    });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.emptyB + 8 * rb.i);
+                if (tid == 0) flat_trace(g, j, TR_P2_END);
+                rb.next(g.KB);
+            }
         }
     }
 }
