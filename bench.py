@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--epilogue", default="none", choices=["none", "lrelu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
     ap.add_argument("--sweep", action="store_true", help="also time the BASELINE.json microbench sweep (extra key)")
     return ap.parse_args()
 
@@ -63,6 +64,21 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(args, n, c, s):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the backward kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/); None for any other workload."""
+    if (n, c, s, args.dtype, args.epilogue) != (1, 48, 96, "bf16", "none"):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_flat_bwd_bf16_1x48x96.txt")) as f:
+            for line in f:
+                if line.strip().startswith("traffic ="):
+                    return float(line.split()[-1])
+    except Exception:
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -337,7 +353,7 @@ def run_ours(args):
 
     # ---- like-for-like GPU competitor: the reference's call sequence on the same B200 through PyTorch
     torch_gpu = None
-    if rank == 0:
+    if rank == 0 and not args.no_torch_ref:
         import torch.nn.functional as F
         xg = xs[0].reshape(n, c, s, s, s).detach().requires_grad_(True)
         dyg = dys[0].reshape(n, c, s, s, s)
@@ -372,7 +388,8 @@ def run_ours(args):
     bwd_gbps = bytes_bwd / (bwd_avg * 1e-6) / 1e9
     fwd_gbps = bytes_fwd / (fwd_avg * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "micn_bwd (backward, 3*E*s algorithmic bytes per launch)",
-                "achieved": bwd_gbps, "peak": peak, "unit": "GB/s", "frac": bwd_gbps / peak, "traffic": None,
+                "achieved": bwd_gbps, "peak": peak, "unit": "GB/s", "frac": bwd_gbps / peak,
+                "traffic": ncu_traffic(args, n, c, s),
                 "peak_source": peak_src, "avg_launch_us": bwd_avg, "bytes_per_launch": bytes_bwd,
                 "fwd": {"achieved": fwd_gbps, "frac": fwd_gbps / peak, "avg_launch_us": fwd_avg,
                         "bytes_per_launch": bytes_fwd},

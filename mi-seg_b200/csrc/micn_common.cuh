@@ -449,14 +449,20 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_park_t(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_hint(bar, parity, 1000u)) return;
     const uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (((++spins) & 0x3fu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+    for (;;) {
+        __nanosleep(SLEEP_NS);  // the suspend hint alone still lets the warp re-issue every few hundred cycles
+        if (mbar_try_wait_hint(bar, parity, 10000u)) return;
+        if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
     }
 }
+// consumers (on the critical path: short naps) / helper warps (producers, publish, gather: longer naps)
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) { mbar_wait_park_t<32>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) { mbar_wait_park_t<200>(bar, parity); }
 
 // x / d for x < 2^31 with a precomputed multiplier (host: fastdiv_make)
 struct FastDiv {
