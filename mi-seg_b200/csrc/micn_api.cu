@@ -319,7 +319,7 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     const long long V = slab_bytes / 16;
     const long long ring = (long long)d.smem_optin - flat_ctl_bytes() - 128;
     long long ovh = g_opt.flat_ovh_vecs.load();
-    if (ovh < 0) ovh = 128;
+    if (ovh < 0) ovh = 2200;
 
     // ring A holds the bytes in flight from HBM (~100 KB per SM streams at the full read rate, tools/streambw.cu;
     // anything much deeper only adds queueing delay to the record exchange); ring B re-reads from L2
@@ -357,9 +357,10 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
         const long long T = slabs * Pe;
         if (T > 0x7fffffffLL) break;
         const long long rounds = (T + G - 1) / G;
-        // bytes cost what they are; the consumer loops cost whole 512-vector sweeps
+        // a round costs its swept vectors (the consumer loops run whole 512-vector sweeps) plus a fixed latency
+        // chain per piece (barrier wake-ups, shuffles, hand-offs: ~1 us, i.e. ~2200 vectors of HBM time per SM)
         const long long sweep = (PV + kFlatConsumerThreads - 1) / kFlatConsumerThreads * kFlatConsumerThreads;
-        const double cost = (double)rounds * (0.5 * (double)PV + 0.5 * (double)sweep + (double)ovh);
+        const double cost = (double)rounds * ((double)sweep + (double)ovh);
         if (cost < best * 0.9999) {
             best = cost;
             bestP = Pe;
