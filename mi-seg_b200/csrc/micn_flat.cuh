@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
                 const uint32_t bytes = pc.pv * 16u, bar = full0 + 8 * r.i;
                 if (!isA) {  // the second touch must find the piece in L2: not before its first touch is through
                     const Ring e = entry_of(j);
-                    mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
+                    mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
                 }
-                if (j >= K) mbar_wait_idle(empty0 + 8 * r.i, r.ph ^ 1u);
+                if (j >= K) mbar_wait_park(empty0 + 8 * r.i, r.ph ^ 1u);
                 flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
                 const uint32_t dst = data0 + r.i * (isA ? c.slot_bytes : c.slot_bytes_b);
                 flat_issue(dst, src, bytes, bar, pol);
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
             const unsigned k = gidx - fastdiv(gidx, g.divP) * g.P;
             const unsigned pv = piece_vecs(g, k);
             const float nw = lane < kFlatConsumerWarps ? (float)(warp_vecs(pv, lane) * VN) : 0.f;
-            mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
             Stat st{0.f, 0.f, 0.f};
             if (lane < kFlatConsumerWarps) {
@@ -564,9 +564,9 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                 const uint32_t dst = data0 + r.i * c.slot_bytes;
                 if (!isA) {
                     const Ring e = entry_of(j);
-                    mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
+                    mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
                 }
-                if (j >= K) mbar_wait_idle(empty0 + 8 * r.i, r.ph ^ 1u);
+                if (j >= K) mbar_wait_park(empty0 + 8 * r.i, r.ph ^ 1u);
                 flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
                 flat_issue(dst, xsrc, bytes, bar, pol);
                 flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
         // ------------------------------------------------------------------ publish
         for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
             const Ring e = entry_of(j);
-            mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
+            mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
             float s1 = 0.f, s2 = 0.f;
             if (lane < kFlatConsumerWarps) {
