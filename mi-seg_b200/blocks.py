@@ -18,7 +18,7 @@ import types
 
 import torch.nn as nn
 
-from .norms import FastForwardMixin
+from .norms import FastForwardMixin, FastPlainForwardMixin
 
 _MISSING = "Modalities must be passed to the forward step when encoder_norm_type is 'instance_cond'."
 
@@ -27,9 +27,14 @@ def _slope(block) -> float:
     return float(getattr(block.lrelu, "negative_slope", 0.01))
 
 
+def _needs_modalities(block) -> bool:
+    return any(isinstance(getattr(block, n, None), FastForwardMixin) for n in ("norm1", "norm2", "norm3"))
+
+
 def unet_res_block_forward(self, inp, modalities=None):
-    """Drop-in for UnetResBlock.forward (dynunet_block.py:100-126) with fused epilogues."""
-    if modalities is None:
+    """Drop-in for UnetResBlock.forward (dynunet_block.py:100-126) with fused epilogues.  Works for the
+    conditional norms (modalities required, as in the reference) and for the decoders' plain instance norms."""
+    if modalities is None and _needs_modalities(self):
         raise ValueError(_MISSING)
     slope = _slope(self)
     out = self.conv1(inp)
@@ -39,13 +44,13 @@ def unet_res_block_forward(self, inp, modalities=None):
     if hasattr(self, "conv3"):
         residual = self.conv3(residual)
     if hasattr(self, "norm3"):
-        residual = self.norm3(residual, modalities)
+        residual = self.norm3.forward_fused(residual, modalities, "none")
     return self.norm2.forward_fused(out, modalities, "add_lrelu", residual=residual, slope=slope)
 
 
 def unet_basic_block_forward(self, inp, modalities=None):
     """Drop-in for UnetBasicBlock.forward (dynunet_block.py:187-203) with fused epilogues."""
-    if modalities is None:
+    if modalities is None and _needs_modalities(self):
         raise ValueError(_MISSING)
     slope = _slope(self)
     out = self.conv1(inp)
@@ -55,10 +60,11 @@ def unet_basic_block_forward(self, inp, modalities=None):
 
 
 def _fusable(block) -> bool:
+    fast = (FastForwardMixin, FastPlainForwardMixin)
     norms = [getattr(block, n, None) for n in ("norm1", "norm2")]
-    if not all(isinstance(n, FastForwardMixin) for n in norms):
+    if not all(isinstance(n, fast) for n in norms):
         return False
-    if hasattr(block, "norm3") and not isinstance(block.norm3, FastForwardMixin):
+    if hasattr(block, "norm3") and not isinstance(block.norm3, fast):
         return False
     return isinstance(getattr(block, "lrelu", None), nn.LeakyReLU) and hasattr(block, "conv1") and hasattr(block, "conv2")
 

@@ -16,6 +16,7 @@ import importlib
 from . import norms
 
 _installed = None
+_installed_plain = None
 
 
 def install(factories_module: str = "networks.layers.factories",
@@ -36,14 +37,46 @@ def install(factories_module: str = "networks.layers.factories",
 
 
 def uninstall():
-    """Restore MI-Seg's own classes under "instance_cond"."""
-    global _installed
-    if _installed is None:
-        return
-    factories, ref, _ = _installed
-    types = (ref.ConditionalInstanceNorm1d, ref.ConditionalInstanceNorm2d, ref.ConditionalInstanceNorm3d)
-    factories.Norm.add_factory_callable("instance_cond", lambda dim: types[dim - 1])
-    _installed = None
+    """Restore MI-Seg's own classes under "instance_cond" (and torch's under "instance")."""
+    global _installed, _installed_plain
+    if _installed is not None:
+        factories, ref, _ = _installed
+        types = (ref.ConditionalInstanceNorm1d, ref.ConditionalInstanceNorm2d, ref.ConditionalInstanceNorm3d)
+        factories.Norm.add_factory_callable("instance_cond", lambda dim: types[dim - 1])
+        _installed = None
+    if _installed_plain is not None:
+        import torch.nn as nn
+
+        plain = (nn.InstanceNorm1d, nn.InstanceNorm2d, nn.InstanceNorm3d)
+        _installed_plain.Norm.add_factory_callable("instance", lambda dim: plain[dim - 1])
+        _installed_plain = None
+
+
+def install_plain(factories_module: str = "networks.layers.factories"):
+    """also route the decoders' plain `("instance", {"affine": True})` norms
+    (factories.py:221-224 -> nn.InstanceNorm{1,2,3}d) through the same kernels.  The fast classes derive from
+    torch's, so `isinstance(m, nn.InstanceNorm3d)` and every state-dict key stay as they were."""
+    global _installed_plain
+    factories = importlib.import_module(factories_module)
+    classes = (norms.FastInstanceNorm1d, norms.FastInstanceNorm2d, norms.FastInstanceNorm3d)
+    factories.Norm.add_factory_callable("instance", lambda dim: classes[dim - 1])
+    _installed_plain = factories
+    return classes
+
+
+def convert_plain(model):
+    """Re-class already-constructed plain nn.InstanceNorm{1,2,3}d modules (no running stats) to the fast
+    ones in place: parameters, buffers and state-dict keys are untouched."""
+    import torch.nn as nn
+
+    table = {nn.InstanceNorm1d: norms.FastInstanceNorm1d, nn.InstanceNorm2d: norms.FastInstanceNorm2d,
+             nn.InstanceNorm3d: norms.FastInstanceNorm3d}
+    count = 0
+    for m in model.modules():
+        if type(m) in table and not m.track_running_stats:
+            m.__class__ = table[type(m)]
+            count += 1
+    return count
 
 
 def convert_module(model, classes=None):

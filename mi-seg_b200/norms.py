@@ -23,7 +23,8 @@ from torch import Tensor
 from .functional import instance_cond
 
 __all__ = ["FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
-           "FastForwardMixin", "make_dropin_classes"]
+           "FastForwardMixin", "make_dropin_classes", "FastInstanceNorm1d", "FastInstanceNorm2d", "FastInstanceNorm3d",
+           "FastPlainForwardMixin", "fast_instance_norm"]
 
 _STYLE_CACHE = {}
 _STYLE_CACHE_MAX = 256
@@ -223,3 +224,69 @@ def make_dropin_classes(ref_module):
     return (build("FastConditionalInstanceNorm1d", ref_module.ConditionalInstanceNorm1d),
             build("FastConditionalInstanceNorm2d", ref_module.ConditionalInstanceNorm2d),
             build("FastConditionalInstanceNorm3d", ref_module.ConditionalInstanceNorm3d))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the plain (unconditional) instance norm of MI-Seg's decoders through the
+# same kernels.  `("instance", {"affine": True})` is the default `norm_name` of every UnetrUpBlock /
+# UnetResBlock of the decoders (networks/blocks/unetr_block.py:61-85, dynunet_block.py:100-126): as many
+# elements per C-Swin-UNETR forward as all instance_cond calls together.
+# ---------------------------------------------------------------------------------------------------
+class FastPlainForwardMixin:
+    """forward() of nn.InstanceNorm{1,2,3}d (torch/nn/modules/instancenorm.py:46-56, 104-125) on the
+    sm_100a kernels: one style, gamma/beta = self.weight / self.bias (or none when affine=False)."""
+
+    def forward(self, input: Tensor) -> Tensor:
+        return self.forward_fused(input, None, "none")
+
+    def forward_fused(self, input: Tensor, styles=None, epilogue: str = "none", residual: Optional[Tensor] = None,
+                      slope: float = 0.01) -> Tensor:
+        """`styles` is accepted (and ignored) so blocks.fuse_blocks() can treat both norm families alike."""
+        if self.track_running_stats:
+            raise NotImplementedError("track_running_stats=True is not supported by the fast instance norm "
+                                      "(MI-Seg never sets it)")
+        self._check_input_dim(input)
+        feature_dim = input.dim() - self._get_no_batch_dim()
+        if input.size(feature_dim) != self.num_features:
+            if self.affine:
+                raise ValueError(f"expected input's size at dim={feature_dim} to match num_features "
+                                 f"({self.num_features}), but got: {input.size(feature_dim)}.")
+            warnings.warn(f"input's size at dim={feature_dim} does not match num_features. "
+                          "You can silence this warning by not passing in num_features, "
+                          "which is not used because affine=False")
+        unbatched = input.dim() == self._get_no_batch_dim()
+        x = input.unsqueeze(0) if unbatched else input
+        m = 1
+        for s in x.shape[2:]:
+            m *= s
+        if m <= 1 and x.numel() > 0:
+            raise ValueError(f"Expected more than 1 spatial element when training, got input size {x.size()}")
+        if residual is not None and unbatched:
+            residual = residual.unsqueeze(0)
+        w = [self.weight] if self.affine else []
+        b = [self.bias] if self.affine else []
+        y = instance_cond(x, None, w, b, eps=self.eps, epilogue=epilogue, residual=residual, slope=slope,
+                          present=None, num_styles=1)
+        return y.squeeze(0) if unbatched else y
+
+
+class FastInstanceNorm1d(FastPlainForwardMixin, nn.InstanceNorm1d):
+    pass
+
+
+class FastInstanceNorm2d(FastPlainForwardMixin, nn.InstanceNorm2d):
+    pass
+
+
+class FastInstanceNorm3d(FastPlainForwardMixin, nn.InstanceNorm3d):
+    pass
+
+
+def fast_instance_norm(input: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+                       eps: float = 1e-5) -> Tensor:
+    """Drop-in for `F.instance_norm(x, weight=..., bias=..., use_input_stats=True)` on a batched [N, C, *]
+    CUDA tensor (e.g. SwinTransformer.proj_out, networks/nets/swin_transformer.py:135-136)."""
+    if (weight is None) != (bias is None):
+        raise ValueError("fast_instance_norm: pass both weight and bias, or neither")
+    return instance_cond(input, None, [weight] if weight is not None else [], [bias] if bias is not None else [],
+                         eps=eps, num_styles=1)

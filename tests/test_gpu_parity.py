@@ -459,3 +459,63 @@ def test_fused_block_matches_reference_block_end_to_end(pkg, path):
             assert present == list(g[f"{nm}_present"])
     with pytest.raises(ValueError, match="Modalities must be passed"):
         blk(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# the decoders' plain instance norm through the same kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("affine", [True, False], ids=["affine", "plain"])
+@pytest.mark.parametrize("shape", [(2, 6, 12, 12, 12), (1, 3, 48, 48, 48), (3, 5, 40)], ids=["12^3", "48^3", "1d"])
+def test_plain_instance_norm_vs_oracle(pkg, shape, affine, dtype):
+    gen = torch.Generator().manual_seed(11)
+    n, c = shape[0], shape[1]
+    cls = pkg.FastInstanceNorm1d if len(shape) == 3 else pkg.FastInstanceNorm3d
+    mod = cls(c, affine=affine).cuda()
+    gamma, beta = np.ones((1, c), np.float32), np.zeros((1, c), np.float32)
+    if affine:
+        gamma = (1 + 0.3 * torch.randn(1, c, generator=gen)).numpy()
+        beta = (0.3 * torch.randn(1, c, generator=gen)).numpy()
+        with torch.no_grad():
+            mod.weight.copy_(torch.from_numpy(gamma[0]))
+            mod.bias.copy_(torch.from_numpy(beta[0]))
+    xq = (torch.randn(*shape, generator=gen) * 2 + 1).to(dtype)
+    dyq = torch.randn(*shape, generator=gen).to(dtype)
+    x = xq.cuda().requires_grad_(True)
+    y = mod(x)
+    y.backward(dyq.cuda())
+    torch.cuda.synchronize()
+    st = [0] * n
+    yr, m_, r_ = O.fwd_f64(xq.float().numpy(), st, gamma, beta)
+    dxr, dgr, dbr, _ = O.bwd_f64(dyq.float().numpy(), xq.float().numpy(), st, gamma, m_, r_)
+    assert y.dtype == dtype and y.shape == x.shape
+    assert rel_err(y.detach().float().cpu().numpy(), yr) < TOL[dtype]
+    assert rel_err(x.grad.float().cpu().numpy(), dxr) < TOL[dtype]
+    if affine:
+        ptol = 5e-5 if dtype == torch.float32 else 5e-3
+        assert rel_err(mod.weight.grad.cpu().numpy()[None], dgr) < ptol
+        assert rel_err(mod.bias.grad.cpu().numpy()[None], dbr) < ptol
+
+
+def test_plain_instance_norm_matches_torch_module_and_functional(pkg):
+    """Same numbers as torch's own nn.InstanceNorm3d / F.instance_norm on the same GPU (fp32, 1e-5)."""
+    torch.manual_seed(5)
+    ref = torch.nn.InstanceNorm3d(7, affine=True).cuda()
+    with torch.no_grad():
+        ref.weight.normal_(1, 0.3)
+        ref.bias.normal_(0, 0.3)
+    fast = pkg.FastInstanceNorm3d(7, affine=True).cuda()
+    fast.load_state_dict(ref.state_dict())
+    assert isinstance(fast, torch.nn.InstanceNorm3d)
+    x = torch.randn(2, 7, 20, 20, 20, device="cuda") * 3 - 1
+    a, b = fast(x), ref(x)
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-5
+    f = pkg.fast_instance_norm(x)
+    g = torch.nn.functional.instance_norm(x)
+    assert float((f - g).abs().max() / g.abs().max()) < 1e-5
+    # convert_plain re-classes an existing model in place
+    model = torch.nn.Sequential(torch.nn.Conv3d(7, 7, 1), torch.nn.InstanceNorm3d(7, affine=True)).cuda()
+    want = model(x)
+    assert pkg.convert_plain(model) == 1 and type(model[1]) is pkg.FastInstanceNorm3d
+    got = model(x)
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5

@@ -156,6 +156,39 @@ print("OK")
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.reference
+def test_install_plain_routes_the_decoder_norm_through_the_factory(have_reference):
+    """`("instance", {"affine": True})` builds the fast subclass of torch's InstanceNorm."""
+    if not have_reference:
+        pytest.skip("/root/reference not present")
+    code = r"""
+import sys, importlib
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import _monai_stub; _monai_stub.install()
+import torch
+pkg = importlib.import_module("mi-seg_b200")
+classes = pkg.install_plain()
+from networks.layers.utils import get_norm_layer
+from networks.blocks.dynunet_block import UnetResBlock
+name = ("instance", {"affine": True})
+for dim in (1, 2, 3):
+    m = get_norm_layer(name=name, spatial_dims=dim, channels=5)
+    assert type(m) is classes[dim - 1] and isinstance(m, getattr(torch.nn, "InstanceNorm%%dd" %% dim))
+    assert list(m.state_dict()) == ["weight", "bias"]
+blk = UnetResBlock(3, 2, 4, kernel_size=3, stride=1, norm_name=name)
+assert type(blk.norm1) is classes[2]
+assert pkg.fuse_blocks(blk) == 1            # plain fast norms fuse like the conditional ones
+pkg.uninstall()
+blk2 = UnetResBlock(3, 2, 4, kernel_size=3, stride=1, norm_name=name)
+assert type(blk2.norm1) is torch.nn.InstanceNorm3d
+assert list(blk.state_dict()) == list(blk2.state_dict())
+assert pkg.convert_plain(blk2) == 3 and type(blk2.norm2) is classes[2]
+print("OK")
+""" % (ROOT, os.path.join(ROOT, "tests"), REFERENCE_ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
 # ------------------------------------------------------------------------------------------------ multi-process (gloo)
 def test_shard_range_partitions_exactly():
     for total in (0, 1, 7, 8, 600):

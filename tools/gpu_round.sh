@@ -16,3 +16,5 @@ B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-torch-re
 $B > $o/${tag}_bench_short.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches.csv $B > $o/${tag}_ncu_launches.log 2>&1
 for f in pytest smoke bench; do tail -n 3 $o/${tag}_$f.log | cut -c1-300; done
+# full-set captures of the forward and backward flat kernels for profiles/
+bash tools/ncu_full.sh ${tag}
