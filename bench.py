@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
     ap.add_argument("--sweep", action="store_true", help="also time the BASELINE.json microbench sweep (extra key)")
+    ap.add_argument("--sweep-out", default=None, help="append every sweep point to this file as JSON lines")
     return ap.parse_args()
 
 
@@ -64,6 +65,84 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_sweep(lib, pkg, dev, peak, out_path=None, budget_bytes=120e9):
+    """BASELINE.json configs[3]: N in {1,4,8} x C in {24,48,96,192,384} x {48^3,96^3,128^3}, fp32 and bf16, forward and
+    backward, device-resident inputs, CUDA events, rotating buffer sets > L2 (or one set when a tensor alone
+    exceeds L2).  Points whose four live tensors exceed `budget_bytes` are skipped."""
+    import torch
+
+    rows = []
+    S = 2
+    stream = torch.cuda.current_stream().cuda_stream
+    for dtype, tdt, code, es in (("bf16", torch.bfloat16, 1, 2), ("fp32", torch.float32, 0, 4)):
+        for sp in (48, 96, 128):
+            m = sp ** 3
+            for n in (1, 4, 8):
+                for c in (24, 48, 96, 192, 384):
+                    E = n * c * m
+                    R = max(1, min(3, int(400e6 // (4 * E * es)) + 1))
+                    if 4 * E * es * R > budget_bytes:
+                        R = 1
+                    if 4 * E * es * R > budget_bytes:
+                        rows.append({"N": n, "C": c, "S": sp, "dtype": dtype, "skipped": "exceeds the memory budget"})
+                        continue
+                    xs = [torch.empty(n, c, m, device=dev, dtype=tdt).normal_(1.0, 2.0) for _ in range(R)]
+                    dys = [torch.empty(n, c, m, device=dev, dtype=tdt).normal_() for _ in range(R)]
+                    ys = [torch.empty_like(xs[0]) for _ in range(R)]
+                    dxs = [torch.empty_like(xs[0]) for _ in range(R)]
+                    mean = torch.empty(n * c, device=dev)
+                    rstd = torch.empty(n * c, device=dev)
+                    gamma = 1 + 0.3 * torch.randn(S, c, device=dev)
+                    beta = 0.3 * torch.randn(S, c, device=dev)
+                    styles = (torch.arange(n, device=dev) % S).to(torch.int64)
+                    grads = torch.empty(2, S, c, device=dev)
+                    wsb = lib.micn_workspace_bytes(n, c, m, code, S)
+                    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+                    gp = (ctypes.c_void_p * S)(*[gamma[k].data_ptr() for k in range(S)])
+                    bp = (ctypes.c_void_p * S)(*[beta[k].data_ptr() for k in range(S)])
+
+                    def fwd(i):
+                        rc = lib.micn_fwd(xs[i].data_ptr(), ys[i].data_ptr(), None, gp, bp, S, styles.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), n, c, m, c * m, m, code, 0, 0.01, 1e-5,
+                                          ws.data_ptr(), wsb, stream)
+                        if rc:
+                            raise RuntimeError(f"micn_fwd rc={rc}")
+
+                    def bwd(i):
+                        rc = lib.micn_bwd(dys[i].data_ptr(), xs[i].data_ptr(), None, gp, bp, S, styles.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), dxs[i].data_ptr(), None,
+                                          grads[0].data_ptr(), grads[1].data_ptr(), n, c, m, c * m, m, code, 0, 0.01,
+                                          ws.data_ptr(), wsb, stream)
+                        if rc:
+                            raise RuntimeError(f"micn_bwd rc={rc}")
+
+                    iters = max(3, min(30, int(3e9 // (5 * E * es)) + 1))
+                    res = {}
+                    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+                        for i in range(3):
+                            fn(i % R)
+                        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        for i in range(iters):
+                            fn(i % R)
+                        b_.record()
+                        torch.cuda.synchronize()
+                        res[name] = a.elapsed_time(b_) / iters * 1e3  # us
+                    fb, bb = 2 * E * es, 3 * E * es
+                    row = {"N": n, "C": c, "S": sp, "dtype": dtype, "path": int(pkg._lib.get_option("last_path")),
+                           "fwd_us": round(res["fwd"], 2), "bwd_us": round(res["bwd"], 2),
+                           "fwd_gbps": round(fb / res["fwd"] * 1e-3, 1), "bwd_gbps": round(bb / res["bwd"] * 1e-3, 1),
+                           "frac": round((fb + bb) / (res["fwd"] + res["bwd"]) * 1e-3 / peak, 3),
+                           "voxels_per_s": round(n * m / ((res["fwd"] + res["bwd"]) * 1e-6)), "buffer_sets": R}
+                    rows.append(row)
+                    if out_path:
+                        with open(out_path, "a") as f:
+                            f.write(json.dumps(row) + "\n")
+                    del xs, dys, ys, dxs, ws
+                    torch.cuda.empty_cache()
+    return rows
 
 
 def ncu_traffic(args, n, c, s):
@@ -426,6 +505,10 @@ def run_ours(args):
         "clocks": clocks, "torch_gpu_reference": torch_gpu,
         "plan": {k: pkg._lib.get_option(k) for k in ("last_path", "last_cs", "last_slots", "last_grid")},
     }
+    if args.sweep and world == 1:
+        del xs, dys, ys, dxs
+        torch.cuda.empty_cache()
+        line["sweep"] = run_sweep(lib, pkg, dev, peak, args.sweep_out)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
             load_affine(p, style, ch, gamma, beta);
             // no polling before this CTA's own piece is through P1: the other CTAs are at the same point
             mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
-            __nanosleep(g.poll_delay_ns);  // ... and let their record stores land
+            // ... and let their record stores land; the last L pieces of the CTA are the kernel's tail, where
+            // nothing hides a late coefficient any more: poll eagerly there
+            __nanosleep(j + g.L >= nj ? g.poll_delay_ns / 4 : g.poll_delay_ns);
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float ref = 0.f, A = 0.f, B = 0.f;
             ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane,
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
             const float mean = pr.x, rstd = pr.y, gamma = pr.z, beta = pr.w;
             // no polling before this CTA's own piece is through P1 (the others are at the same point)
             mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
-            __nanosleep(g.poll_delay_ns);  // let the record stores land
+            __nanosleep(j + g.L >= nj ? g.poll_delay_ns / 4 : g.poll_delay_ns);  // let the record stores land (tail: eager)
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float S1 = 0.f, S2 = 0.f;
             ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane, [](float, float) {},
