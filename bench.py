@@ -286,6 +286,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n, c, s, m = workload(args)
     S = 2
+    for kv in os.environ.get("MICN_BENCH_OPTS", "").split(","):  # (debug knob: library options, name=value)
+        if "=" in kv:
+            pkg._lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     es = DT_BYTES[args.dtype]
     tdt = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[args.dtype]
     code = {"fp32": 0, "bf16": 1, "fp16": 2}[args.dtype]
@@ -305,7 +308,14 @@ def run_ours(args):
     gamma = 1 + 0.3 * torch.randn(S, c, device=dev)
     beta = 0.3 * torch.randn(S, c, device=dev)
     styles = (torch.arange(n, device=dev) % S).to(torch.int64)
-    grads = torch.empty(2, S, c, device=dev)  # dgamma, dbeta: one bucket for the all-reduce
+    # dgamma, dbeta: one bucket per step for the all-reduce, double-buffered so that the collective of step i (a few
+    # microseconds of NCCL on one SM) runs while step i+1 computes - the way DDP overlaps its buckets with the
+    # rest of backward; a bucket is waited for before it is written again and before the clock stops
+    grads2 = [torch.empty(2, S, c, device=dev) for _ in range(2)]
+    pending = [None, None]
+    overlap = world > 1 and not os.environ.get("MICN_BENCH_SYNC_ALLREDUCE")
+    if overlap:  # leave one SM to NCCL (the flat kernels are persistent, one CTA per SM)
+        pkg._lib.set_option("flat_grid", torch.cuda.get_device_properties(dev).multi_processor_count - 1)
     wsb = lib.micn_workspace_bytes(n, c, m, code, S)
     ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
     gp = (ctypes.c_void_p * S)(*[gamma[k].data_ptr() for k in range(S)])
@@ -318,7 +328,7 @@ def run_ours(args):
         if rc:
             raise RuntimeError(f"micn_fwd rc={rc}")
 
-    def bwd(i):
+    def bwd(i, grads):
         rc = lib.micn_bwd(dys[i].data_ptr(), xs[i].data_ptr(), None, gp, bp, S, styles.data_ptr(), means[i].data_ptr(),
                           rstds[i].data_ptr(), dxs[i].data_ptr(), None, grads[0].data_ptr(), grads[1].data_ptr(),
                           n, c, m, c * m, m, code, epi, 0.01, ws.data_ptr(), wsb, stream)
@@ -328,30 +338,44 @@ def run_ours(args):
     def step(i):
         # forward on set i, backward on the NEXT set (its statistics come from an earlier forward of the
         # same data): neither kernel finds its inputs in L2 from the launch before it
+        b = i & 1
         fwd(i % R)
-        bwd((i + 1) % R)
-        if world > 1:
-            dist.all_reduce(grads)
+        if pending[b] is not None:  # the bucket's previous all-reduce must be through before it is overwritten
+            pending[b].wait()
+            pending[b] = None
+        bwd((i + 1) % R, grads2[b])
+        if world > 1 and not os.environ.get("MICN_BENCH_NO_ALLREDUCE"):  # (debug knob: isolate the collective)
+            if overlap:
+                pending[b] = dist.all_reduce(grads2[b], async_op=True)
+            else:
+                dist.all_reduce(grads2[b])
+
+    def drain():
+        for b in range(2):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     for i in range(R):  # statistics for every set
         fwd(i)
     for i in range(args.warmup):
         step(i)
+    drain()
     torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:  # BEFORE the barrier: a rank that starts late would be waited for inside the others' timed region
+        sampler.start()
+        time.sleep(0.25)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
     launches0 = pkg._lib.get_option("launches")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         step(i)
+    drain()  # every step's collective completes inside the timed region
     e1.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
@@ -368,7 +392,7 @@ def run_ours(args):
         evs[i][0].record()
         fwd(i % R)
         evs[i][1].record()
-        bwd((i + 1) % R)
+        bwd((i + 1) % R, grads2[0])
         evs[i][2].record()
     torch.cuda.synchronize()
     t_region_end = time.perf_counter()
@@ -498,7 +522,10 @@ def run_ours(args):
                    "global_batch": n * world, "parallelism": f"dp{world}",
                    "l2": f"{R} rotating buffer sets ({R * 4 * E * es / 1e6:.0f} MB) > 126 MB L2; backward reads a "
                          "different set than the forward before it",
-                   "collective": "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none"},
+                   "collective": ("all_reduce(dgamma,dbeta) per step over NCCL, overlapped with the next step's kernels "
+                                  "(double-buffered buckets, waited before reuse and before the clock stops; "
+                                  "147 of 148 SMs run the norm kernels, one is left to NCCL)" if overlap else
+                                  "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none")},
         "voxels_per_s": world * n * m / (ms_step * 1e-3),
         "frac_of_peak": value / world / peak,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
