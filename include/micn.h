@@ -73,10 +73,11 @@ long long micn_get_option(const char* key);
 
 /* Bytes of device workspace micn_fwd/micn_bwd need for this problem (cross-CTA exchange records of
  * the flat path, per-slab sums).  The workspace must be zero-filled ONCE when it is allocated and can
- * then be reused by every later call on the same stream: records are tagged with a per-launch epoch
- * and the few control words are left zero again.  Two kernels running CONCURRENTLY (different
- * streams) need different workspaces.  Without a workspace (or with one that is too small) the
- * calls still work through the slower cluster / small paths. */
+ * then be reused by any number of calls of any shape that fits: exchange records are tagged with a
+ * launch epoch that lives in the workspace header and is advanced by the kernels themselves, so the calls
+ * are safe to capture in a CUDA graph and replay (no per-launch state on the host).  Calls that may
+ * overlap in time (different streams) need different workspaces.  Without a workspace (or with one that is
+ * too small) the large-slab fast path is not used. */
 size_t micn_workspace_bytes(int64_t N, int64_t C, int64_t M, int dtype, int num_styles);
 
 /* Host-blocking read (cudaMemcpy) of the sticky status word: bit 0 = a style index was out of

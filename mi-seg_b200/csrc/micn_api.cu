@@ -255,16 +255,9 @@ int launch_cluster(K kernel, const P& p, const Plan& pl, int NS, cudaStream_t st
 struct FlatWs {
     uint4* piece;
     uint4* slab;
+    unsigned* ctl;  // header words [2] epoch, [3] CTAs done
 };
-std::atomic<unsigned> g_epoch{0};
-
-unsigned next_epoch() {
-    unsigned e = g_epoch.fetch_add(1u) + 1u;
-    if (e == 0u) e = g_epoch.fetch_add(1u) + 1u;  // 0 is what a zero-filled workspace holds
-    return e;
-}
-
-constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32)
+constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32), [8] flat launch epoch (u32), [12] flat CTAs done (u32)
 
 // upper bound of the pieces the flat planner can cut one slab into
 long long flat_max_pieces(long long slab_bytes) {
@@ -392,7 +385,6 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     fp->g.KB = (unsigned)KB;
     fp->g.L = (unsigned)L_;
     fp->g.slot_vecs = (unsigned)slot_vecs;
-    fp->g.epoch = next_epoch();
     fp->g.divP = fastdiv_make((unsigned)bestP);
     fp->g.divC = fastdiv_make((unsigned)C);
     const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
@@ -451,6 +443,7 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
             if (g_opt.flat_trace_which.load() == 2) fpl.g.trace = nullptr;
             fpl.g.ws_piece = ws_flat->piece;
             fpl.g.ws_slab = ws_flat->slab;
+            fpl.g.ws_ctl = ws_flat->ctl;
             record_flat(fpl);
             return launch_flat(kernel, p, fpl, st);
         }
@@ -499,6 +492,7 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
             if (g_opt.flat_trace_which.load() == 1) fpl.g.trace = nullptr;
             fpl.g.ws_piece = ws_flat->piece;
             fpl.g.ws_slab = ws_flat->slab;
+            fpl.g.ws_ctl = ws_flat->ctl;
             record_flat(fpl);
             return launch_flat(kernel, p, fpl, st);
         }
@@ -659,12 +653,13 @@ int micn_fwd(const void* x, void* y, const void* residual, const float* const* g
     const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(y) && (!p.res || aligned16(p.res)) &&
                              ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    FlatWs wf = {nullptr, nullptr};
+    FlatWs wf = {nullptr, nullptr, nullptr};
     const WsLayout wl = ws_layout(N, C, M, es);
     const bool have_flat_ws = workspace && workspace_bytes >= wl.total;
     if (have_flat_ws) {
         wf.slab = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.slab_off);
         wf.piece = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.piece_off);
+        wf.ctl = reinterpret_cast<unsigned*>(workspace) + 2;
     }
     const FlatWs* wfp = have_flat_ws ? &wf : nullptr;
     switch (dtype) {
@@ -747,12 +742,13 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
                              (!p.act_out || aligned16(p.act_out)) && (!p.dres || aligned16(p.dres)) &&
                              ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    FlatWs wf = {nullptr, nullptr};
+    FlatWs wf = {nullptr, nullptr, nullptr};
     const WsLayout wl = ws_layout(N, C, M, es);
     const bool have_flat_ws = workspace && workspace_bytes >= wl.total;
     if (have_flat_ws) {
         wf.slab = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.slab_off);
         wf.piece = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.piece_off);
+        wf.ctl = reinterpret_cast<unsigned*>(workspace) + 2;
     }
     const FlatWs* wfp = have_flat_ws ? &wf : nullptr;
     switch (dtype) {

@@ -81,7 +81,7 @@ struct FlatGeom {
     unsigned KA, KB;       // shared-memory slots of ring A (P1) and ring B (P2)
     unsigned L;            // steps P2 trails P1
     unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
-    unsigned epoch;        // per-launch tag of the workspace records (never 0)
+    unsigned* ws_ctl;      // workspace header: [0] launch epoch, [1] CTAs done (device-side, CUDA-graph safe)
     unsigned poll_delay_ns, poll_backoff_ns;
     FastDiv divP, divC;    // piece index -> slab, slab -> sample
     uint4* ws_piece;       // [T] piece records
@@ -97,13 +97,30 @@ __device__ __forceinline__ void flat_trace(const FlatGeom& g, unsigned j, int ev
         g.trace[((size_t)blockIdx.x * kFlatTraceSteps + j) * 16 + ev] = (long long)globaltimer_ns();
 }
 
+// The tag of this launch's records comes from the workspace itself, not from the host: a captured CUDA graph
+// replays the same kernel parameters, and records left by the previous replay must not look current.  One lane
+// per CTA reads the epoch word e0 and THEN arrives on a counter in the header; the last CTA to arrive (all CTAs
+// are co-resident) resets the counter and bumps the epoch for the next launch - after every CTA has read e0.
+// All of this happens off the critical path, during the first piece's load; nothing is added at kernel end.
+__device__ __forceinline__ unsigned flat_epoch_tag(const FlatGeom& g) {
+    const unsigned e0 = *reinterpret_cast<const volatile unsigned*>(g.ws_ctl);
+    // the data dependency on e0 orders the read before the arrival
+    if (atomicAdd(g.ws_ctl + 1, 1u + (e0 & 0u)) == gridDim.x - 1) {
+        g.ws_ctl[1] = 0u;
+        __threadfence();
+        atomicAdd(g.ws_ctl, 1u);
+    }
+    return (e0 + 1u) | 0x80000000u;  // never 0: a zero-filled workspace holds no valid record
+}
+
 // control block: slot barriers of both rings + the per-piece ring
 __host__ __device__ constexpr int flat_ctl_bytes() {
-    return kFlatMaxSlots * (4 * 8 + 16) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 32);
+    return kFlatMaxSlots * (4 * 8 + 16) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 32) + 16;
 }
 
 struct FlatCtx {
-    uint32_t dataA, dataB, fullA, emptyA, fullB, emptyB, p1d0, coef0;  // shared::cta addresses
+    uint32_t dataA, dataB, fullA, emptyA, fullB, emptyB, p1d0, coef0, tagbar;  // shared::cta addresses
+    volatile unsigned* tagw;                     // this launch's record tag (written once by the publish warp)
     float* slot_prec;                            // [KA][4]  slab constants of the piece in the A slot (backward)
     float* warp_part;                            // [NB][16][4]
     float* coefv;                                // [NB][8]
@@ -129,7 +146,10 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
     c.slot_prec = f;
     c.warp_part = c.slot_prec + kFlatMaxSlots * 4;
     c.coefv = c.warp_part + kFlatNB * kFlatConsumerWarps * 4;
+    c.tagw = reinterpret_cast<volatile unsigned*>(c.coefv + kFlatNB * 8);
+    c.tagbar = smem_u32(const_cast<unsigned*>(c.tagw) + 2);
     if (threadIdx.x == 0) {
+        mbar_init(c.tagbar, 1);
         for (unsigned i = 0; i < g.KA; ++i) {
             mbar_init(c.fullA + 8 * i, 1);
             mbar_init(c.emptyA + 8 * i, kFlatConsumerWarps);
@@ -334,6 +354,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
         }
     } else if (warp >= kFlatPublishWarp0 && warp < kFlatGatherWarp0) {
         // ------------------------------------------------------------------ publish: warp partials -> piece record
+        if (lane == 0) {  // this launch's record tag, shared with the gather warps
+            *c.tagw = flat_epoch_tag(g);
+            mbar_arrive(c.tagbar);
+        }
+        __syncwarp();
+        const unsigned tag = *c.tagw;
         for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
             const Ring e = entry_of(j);
             const unsigned gidx = j * G + cta;
@@ -353,11 +379,13 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
             const float A = warp_sum(st.n * d), B = warp_sum(fmaf(st.n * d, d, st.m2));
             const float N = (float)(pv * VN);
             const float m = A / N;
-            if (lane == 0) ll_store(g.ws_piece + gidx, ref + m, fmaxf(B - A * m, 0.f), g.epoch);
+            if (lane == 0) ll_store(g.ws_piece + gidx, ref + m, fmaxf(B - A * m, 0.f), tag);
             if (lane == 0) flat_trace(g, j, TR_PUB_END);
         }
     } else if (warp >= kFlatGatherWarp0) {
         // ------------------------------------------------------------------ gather: slab records -> coefficients for P2
+        mbar_wait_idle(c.tagbar, 0u);
+        const unsigned tag = *c.tagw;
         for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
             const Ring e = entry_of(j);
             const PieceId pc = piece_of(g, j * G + cta);
@@ -373,7 +401,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
             __nanosleep(j + g.L >= nj ? g.poll_delay_ns / 4 : g.poll_delay_ns);
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float ref = 0.f, A = 0.f, B = 0.f;
-            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane,
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, tag, g.poll_backoff_ns, lane,
                       [&](float a0, float) { ref = a0; },
                       [&](unsigned q, float a, float b) {
                           const float nq = (float)(piece_vecs(g, q) * VN), d = a - ref;
@@ -581,6 +609,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
         }
     } else if (warp >= kFlatPublishWarp0 && warp < kFlatGatherWarp0) {
         // ------------------------------------------------------------------ publish
+        if (lane == 0) {  // this launch's record tag, shared with the gather warps
+            *c.tagw = flat_epoch_tag(g);
+            mbar_arrive(c.tagbar);
+        }
+        __syncwarp();
+        const unsigned tag = *c.tagw;
         for (unsigned j = warp - kFlatPublishWarp0; j < nj; j += kFlatPublishWarps) {
             const Ring e = entry_of(j);
             mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
@@ -593,12 +627,14 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
             }
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
-            if (lane == 0) ll_store(g.ws_piece + (j * G + cta), s1, s2, g.epoch);
+            if (lane == 0) ll_store(g.ws_piece + (j * G + cta), s1, s2, tag);
             if (lane == 0) flat_trace(g, j, TR_PUB_END);
         }
     } else if (warp >= kFlatGatherWarp0) {
         // ------------------------------------------------------------------ gather
         const float invM = 1.f / (float)p.M;
+        mbar_wait_idle(c.tagbar, 0u);
+        const unsigned tag = *c.tagw;
         for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
             const Ring e = entry_of(j);
             const PieceId pc = piece_of(g, j * G + cta);
@@ -610,7 +646,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
             __nanosleep(j + g.L >= nj ? g.poll_delay_ns / 4 : g.poll_delay_ns);  // let the record stores land (tail: eager)
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float S1 = 0.f, S2 = 0.f;
-            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, g.epoch, g.poll_backoff_ns, lane, [](float, float) {},
+            ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, tag, g.poll_backoff_ns, lane, [](float, float) {},
                       [&](unsigned, float a, float b) {
                           S1 += a;
                           S2 += b;
@@ -638,14 +674,14 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                         p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
                     }
                 } else {
-                    if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, g.epoch);
+                    if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, tag);
                     if (n == (unsigned)p.N - 1) {
                         // last sample of this channel: fold every sample's record per style, fixed order
                         for (int s = 0; s < p.num_styles; ++s) {
                             float ab = 0.f, ag = 0.f;
                             for (unsigned nn = lane; nn < (unsigned)p.N; nn += 32) {
                                 float ra, rb;
-                                ll_wait1(g.ws_slab + (size_t)nn * C + ch, g.epoch, g.poll_backoff_ns, ra, rb);
+                                ll_wait1(g.ws_slab + (size_t)nn * C + ch, tag, g.poll_backoff_ns, ra, rb);
                                 if (load_style(p.styles, nn, p.num_styles, nullptr) == s) {
                                     ab += ra;
                                     ag += rb;

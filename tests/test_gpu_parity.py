@@ -519,3 +519,36 @@ def test_plain_instance_norm_matches_torch_module_and_functional(pkg):
     assert pkg.convert_plain(model) == 1 and type(model[1]) is pkg.FastInstanceNorm3d
     got = model(x)
     assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+
+
+def test_cuda_graph_replay_is_safe(pkg):
+    """A captured graph replays the same kernel parameters; the flat path's record tags come from the workspace
+    (device-side epoch), so records of the previous replay can never be mistaken for current ones."""
+    torch.manual_seed(3)
+    n, c, s = 2, 6, 48  # 221 KB bf16 slabs: the flat (cross-CTA exchange) path
+    mod = pkg.FastConditionalInstanceNorm3d(num_styles=2, num_features=c).cuda()
+    with torch.no_grad():
+        for k in range(2):
+            mod.norms[k].weight.normal_(1, 0.3)
+            mod.norms[k].bias.normal_(0, 0.3)
+    styles = torch.tensor([1, 0], device="cuda")
+    x_static = torch.randn(n, c, s, s, s, device="cuda").bfloat16()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):
+            mod(x_static, styles)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph), torch.no_grad():
+        y_static = mod(x_static, styles)
+    assert pkg._lib.get_option("last_path") == 2
+    gamma = np.stack([m.weight.detach().cpu().numpy() for m in mod.norms])
+    beta = np.stack([m.bias.detach().cpu().numpy() for m in mod.norms])
+    for rep in range(4):
+        xn = (torch.randn(n, c, s, s, s) * (1 + rep) + rep).bfloat16()
+        x_static.copy_(xn.cuda())
+        graph.replay()
+        torch.cuda.synchronize()
+        yr, _, _ = O.fwd_f64(xn.float().numpy(), [1, 0], gamma, beta)
+        assert rel_err(y_static.float().cpu().numpy(), yr) < TOL[torch.bfloat16], rep
