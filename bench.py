@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
+    ap.add_argument("--no-model-calls", action="store_true", help="skip the C-Swin-UNETR norm-call-list leg")
     ap.add_argument("--sweep", action="store_true", help="also time the BASELINE.json microbench sweep (extra key)")
     ap.add_argument("--sweep-out", default=None, help="append every sweep point to this file as JSON lines")
     return ap.parse_args()
@@ -143,6 +144,101 @@ def run_sweep(lib, pkg, dev, peak, out_path=None, budget_bytes=120e9):
                     del xs, dys, ys, dxs, ws
                     torch.cuda.empty_cache()
     return rows
+
+
+SWIN_UNETR_CALLS = (  # the 31 instance_cond calls of one C-Swin-UNETR (f=48, 96^3, B=1) forward
+    [("encoder1.norm%d" % i, 48, 96, False) for i in (1, 2, 3)] +
+    [("encoder2.norm%d" % i, 48, 48, False) for i in (1, 2)] + [("encoder3.norm%d" % i, 96, 24, False) for i in (1, 2)] +
+    [("encoder4.norm%d" % i, 192, 12, False) for i in (1, 2)] + [("encoder10.norm%d" % i, 768, 3, False) for i in (1, 2)] +
+    [("swin.l1.b%d.norm%d" % (b, i), 48, 48, False) for b in (0, 1) for i in (1, 2)] +
+    [("swin.l2.b%d.norm%d" % (b, i), 96, 24, False) for b in (0, 1) for i in (1, 2)] +
+    [("swin.l3.b%d.norm%d" % (b, i), 192, 12, False) for b in (0, 1) for i in (1, 2)] +
+    [("swin.l4.b%d.norm%d" % (b, i), 384, 6, False) for b in (0, 1) for i in (1, 2)] +
+    [("merge1.norm", 384, 24, True), ("merge2.norm", 768, 12, True), ("merge3.norm", 1536, 6, True),
+     ("merge4.norm", 3072, 3, True)])
+
+
+def run_model_calls(pkg, dev, tdt, reps=20):
+    """The hot path at model scale: every instance_cond call of one C-Swin-UNETR training step (forward + backward),
+    timed as one sequence three ways: (1) raw C-ABI launches back to back (what the GPU needs), (2) through the
+    drop-in nn.Module + autograd (what a training script calls; ~250 us of Python / autograd-engine time per call,
+    which a real step hides behind its convolutions), (3) the reference's call sequence (per-sample F.instance_norm
+    + torch.stack) through PyTorch/ATen on the same GPU.  PatchMerging inputs arrive channels-last (stride_C = 1)."""
+    import torch
+    import torch.nn.functional as F
+
+    lib = pkg._lib.lib()
+    torch.manual_seed(1)
+    code = {torch.bfloat16: 1, torch.float32: 0, torch.float16: 2}[tdt]
+    stream = torch.cuda.current_stream().cuda_stream
+    calls, raw = [], []
+    elems = 0
+    for name, c, sp, chlast in SWIN_UNETR_CALLS:
+        mod = pkg.FastConditionalInstanceNorm3d(num_styles=2, num_features=c).to(dev)
+        shape = (1, c, sp, sp, sp)
+        if chlast:
+            x = (torch.randn(1, sp, sp, sp, c, device=dev) * 2 + 1).to(tdt).permute(0, 4, 1, 2, 3)
+        else:
+            x = (torch.randn(*shape, device=dev) * 2 + 1).to(tdt)
+        x.requires_grad_(True)
+        dy = torch.randn(*shape, device=dev).to(tdt)
+        calls.append((mod, x, dy))
+        m = sp ** 3
+        wsb = lib.micn_workspace_bytes(1, c, m, code, 2)
+        raw.append({"x": x.detach(), "dy": dy, "y": torch.empty(shape, device=dev, dtype=tdt),
+                    "dx": torch.empty(shape, device=dev, dtype=tdt), "stats": torch.empty(2, c, device=dev),
+                    "grads": torch.empty(2, 2, c, device=dev), "ws": torch.zeros(wsb, dtype=torch.uint8, device=dev),
+                    "wsb": wsb, "c": c, "m": m, "chlast": chlast,
+                    "gp": (ctypes.c_void_p * 2)(*[n_.weight.data_ptr() for n_ in mod.norms]),
+                    "bp": (ctypes.c_void_p * 2)(*[n_.bias.data_ptr() for n_ in mod.norms])})
+        elems += c * m
+    styles = torch.tensor([1], device=dev)
+
+    def ours_module():
+        for mod, x, dy in calls:
+            mod(x, styles).backward(dy)
+
+    def torch_module():
+        for mod, x, dy in calls:
+            w, b = mod.norms[1].weight, mod.norms[1].bias
+            torch.stack([F.instance_norm(x[i].unsqueeze(0), None, None, w, b, True, 0.1, 1e-5).squeeze(0)
+                         for i in range(x.shape[0])]).backward(dy)
+
+    def ours_cabi():
+        for r in raw:
+            x = r["x"].contiguous() if r["chlast"] else r["x"]  # the copy a strided input costs is inside the clock
+            c, m = r["c"], r["m"]
+            rc = lib.micn_fwd(x.data_ptr(), r["y"].data_ptr(), None, r["gp"], r["bp"], 2, styles.data_ptr(),
+                              r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), 1, c, m, c * m, m, code, 0, 0.01, 1e-5,
+                              r["ws"].data_ptr(), r["wsb"], stream)
+            rc = rc or lib.micn_bwd(r["dy"].data_ptr(), x.data_ptr(), None, r["gp"], r["bp"], 2, styles.data_ptr(),
+                                    r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), r["dx"].data_ptr(), None,
+                                    r["grads"][0].data_ptr(), r["grads"][1].data_ptr(), 1, c, m, c * m, m, code, 0, 0.01,
+                                    r["ws"].data_ptr(), r["wsb"], stream)
+            if rc:
+                raise RuntimeError(f"model call list: rc={rc}")
+
+    out = {}
+    for key, fn in (("ours_cabi_ms", ours_cabi), ("ours_module_ms", ours_module), ("torch_module_ms", torch_module)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        out[key] = a_.elapsed_time(b_) / reps
+    es = torch.empty(0, dtype=tdt).element_size()
+    out.update({"calls": len(calls), "elements_per_forward": elems, "algorithmic_bytes": 5 * elems * es,
+                "ours_cabi_gbps": 5 * elems * es / (out["ours_cabi_ms"] * 1e-3) / 1e9,
+                "patch_voxels_per_s_norm_only": 96 ** 3 / (out["ours_cabi_ms"] * 1e-3),
+                "speedup_vs_torch_gpu_module_level": out["torch_module_ms"] / out["ours_module_ms"],
+                "speedup_vs_torch_gpu_device_level": out["torch_module_ms"] / out["ours_cabi_ms"],
+                "what": "all 31 instance_cond calls of one C-Swin-UNETR (f=48, 96^3, B=1) step, fwd+bwd; norm-only time, "
+                        "convs / attention not run"})
+    return out
 
 
 def ncu_traffic(args, n, c, s):
@@ -532,6 +628,8 @@ def run_ours(args):
         "clocks": clocks, "torch_gpu_reference": torch_gpu,
         "plan": {k: pkg._lib.get_option(k) for k in ("last_path", "last_cs", "last_slots", "last_grid")},
     }
+    if world == 1 and not args.no_model_calls:
+        line["swin_unetr_norm_calls"] = run_model_calls(pkg, dev, tdt)
     if args.sweep and world == 1:
         del xs, dys, ys, dxs
         torch.cuda.empty_cache()

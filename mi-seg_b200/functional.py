@@ -24,18 +24,46 @@ _DTYPES = {torch.float32: _lib.MICN_F32, torch.bfloat16: _lib.MICN_BF16, torch.f
 _EPILOGUES = {"none": _lib.EPI_NONE, "lrelu": _lib.EPI_LRELU, "add_lrelu": _lib.EPI_ADD_LRELU}
 
 _workspaces = {}
+_ptr_arrays = {}
 
 
-def _workspace(device: torch.device, n: int, c: int, m: int, dtype_code: int, num_styles: int) -> torch.Tensor:
+_ws_need = {}
+
+
+def _workspace(device: torch.device, stream: int, n: int, c: int, m: int, dtype_code: int, num_styles: int) -> torch.Tensor:
     """Zero-filled device workspace, one per (device, stream), grown on demand (micn.h: must be
     zero-filled once when allocated; the kernels leave it reusable)."""
-    need = int(_lib.lib().micn_workspace_bytes(n, c, m, dtype_code, num_styles))
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    shape_key = (n, c, m, dtype_code, num_styles)
+    need = _ws_need.get(shape_key)
+    if need is None:
+        need = int(_lib.lib().micn_workspace_bytes(n, c, m, dtype_code, num_styles))
+        if len(_ws_need) > 4096:
+            _ws_need.clear()
+        _ws_need[shape_key] = need
+    key = (device.index, stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when `dev` is not already current (the context manager costs ~10 us)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        self.ctx = None if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def reset_workspaces() -> None:
@@ -44,9 +72,14 @@ def reset_workspaces() -> None:
 
 
 def _ptr_array(tensors: Sequence[torch.Tensor]):
-    arr = (ctypes.c_void_p * len(tensors))()
-    for i, t in enumerate(tensors):
-        arr[i] = t.data_ptr()
+    """ctypes array of the tensors' device pointers (cached: parameters keep their storage between steps)."""
+    key = tuple(t.data_ptr() for t in tensors)
+    arr = _ptr_arrays.get(key)
+    if arr is None:
+        arr = (ctypes.c_void_p * len(key))(*key)
+        if len(_ptr_arrays) > 4096:
+            _ptr_arrays.clear()
+        _ptr_arrays[key] = arr
     return arr
 
 
@@ -108,16 +141,16 @@ class _InstanceCondFn(torch.autograd.Function):
         if affine and any(w.numel() != c for w in weights + biases):
             raise ValueError("instance_cond: parameter length does not match the channel count")
         y = torch.empty(xs.shape, dtype=xs.dtype, device=dev)  # fresh contiguous NC* (as torch.stack gives)
-        mean = torch.empty(n * c, dtype=torch.float32, device=dev)
-        rstd = torch.empty(n * c, dtype=torch.float32, device=dev)
+        stats = torch.empty(2, n * c, dtype=torch.float32, device=dev)
+        mean, rstd = stats[0], stats[1]
         res = None
         if epilogue == _lib.EPI_ADD_LRELU:
             if residual is None or residual.shape != xs.shape or residual.dtype != xs.dtype:
                 raise ValueError("instance_cond: add_lrelu needs a residual of the input's shape and dtype")
             res = residual.contiguous()
-        ws = _workspace(dev, n, c, m, _DTYPES[xs.dtype], num_styles)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _workspace(dev, stream, n, c, m, _DTYPES[xs.dtype], num_styles)
+        with _on_device(dev):
             gp = _ptr_array(weights) if affine else None
             bp = _ptr_array(biases) if affine else None
             rc = lib.micn_fwd(xs.data_ptr(), y.data_ptr(), res.data_ptr() if res is not None else None, gp, bp,
@@ -146,11 +179,12 @@ class _InstanceCondFn(torch.autograd.Function):
         dx = torch.empty(dy.shape, dtype=xs.dtype, device=dev)
         dres = torch.empty_like(dx) if has_res else None
         need_param_grads = affine and any(ctx.needs_input_grad[8:])
-        dgamma = torch.empty((num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
-        dbeta = torch.empty((num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
-        ws = _workspace(dev, n, c, m, _DTYPES[xs.dtype], num_styles)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
+        pgrads = torch.empty((2, num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
+        dgamma = pgrads[0] if need_param_grads else None
+        dbeta = pgrads[1] if need_param_grads else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _workspace(dev, stream, n, c, m, _DTYPES[xs.dtype], num_styles)
+        with _on_device(dev):
             gp = _ptr_array(weights) if affine else None
             bp = _ptr_array(biases) if affine else None
             rc = lib.micn_bwd(dy.data_ptr(), xs.data_ptr(), act_out.data_ptr() if act_out is not None else None,
