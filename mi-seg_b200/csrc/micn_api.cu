@@ -445,9 +445,14 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
             fpl.g.ws_slab = ws_flat->slab;
             fpl.g.ws_ctl = ws_flat->ctl;
             record_flat(fpl);
-            return launch_flat(kernel, p, fpl, st);
+            const int lrc = launch_flat(kernel, p, fpl, st);
+            // a device that cannot hold the whole persistent grid right now (MPS share, another resident kernel)
+            // refuses the cooperative launch: take the cluster / small path instead of failing the call
+            if (lrc != (int)cudaErrorCooperativeLaunchTooLarge) return lrc;
+            cudaGetLastError();
+        } else if (rc != 1) {
+            return rc;
         }
-        if (rc != 1) return rc;
     }
     if (use_cluster) {
         auto kernel = micn_fwd_cluster_kernel<T, EPI>;
@@ -494,9 +499,12 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
             fpl.g.ws_slab = ws_flat->slab;
             fpl.g.ws_ctl = ws_flat->ctl;
             record_flat(fpl);
-            return launch_flat(kernel, p, fpl, st);
+            const int lrc = launch_flat(kernel, p, fpl, st);
+            if (lrc != (int)cudaErrorCooperativeLaunchTooLarge) return lrc;  // see fwd_typed
+            cudaGetLastError();
+        } else if (rc != 1) {
+            return rc;
         }
-        if (rc != 1) return rc;
     }
     if (use_cluster) {
         auto kernel = micn_bwd_cluster_kernel<T, EPI>;
