@@ -771,6 +771,7 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
 namespace {
 constexpr int kHostStreams = 3;
 cudaStream_t g_hs[kHostStreams] = {nullptr, nullptr, nullptr};
+std::vector<cudaEvent_t> g_hev;  // per-group hand-off events of the host path (created once, reused)
 std::mutex g_host_mu;
 
 inline size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -840,20 +841,24 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
     const size_t ws_each = micn_workspace_bytes(N, cg + 1, M, dtype, num_styles);
     unsigned char* ws0 = take((size_t)G * ws_each);
 
-    // small parameters first (stream 0), everyone else waits on them through an event
-    cudaStream_t s0 = g_hs[0];
+    // Three role streams: uploads (H2D), kernels, downloads (D2H).  The upload engine never idles (x and dy of
+    // group g, then group g+1, ...), the kernels of group g start as soon as its x has landed, and the download of
+    // y / dx trails the kernels: PCIe runs full duplex for the whole call.
+    cudaStream_t s_up = g_hs[0], s_comp = g_hs[1], s_down = g_hs[2];
     const bool affine = gamma_host != nullptr;
     if (affine) {
-        if ((e = cudaMemcpyAsync(gd, gamma_host, SCb, cudaMemcpyHostToDevice, s0)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(bd, beta_host, SCb, cudaMemcpyHostToDevice, s0)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(gd, gamma_host, SCb, cudaMemcpyHostToDevice, s_comp)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(bd, beta_host, SCb, cudaMemcpyHostToDevice, s_comp)) != cudaSuccess) return (int)e;
     }
-    if (styles_host && (e = cudaMemcpyAsync(sd, styles_host, (size_t)N * 8, cudaMemcpyHostToDevice, s0)) != cudaSuccess)
+    if (styles_host && (e = cudaMemcpyAsync(sd, styles_host, (size_t)N * 8, cudaMemcpyHostToDevice, s_comp)) != cudaSuccess)
         return (int)e;
-    if ((e = cudaMemsetAsync(ws0, 0, (size_t)G * ws_each, s0)) != cudaSuccess) return (int)e;
-    cudaEvent_t ready;
-    if ((e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-    cudaEventRecord(ready, s0);
-    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(g_hs[i], ready, 0);
+    if ((e = cudaMemsetAsync(ws0, 0, (size_t)G * ws_each, s_comp)) != cudaSuccess) return (int)e;
+    const size_t need_ev = (size_t)G * 4;
+    while (g_hev.size() < need_ev) {
+        cudaEvent_t ev;
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        g_hev.push_back(ev);
+    }
 
     // channel groups: sub-tensors [N, cg, M] staged densely on the device, 2-D copies on the host side
     int rc = 0;
@@ -864,47 +869,61 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
         const int64_t c0 = g * cg, c1 = std::min<int64_t>(C, c0 + cg);
         if (c0 >= c1) break;
         const int64_t cc = c1 - c0;
-        cudaStream_t st = g_hs[g % kHostStreams];
+        cudaEvent_t ev_x = g_hev[4 * g], ev_dy = g_hev[4 * g + 1], ev_y = g_hev[4 * g + 2], ev_dx = g_hev[4 * g + 3];
         const size_t width = (size_t)cc * M * es;
         const size_t sub = (size_t)N * width;
         const unsigned char* xh = reinterpret_cast<const unsigned char*>(x_host) + (size_t)c0 * M * es;
         unsigned char* yh = reinterpret_cast<unsigned char*>(y_host) + (size_t)c0 * M * es;
-        if ((e = cudaMemcpy2DAsync(xd + dev_off, width, xh, row_pitch, width, N, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+        // ---- uploads
+        if ((e = cudaMemcpy2DAsync(xd + dev_off, width, xh, row_pitch, width, N, cudaMemcpyHostToDevice, s_up)) != cudaSuccess) {
             rc = (int)e;
             break;
         }
-        for (int s = 0; s < num_styles; ++s) {
-            gp[s] = gd + (size_t)s * C + c0;
-            bp[s] = bd + (size_t)s * C + c0;
-        }
-        // per-group stats live in the [N*C] arrays at a dense per-group offset
-        float* gmean = mean + (size_t)N * c0;
-        float* grstd = rstd + (size_t)N * c0;
-        unsigned char* ws = ws0 + (size_t)g * ws_each;
-        rc = micn_fwd(xd + dev_off, yd + dev_off, nullptr, affine ? gp.data() : nullptr, affine ? bp.data() : nullptr,
-                      num_styles, styles_host ? sd : nullptr, gmean, grstd, N, cc, M, cc * M, M, dtype, epilogue, slope, eps,
-                      ws, ws_each, st);
-        if (rc) break;
-        if ((e = cudaMemcpy2DAsync(yh, row_pitch, yd + dev_off, width, width, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
-            rc = (int)e;
-            break;
-        }
+        cudaEventRecord(ev_x, s_up);
         if (bwd) {
             const unsigned char* dyh = reinterpret_cast<const unsigned char*>(dy_host) + (size_t)c0 * M * es;
-            unsigned char* dxh = reinterpret_cast<unsigned char*>(dx_host) + (size_t)c0 * M * es;
-            if ((e = cudaMemcpy2DAsync(dyd + dev_off, width, dyh, row_pitch, width, N, cudaMemcpyHostToDevice, st)) !=
+            if ((e = cudaMemcpy2DAsync(dyd + dev_off, width, dyh, row_pitch, width, N, cudaMemcpyHostToDevice, s_up)) !=
                 cudaSuccess) {
                 rc = (int)e;
                 break;
             }
+            cudaEventRecord(ev_dy, s_up);
+        }
+        // ---- kernels
+        for (int s = 0; s < num_styles; ++s) {
+            gp[s] = gd + (size_t)s * C + c0;
+            bp[s] = bd + (size_t)s * C + c0;
+        }
+        float* gmean = mean + (size_t)N * c0;  // per-group stats live in the [N*C] arrays at a dense per-group offset
+        float* grstd = rstd + (size_t)N * c0;
+        unsigned char* ws = ws0 + (size_t)g * ws_each;
+        cudaStreamWaitEvent(s_comp, ev_x, 0);
+        rc = micn_fwd(xd + dev_off, yd + dev_off, nullptr, affine ? gp.data() : nullptr, affine ? bp.data() : nullptr,
+                      num_styles, styles_host ? sd : nullptr, gmean, grstd, N, cc, M, cc * M, M, dtype, epilogue, slope, eps,
+                      ws, ws_each, s_comp);
+        if (rc) break;
+        cudaEventRecord(ev_y, s_comp);
+        if (bwd) {
             // group-dense [S, cc] gradient blocks, scattered into [S, C] on the host afterwards
             float* gdg = dgamma_host ? dgd + (size_t)num_styles * c0 : nullptr;
             float* gdb = dgamma_host ? dbd + (size_t)num_styles * c0 : nullptr;
+            cudaStreamWaitEvent(s_comp, ev_dy, 0);
             rc = micn_bwd(dyd + dev_off, xd + dev_off, nullptr, affine ? gp.data() : nullptr, affine ? bp.data() : nullptr,
                           num_styles, styles_host ? sd : nullptr, gmean, grstd, dxd + dev_off, nullptr, gdg, gdb, N, cc, M,
-                          cc * M, M, dtype, epilogue, slope, ws, ws_each, st);
+                          cc * M, M, dtype, epilogue, slope, ws, ws_each, s_comp);
             if (rc) break;
-            if ((e = cudaMemcpy2DAsync(dxh, row_pitch, dxd + dev_off, width, width, N, cudaMemcpyDeviceToHost, st)) !=
+            cudaEventRecord(ev_dx, s_comp);
+        }
+        // ---- downloads
+        cudaStreamWaitEvent(s_down, ev_y, 0);
+        if ((e = cudaMemcpy2DAsync(yh, row_pitch, yd + dev_off, width, width, N, cudaMemcpyDeviceToHost, s_down)) != cudaSuccess) {
+            rc = (int)e;
+            break;
+        }
+        if (bwd) {
+            unsigned char* dxh = reinterpret_cast<unsigned char*>(dx_host) + (size_t)c0 * M * es;
+            cudaStreamWaitEvent(s_down, ev_dx, 0);
+            if ((e = cudaMemcpy2DAsync(dxh, row_pitch, dxd + dev_off, width, width, N, cudaMemcpyDeviceToHost, s_down)) !=
                 cudaSuccess) {
                 rc = (int)e;
                 break;
@@ -934,7 +953,6 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
         e = cudaStreamSynchronize(g_hs[i]);
         if (e != cudaSuccess && !rc) rc = (int)e;
     }
-    cudaEventDestroy(ready);
     return rc;
 }
 
