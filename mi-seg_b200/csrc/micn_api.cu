@@ -380,6 +380,7 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     fp->g.V = (unsigned long long)V;
     fp->g.P = (unsigned)bestP;
     fp->g.PV = (unsigned)bestPV;
+    fp->g.PVlast = (unsigned)(V - (bestP - 1) * bestPV);
     fp->g.T = (unsigned)(slabs * bestP);
     fp->g.KA = (unsigned)KA;
     fp->g.KB = (unsigned)KB;

@@ -452,12 +452,15 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_park_t(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait_hint(bar, parity, 1000u)) return;
-    const uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    for (;;) {
+    uint64_t t0 = 0;  // the clock is read only once a wait has lasted ~256 naps: ordinary waits never touch it
+    for (uint32_t spins = 1;; ++spins) {
         __nanosleep(SLEEP_NS);  // the suspend hint alone still lets the warp re-issue every few hundred cycles
         if (mbar_try_wait_hint(bar, parity, 10000u)) return;
-        if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+        if ((spins & 0xffu) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+        }
     }
 }
 // consumers (on the critical path: short naps) / helper warps (producers, publish, gather: longer naps)

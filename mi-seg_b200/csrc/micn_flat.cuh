@@ -77,7 +77,8 @@ struct FlatGeom {
     unsigned long long V;  // 16-byte vectors per slab
     unsigned T;            // total pieces = num_slabs * P
     unsigned P;            // pieces per slab
-    unsigned PV;           // vectors per piece (the last piece of a slab may be shorter)
+    unsigned PV;           // vectors per piece ...
+    unsigned PVlast;       // ... except the last piece of a slab
     unsigned KA, KB;       // shared-memory slots of ring A (P1) and ring B (P2)
     unsigned L;            // steps P2 trails P1
     unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
@@ -92,9 +93,20 @@ struct FlatGeom {
 constexpr int kFlatTraceSteps = 64;
 enum { TR_LOAD = 0, TR_P1_BEGIN, TR_P1_END, TR_PUB_BEGIN, TR_PUB_END, TR_GA_BEGIN, TR_GA_POLLED, TR_GA_END,
        TR_P2_WAIT, TR_P2_BEGIN, TR_P2_END, TR_LOAD2 };
+// compiled in only for the bring-up build (tools/Makefile target `trace`): the checks alone were 3 % of the
+// executed instructions
+#ifndef MICN_FLAT_TRACE
+#define MICN_FLAT_TRACE 0
+#endif
 __device__ __forceinline__ void flat_trace(const FlatGeom& g, unsigned j, int ev) {
+#if MICN_FLAT_TRACE
     if (g.trace && j < kFlatTraceSteps)
         g.trace[((size_t)blockIdx.x * kFlatTraceSteps + j) * 16 + ev] = (long long)globaltimer_ns();
+#else
+    (void)g;
+    (void)j;
+    (void)ev;
+#endif
 }
 
 // The tag of this launch's records comes from the workspace itself, not from the host: a captured CUDA graph
@@ -171,10 +183,7 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
 struct PieceId {
     unsigned slab, k, pv;  // slab index, piece index inside the slab, vectors in this piece
 };
-__device__ __forceinline__ unsigned piece_vecs(const FlatGeom& g, unsigned k) {
-    const unsigned long long left = g.V - (unsigned long long)k * g.PV;
-    return left < g.PV ? (unsigned)left : g.PV;
-}
+__device__ __forceinline__ unsigned piece_vecs(const FlatGeom& g, unsigned k) { return k + 1 == g.P ? g.PVlast : g.PV; }
 __device__ __forceinline__ PieceId piece_of(const FlatGeom& g, unsigned gidx) {
     PieceId p;
     p.slab = fastdiv(gidx, g.divP);
