@@ -34,8 +34,6 @@ struct Options {
     std::atomic<long long> flat_slots_b{-1};  // ring B slots (second touch, L2)
     std::atomic<long long> flat_lag{-1};      // steps P2 trails P1
     std::atomic<long long> flat_l2_mb{-1};    // L2 budget (MB) the lag is sized for
-    std::atomic<long long> flat_prefer_p1{-1};  // (unused)
-    std::atomic<long long> flat_groups{-1};   // (unused; kept so old option scripts do not fail)
     std::atomic<long long> flat_poll_delay_ns{-1}, flat_poll_backoff_ns{-1};
     std::atomic<long long> flat_piece_vecs{-1};  // cap on vectors per piece
     std::atomic<long long> flat_min_bytes{-1};   // smallest slab the flat path takes
@@ -65,8 +63,8 @@ const OptName kOptNames[] = {
     {"launches", &g_opt.launches},         {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
-    {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace}, {"flat_groups", &g_opt.flat_groups},
-    {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb}, {"flat_prefer_p1", &g_opt.flat_prefer_p1},
+    {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace},
+    {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
     {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
 

@@ -89,7 +89,7 @@ struct Case {
     long long pad_c = 0;      // extra elements between channel slabs of x (strided input)
     long long misalign = 0;   // element offset applied to every buffer (unaligned path)
     int cs = -1, slots = -1, max_clusters = -1, force_path = -1, tps = -1;
-    int fslots = -1, flag = -1, fpv = -1, fgrid = -1, fovh = -1, fcoop = -1, fgroups = -1, fpd = -1, fpb = -1;  // flat path knobs
+    int fslots = -1, flag = -1, fpv = -1, fgrid = -1, fovh = -1, fcoop = -1, fpd = -1, fpb = -1;  // flat path knobs
     int num_styles = 2;
     bool affine = true;
     float mean = 1.0f, stdv = 2.0f;
@@ -140,7 +140,6 @@ static void set_opts(const Case& c) {
     micn_set_option("flat_grid", c.fgrid);
     micn_set_option("flat_ovh_vecs", c.fovh);
     micn_set_option("flat_coop", c.fcoop);
-    micn_set_option("flat_groups", c.fgroups);
     micn_set_option("flat_poll_delay_ns", c.fpd);
     micn_set_option("flat_poll_backoff_ns", c.fpb);
     for (auto& o : g_extra_opts) micn_set_option(o.first.c_str(), o.second);
@@ -494,7 +493,7 @@ int main(int argc, char** argv) {
     double peak = 6542.1;
     long long oN = 1, oC = 48, oS = 96, oM = -1;
     int odt = MICN_BF16, oepi = MICN_EPI_NONE, ocs = -1, oslots = -1, oiters = 30, omaxcl = -1;
-    int opath = -1, ofslots = -1, oflag = -1, ofpv = -1, ofgrid = -1, ofovh = -1, ofcoop = -1, ofgroups = -1, ofpd = -1, ofpb = -1;
+    int opath = -1, ofslots = -1, oflag = -1, ofpv = -1, ofgrid = -1, ofovh = -1, ofcoop = -1, ofpd = -1, ofpb = -1;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--suite") && i + 1 < argc) suite = argv[++i];
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
@@ -517,7 +516,6 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--fgrid") && i + 1 < argc) ofgrid = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fovh") && i + 1 < argc) ofovh = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fcoop") && i + 1 < argc) ofcoop = atoi(argv[++i]);
-        else if (!strcmp(argv[i], "--fgroups") && i + 1 < argc) ofgroups = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fpd") && i + 1 < argc) ofpd = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fpb") && i + 1 < argc) ofpb = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--opt") && i + 1 < argc) {
@@ -669,14 +667,14 @@ int main(int argc, char** argv) {
     if (suite == "check") {
         Case c = mk("check", oN, oC, oM > 0 ? oM : oS * oS * oS, odt, oepi);
         c.cs = ocs; c.slots = oslots; c.max_clusters = omaxcl;
-        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fgroups = ofgroups; c.fpd = ofpd; c.fpb = ofpb;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fpd = ofpd; c.fpb = ofpb;
         fails += run_correctness(c, true);
     }
     if (suite == "one") {
         const long long M = oS * oS * oS;
         Case c = mk("one", oN, oC, M, odt, oepi);
         c.cs = ocs; c.slots = oslots; c.max_clusters = omaxcl;
-        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fgroups = ofgroups; c.fpd = ofpd; c.fpb = ofpb;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fpd = ofpd; c.fpb = ofpb;
         PerfResult r = run_perf(c, oiters, 3);
         const double E = (double)oN * oC * M * esize(odt);
         const double fb = (oepi == MICN_EPI_ADD_LRELU ? 3 : 2) * E, bb = (oepi == MICN_EPI_ADD_LRELU ? 4 : 3) * E;
@@ -691,7 +689,7 @@ int main(int argc, char** argv) {
         // per-piece SM-clock timeline of a few CTAs of the flat forward kernel (bring-up aid)
         const long long M = oS * oS * oS;
         Case c = mk("trace", oN, oC, M, odt, oepi);
-        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fgroups = ofgroups; c.fpd = ofpd; c.fpb = ofpb;
+        c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fpd = ofpd; c.fpb = ofpb;
         const size_t tb = (size_t)prop.multiProcessorCount * 64 * 16 * sizeof(long long);
         long long* dtrace = nullptr;
         CK(cudaMalloc(&dtrace, tb));
