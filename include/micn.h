@@ -112,6 +112,31 @@ int micn_bwd(const void* dy, const void* x, const void* act_out,
              int dtype, int epilogue, float slope,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same two calls with the activation slope read from DEVICE memory: `slope_dev` points at the single weight of
+ * the nn.PReLU that follows the norm in C-UNet's ADN block ("NDA": norm -> dropout(0) -> PReLU,
+ * networks/blocks/acti_norm.py:104-110, convolutions.py:173-179), so prelu(norm(x)) and its input gradient are one
+ * kernel each and no host read of the parameter is needed.  epilogue must be MICN_EPI_LRELU or MICN_EPI_ADD_LRELU.
+ * The gradient of the slope itself, sum over pre < 0 of dy * pre, is a plain reduction over y and dy
+ * (pre = y / slope there) that the host side leaves to the framework. */
+int micn_fwd_prelu(const void* x, void* y, const void* residual,
+                   const float* const* gamma, const float* const* beta, int num_styles,
+                   const int64_t* styles,
+                   float* save_mean, float* save_rstd,
+                   int64_t N, int64_t C, int64_t M,
+                   int64_t x_stride_n, int64_t x_stride_c,
+                   int dtype, int epilogue, const float* slope_dev, float eps,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int micn_bwd_prelu(const void* dy, const void* x, const void* act_out,
+                   const float* const* gamma, const float* const* beta, int num_styles,
+                   const int64_t* styles,
+                   const float* save_mean, const float* save_rstd,
+                   void* dx, void* dresidual,
+                   float* dgamma, float* dbeta,
+                   int64_t N, int64_t C, int64_t M,
+                   int64_t x_stride_n, int64_t x_stride_c,
+                   int dtype, int epilogue, const float* slope_dev,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-buffer convenience path: x (and dy) live in HOST memory (pinned for full speed); the call
  * stages slab groups through `dev_scratch` (device, >= micn_host_scratch_bytes) with
  * H2D / kernels / D2H overlapped on internal streams, and BLOCKS until y (and dx, dgamma, dbeta)

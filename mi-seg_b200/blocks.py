@@ -8,6 +8,9 @@ and written once per norm instead of three to five times.
     out = norm2(conv2(out)); out += residual;   norm2.forward_fused(conv2(out), m, "add_lrelu", residual)
     out = lrelu(out)
 
+C-UNet's `ADN` blocks (acti_norm.py:104-110, "NDA": norm -> dropout(0) -> PReLU) fuse the same way, with the PReLU
+weight read on the device (`adn_forward`).
+
 `fuse_blocks(model)` rebinds `forward` on the block INSTANCES whose norms are the fast classes; class
 definitions, parameters and state-dict keys of `networks/` stay untouched.  Convolutions remain
 PyTorch/cuDNN (north_star).
@@ -59,6 +62,27 @@ def unet_basic_block_forward(self, inp, modalities=None):
     return self.norm2.forward_fused(out, modalities, "lrelu", slope=slope)
 
 
+def adn_forward(self, input, modalities=None):
+    """Drop-in for ADN.forward (networks/blocks/acti_norm.py:104-110) in the "NDA" ordering C-UNet uses
+    (norm -> dropout(p=0) -> PReLU, convolutions.py:173-179): prelu(norm(x)) in one kernel, the PReLU weight read
+    on the device.  A conditional norm validates `modalities` exactly as it does in the reference."""
+    act = self.A
+    slope = act.weight if isinstance(act, nn.PReLU) else float(act.negative_slope)
+    return self.N.forward_fused(input, modalities, "lrelu", slope=slope)
+
+
+def _adn_fusable(block) -> bool:
+    names = [n for n, _ in block.named_children()]
+    if names not in (["N", "A"], ["N", "D", "A"]):
+        return False
+    if not isinstance(block.N, (FastForwardMixin, FastPlainForwardMixin)):
+        return False
+    if "D" in names and not (isinstance(block.D, (nn.Dropout, nn.Dropout2d, nn.Dropout3d)) and block.D.p == 0):
+        return False
+    act = block.A
+    return (isinstance(act, nn.PReLU) and act.weight.numel() == 1) or isinstance(act, nn.LeakyReLU)
+
+
 def _fusable(block) -> bool:
     fast = (FastForwardMixin, FastPlainForwardMixin)
     norms = [getattr(block, n, None) for n in ("norm1", "norm2")]
@@ -80,5 +104,8 @@ def fuse_blocks(model: nn.Module) -> int:
             count += 1
         elif name == "UnetBasicBlock" and _fusable(m):
             m.forward = types.MethodType(unet_basic_block_forward, m)
+            count += 1
+        elif name == "ADN" and _adn_fusable(m):
+            m.forward = types.MethodType(adn_forward, m)
             count += 1
     return count

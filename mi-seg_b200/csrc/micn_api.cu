@@ -610,10 +610,10 @@ int micn_read_status(void* workspace, void* stream, int* status_out) {
     return (int)cudaStreamSynchronize(st);
 }
 
-int micn_fwd(const void* x, void* y, const void* residual, const float* const* gamma, const float* const* beta,
-             int num_styles, const int64_t* styles, float* save_mean, float* save_rstd, int64_t N, int64_t C, int64_t M,
-             int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope, float eps, void* workspace,
-             size_t workspace_bytes, void* stream) {
+static int fwd_impl(const void* x, void* y, const void* residual, const float* const* gamma, const float* const* beta,
+                    int num_styles, const int64_t* styles, float* save_mean, float* save_rstd, int64_t N, int64_t C,
+                    int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope,
+                    const float* slope_dev, float eps, void* workspace, size_t workspace_bytes, void* stream) {
     const int es = elem_size(dtype);
     if (!es) return MICN_ERR_BAD_DTYPE;
     if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
@@ -656,6 +656,7 @@ int micn_fwd(const void* x, void* y, const void* residual, const float* const* g
     p.num_styles = num_styles;
     p.eps = eps;
     p.slope = slope;
+    p.slope_dev = slope_dev;
 
     const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(y) && (!p.res || aligned16(p.res)) &&
                              ((M * es) % 16 == 0) && ((x_stride_n * es) % 16 == 0) && ((x_stride_c * es) % 16 == 0);
@@ -677,11 +678,28 @@ int micn_fwd(const void* x, void* y, const void* residual, const float* const* g
     return MICN_ERR_BAD_DTYPE;
 }
 
-int micn_bwd(const void* dy, const void* x, const void* act_out, const float* const* gamma, const float* const* beta,
-             int num_styles, const int64_t* styles, const float* save_mean, const float* save_rstd, void* dx,
-             void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C, int64_t M, int64_t x_stride_n,
-             int64_t x_stride_c, int dtype, int epilogue, float slope, void* workspace, size_t workspace_bytes,
-             void* stream) {
+int micn_fwd(const void* x, void* y, const void* residual, const float* const* gamma, const float* const* beta,
+             int num_styles, const int64_t* styles, float* save_mean, float* save_rstd, int64_t N, int64_t C, int64_t M,
+             int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope, float eps, void* workspace,
+             size_t workspace_bytes, void* stream) {
+    return fwd_impl(x, y, residual, gamma, beta, num_styles, styles, save_mean, save_rstd, N, C, M, x_stride_n, x_stride_c,
+                    dtype, epilogue, slope, nullptr, eps, workspace, workspace_bytes, stream);
+}
+
+int micn_fwd_prelu(const void* x, void* y, const void* residual, const float* const* gamma, const float* const* beta,
+                   int num_styles, const int64_t* styles, float* save_mean, float* save_rstd, int64_t N, int64_t C,
+                   int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, const float* slope_dev,
+                   float eps, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!slope_dev || epilogue == MICN_EPI_NONE) return MICN_ERR_BAD_ARG;
+    return fwd_impl(x, y, residual, gamma, beta, num_styles, styles, save_mean, save_rstd, N, C, M, x_stride_n, x_stride_c,
+                    dtype, epilogue, 0.f, slope_dev, eps, workspace, workspace_bytes, stream);
+}
+
+static int bwd_impl(const void* dy, const void* x, const void* act_out, const float* const* gamma,
+                    const float* const* beta, int num_styles, const int64_t* styles, const float* save_mean,
+                    const float* save_rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C,
+                    int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope,
+                    const float* slope_dev, void* workspace, size_t workspace_bytes, void* stream) {
     const int es = elem_size(dtype);
     if (!es) return MICN_ERR_BAD_DTYPE;
     if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
@@ -744,6 +762,7 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
     p.x_sC = x_stride_c;
     p.num_styles = num_styles;
     p.slope = slope;
+    p.slope_dev = slope_dev;
 
     const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(dy) && aligned16(dx) &&
                              (!p.act_out || aligned16(p.act_out)) && (!p.dres || aligned16(p.dres)) &&
@@ -764,6 +783,25 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
         case MICN_F16: return bwd_by_epi<__half>(epilogue, p, can_cluster, wfp, *d, st);
     }
     return MICN_ERR_BAD_DTYPE;
+}
+
+int micn_bwd(const void* dy, const void* x, const void* act_out, const float* const* gamma, const float* const* beta,
+             int num_styles, const int64_t* styles, const float* save_mean, const float* save_rstd, void* dx,
+             void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C, int64_t M, int64_t x_stride_n,
+             int64_t x_stride_c, int dtype, int epilogue, float slope, void* workspace, size_t workspace_bytes,
+             void* stream) {
+    return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
+                    M, x_stride_n, x_stride_c, dtype, epilogue, slope, nullptr, workspace, workspace_bytes, stream);
+}
+
+int micn_bwd_prelu(const void* dy, const void* x, const void* act_out, const float* const* gamma,
+                   const float* const* beta, int num_styles, const int64_t* styles, const float* save_mean,
+                   const float* save_rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C,
+                   int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, const float* slope_dev,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!slope_dev || epilogue == MICN_EPI_NONE) return MICN_ERR_BAD_ARG;
+    return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
+                    M, x_stride_n, x_stride_c, dtype, epilogue, 0.f, slope_dev, workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------ host-buffer path

@@ -408,13 +408,13 @@ __global__ void __launch_bounds__(kClusterThreads, 1) micn_fwd_cluster_kernel(co
                         for (int i = 0; i < 4; ++i) v[i] = lds128(addr + i * 512);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            stg_stream(ydst + goff + i * 512, fwd_apply<T, EPI>(v[i], rv[i], sub, a, b, p.slope));
+                            stg_stream(ydst + goff + i * 512, fwd_apply<T, EPI>(v[i], rv[i], sub, a, b, load_slope(p)));
                     } else if (vb < c.nv) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             if (vb + i * 32 + lane < c.nv)
                                 stg_stream(ydst + goff + i * 512,
-                                           fwd_apply<T, EPI>(lds128(addr + i * 512), rv[i], sub, a, b, p.slope));
+                                           fwd_apply<T, EPI>(lds128(addr + i * 512), rv[i], sub, a, b, load_slope(p)));
                     }
                     unit_release(c.empty0 + 8 * cu.slot);
                     cu = cursor_add(cu, kConsumerWarps / kUnitsPerChunk, S);
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) micn_bwd_cluster_kernel(co
             float gamma, beta;
             load_affine(p, style, ch, gamma, beta);
             const BwdSlab sc =
-                bwd_slab_consts<T, EPI>(__ldg(p.save_mean + slab), __ldg(p.save_rstd + slab), gamma, beta, p.slope);
+                bwd_slab_consts<T, EPI>(__ldg(p.save_mean + slab), __ldg(p.save_rstd + slab), gamma, beta, load_slope(p));
 
             // ---- pass 1
             BwdSums<T, EPI> acc;

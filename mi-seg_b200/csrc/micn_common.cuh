@@ -36,6 +36,7 @@ struct FwdParams {
     int num_styles;
     int affine;  // 0 -> gamma = 1, beta = 0
     float eps, slope;
+    const float* slope_dev;  // non-null: the activation slope lives in device memory (nn.PReLU weight, one element)
 };
 
 struct BwdParams {
@@ -60,6 +61,7 @@ struct BwdParams {
     int num_styles;
     int affine;
     float slope;
+    const float* slope_dev;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -294,6 +296,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// activation slope: a launch parameter (LeakyReLU) or a device scalar (PReLU, acti_norm.py:104-110)
+template <typename P>
+__device__ __forceinline__ float load_slope(const P& p) {
+    return p.slope_dev ? __ldg(p.slope_dev) : p.slope;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
     } else {
         // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
         Ring ra{0u, 0u}, rb{0u, 0u};
+        const float slope = load_slope(p);
         for (unsigned s = 0; s < nj + g.L; ++s) {
             if (s < nj) {
                 // ---- P1(s): statistics; the slot goes straight back, the piece stays in L2
@@ -514,8 +515,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
                             if (EPI != MICN_EPI_NONE) {
                                 float lo, hi;
                                 f2_split(o, lo, hi);
-                                lo = lo > 0.f ? lo : lo * p.slope;
-                                hi = hi > 0.f ? hi : hi * p.slope;
+                                lo = lo > 0.f ? lo : lo * slope;
+                                hi = hi > 0.f ? hi : hi * slope;
                                 o = f2_make(lo, hi);
                             }
                             f[k] = o;
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
     } else {
         // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
         Ring ra{0u, 0u}, rb{0u, 0u};
+        const float slope = load_slope(p);
         const uint32_t sb = c.stream_bytes;
         for (unsigned s = 0; s < nj + g.L; ++s) {
             if (s < nj) {
@@ -741,8 +743,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                         if (NS == 3) VecT<T>::unpack2(qo[i], of);
 #pragma unroll
                         for (int k = 0; k < VN / 2; k += 2) {
-                            const f32x2 g0 = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, ca2, bq2, p.slope);
-                            const f32x2 g1 = bwd_masked2<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0ull, mean2, ca2, bq2, p.slope);
+                            const f32x2 g0 = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, ca2, bq2, slope);
+                            const f32x2 g1 = bwd_masked2<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0ull, mean2, ca2, bq2, slope);
                             s1a = f2_add(s1a, g0);
                             s1b = f2_add(s1b, g1);
                             s2a = f2_fma(g0, f2_sub(xf[k], mean2), s2a);
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                         if (NS == 3) VecT<T>::unpack2(qo[i], of);
 #pragma unroll
                         for (int k = 0; k < VN / 2; ++k) {
-                            const f32x2 gg = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, A2, bq2, p.slope);
+                            const f32x2 gg = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, A2, bq2, slope);
                             gf[k] = gg;
                             xf[k] = f2_fma(A2, gg, f2_fma(B12, sizeof(T) == 4 ? f2_sub(xf[k], mean2) : xf[k], B02));
                         }

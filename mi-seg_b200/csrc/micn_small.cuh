@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_fwd_small_kernel(co
     auto apply = [&](float x, float r) {
         float v = fmaf(x - mean, a, beta);
         if (EPI == MICN_EPI_ADD_LRELU) v += r;
-        if (EPI != MICN_EPI_NONE) v = v > 0.f ? v : v * p.slope;
+        if (EPI != MICN_EPI_NONE) v = v > 0.f ? v : v * load_slope(p);
         return v;
     };
     for (long long i = t; i < pl.head; i += TPS)
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
         const Peel pl = make_peel<T>(p.M, xs, gs, os, dxs, drs);
 
         auto masked = [&](float d, float g, float o) {
-            if (EPI == MICN_EPI_LRELU) g = fmaf(d, a, beta) > 0.f ? g : g * p.slope;
-            if (EPI == MICN_EPI_ADD_LRELU) g = o > 0.f ? g : g * p.slope;
+            if (EPI == MICN_EPI_LRELU) g = fmaf(d, a, beta) > 0.f ? g : g * load_slope(p);
+            if (EPI == MICN_EPI_ADD_LRELU) g = o > 0.f ? g : g * load_slope(p);
             return g;
         };
 

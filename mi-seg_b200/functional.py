@@ -121,8 +121,21 @@ def _f32_params(ts: Sequence[torch.Tensor], device) -> List[torch.Tensor]:
     return out
 
 
+def _slope_tensor(slope, dev) -> Optional[torch.Tensor]:
+    """The PReLU weight as a one-element fp32 CUDA tensor, or None for a python float (LeakyReLU)."""
+    if not isinstance(slope, torch.Tensor):
+        return None
+    if slope.numel() != 1:
+        raise ValueError("instance_cond: only a single-parameter PReLU slope is supported (nn.PReLU(num_parameters=1))")
+    if slope.device != dev:
+        raise RuntimeError(f"instance_cond: slope on {slope.device}, input on {dev}")
+    t = slope.detach().reshape(1)
+    return t if t.dtype == torch.float32 else t.float()
+
+
 class _InstanceCondFn(torch.autograd.Function):
-    """forward(x, styles_dev, residual, eps, epilogue, slope, present, S, *weights, *biases)."""
+    """forward(x, styles_dev, residual, eps, epilogue, slope, present, S, *weights, *biases); `slope` is a float
+    (LeakyReLU) or the one-element weight tensor of an nn.PReLU (read on the device, gradient returned)."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
@@ -153,15 +166,25 @@ class _InstanceCondFn(torch.autograd.Function):
         with _on_device(dev):
             gp = _ptr_array(weights) if affine else None
             bp = _ptr_array(biases) if affine else None
-            rc = lib.micn_fwd(xs.data_ptr(), y.data_ptr(), res.data_ptr() if res is not None else None, gp, bp,
-                              num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
-                              mean.data_ptr(), rstd.data_ptr(), n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue,
-                              float(slope), float(eps), ws.data_ptr(), ws.numel(), stream)
+            slope_t = _slope_tensor(slope, dev)
+            if slope_t is not None and epilogue == _lib.EPI_NONE:
+                raise ValueError("instance_cond: a PReLU slope needs the 'lrelu' or 'add_lrelu' epilogue")
+            if slope_t is None:
+                rc = lib.micn_fwd(xs.data_ptr(), y.data_ptr(), res.data_ptr() if res is not None else None, gp, bp,
+                                  num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
+                                  mean.data_ptr(), rstd.data_ptr(), n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue,
+                                  float(slope), float(eps), ws.data_ptr(), ws.numel(), stream)
+            else:
+                rc = lib.micn_fwd_prelu(xs.data_ptr(), y.data_ptr(), res.data_ptr() if res is not None else None, gp, bp,
+                                        num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
+                                        mean.data_ptr(), rstd.data_ptr(), n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue,
+                                        slope_t.data_ptr(), float(eps), ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "micn_fwd")
-        ctx.save_for_backward(xs, styles_dev, mean, rstd, y if epilogue == _lib.EPI_ADD_LRELU else None, *weights,
-                              *biases)
-        ctx.meta = (n, c, m, sn, sc, epilogue, float(slope), num_styles, affine, present,
+        keep_y = epilogue == _lib.EPI_ADD_LRELU or slope_t is not None  # the PReLU slope gradient is read off y
+        ctx.save_for_backward(xs, styles_dev, mean, rstd, y if keep_y else None, slope_t, *weights, *biases)
+        ctx.meta = (n, c, m, sn, sc, epilogue, None if slope_t is not None else float(slope), num_styles, affine, present,
                     residual is not None and epilogue == _lib.EPI_ADD_LRELU)
+        ctx.slope_shape = tuple(slope.shape) if slope_t is not None else None
         return y
 
     @staticmethod
@@ -169,7 +192,7 @@ class _InstanceCondFn(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         n, c, m, sn, sc, epilogue, slope, num_styles, affine, present, has_res = ctx.meta
-        xs, styles_dev, mean, rstd, act_out, *params = ctx.saved_tensors
+        xs, styles_dev, mean, rstd, act_out, slope_t, *params = ctx.saved_tensors
         weights, biases = params[:num_styles], params[num_styles:]
         lib = _lib.lib()
         dev = xs.device
@@ -187,15 +210,26 @@ class _InstanceCondFn(torch.autograd.Function):
         with _on_device(dev):
             gp = _ptr_array(weights) if affine else None
             bp = _ptr_array(biases) if affine else None
-            rc = lib.micn_bwd(dy.data_ptr(), xs.data_ptr(), act_out.data_ptr() if act_out is not None else None,
-                              gp, bp, num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
-                              mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-                              dres.data_ptr() if dres is not None else None,
-                              dgamma.data_ptr() if dgamma is not None else None,
-                              dbeta.data_ptr() if dbeta is not None else None, n, c, m, sn, sc, _DTYPES[xs.dtype],
-                              epilogue, slope, ws.data_ptr(), ws.numel(), stream)
+            act_ptr = act_out.data_ptr() if (act_out is not None and epilogue == _lib.EPI_ADD_LRELU) else None
+            common = (dy.data_ptr(), xs.data_ptr(), act_ptr, gp, bp, num_styles,
+                      styles_dev.data_ptr() if styles_dev is not None else None, mean.data_ptr(), rstd.data_ptr(),
+                      dx.data_ptr(), dres.data_ptr() if dres is not None else None,
+                      dgamma.data_ptr() if dgamma is not None else None, dbeta.data_ptr() if dbeta is not None else None,
+                      n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue)
+            if slope_t is None:
+                rc = lib.micn_bwd(*common, slope, ws.data_ptr(), ws.numel(), stream)
+            else:
+                rc = lib.micn_bwd_prelu(*common, slope_t.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "micn_bwd")
-        grads: List[Optional[torch.Tensor]] = [dx, None, dres, None, None, None, None, None]
+        dslope = None
+        if slope_t is not None and ctx.needs_input_grad[5]:
+            # d/da prelu(pre) = pre where pre < 0, and there y = a * pre:  sum dy * pre = sum_{y<0} dy * y / a.
+            # (sign(y) = sign(pre) needs a > 0, which holds for the 0.25-initialised slopes of MI-Seg's nets; a
+            # slope of exactly 0 has no recoverable negative side and gets a zero gradient.)
+            yf, gf = act_out.float(), dy.float()
+            num = torch.where(yf < 0, gf * yf, torch.zeros((), device=dev)).sum()
+            dslope = torch.where(slope_t != 0, num / slope_t, torch.zeros_like(slope_t)).reshape(ctx.slope_shape)
+        grads: List[Optional[torch.Tensor]] = [dx, None, dres, None, None, dslope, None, None]
         if affine:
             for which in (dgamma, dbeta):
                 for s in range(num_styles):
@@ -207,7 +241,7 @@ class _InstanceCondFn(torch.autograd.Function):
 
 def instance_cond(x: torch.Tensor, styles_dev: Optional[torch.Tensor], weights: Sequence[torch.Tensor],
                   biases: Sequence[torch.Tensor], eps: float = 1e-5, epilogue: str = "none",
-                  residual: Optional[torch.Tensor] = None, slope: float = 0.01,
+                  residual: Optional[torch.Tensor] = None, slope=0.01,
                   present: Optional[Sequence[bool]] = None, num_styles: Optional[int] = None) -> torch.Tensor:
     """Batched input [N, C, *spatial]; `styles_dev` an int64 CUDA tensor [N] (None = style 0 everywhere);
     `weights` / `biases` per-style lists of [C] tensors (norms[s].weight / .bias), or empty for a

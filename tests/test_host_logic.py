@@ -252,3 +252,33 @@ def test_style_gradient_allreduce_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+def test_adn_fusion_selection_logic():
+    """blocks._adn_fusable picks exactly the 'N [D(p=0)] A' blocks whose norm is a fast module and whose activation is
+    a single-parameter PReLU or a LeakyReLU (acti_norm.py:104-110 ordering 'NDA')."""
+    blocks = importlib.import_module("mi-seg_b200.blocks")
+
+    class ADN(torch.nn.Sequential):
+        pass
+
+    def make(norm, act, drop=None):
+        m = ADN()
+        m.add_module("N", norm)
+        if drop is not None:
+            m.add_module("D", drop)
+        m.add_module("A", act)
+        return m
+
+    fast = pkg.FastConditionalInstanceNorm3d(2, 4)
+    plain = pkg.FastInstanceNorm3d(4, affine=True)
+    assert blocks._adn_fusable(make(fast, torch.nn.PReLU()))
+    assert blocks._adn_fusable(make(plain, torch.nn.PReLU(), torch.nn.Dropout(0.0)))
+    assert blocks._adn_fusable(make(fast, torch.nn.LeakyReLU(0.1)))
+    assert not blocks._adn_fusable(make(fast, torch.nn.PReLU(num_parameters=4)))      # per-channel slopes: not fused
+    assert not blocks._adn_fusable(make(fast, torch.nn.PReLU(), torch.nn.Dropout(0.1)))
+    assert not blocks._adn_fusable(make(torch.nn.InstanceNorm3d(4), torch.nn.PReLU()))
+    assert not blocks._adn_fusable(make(fast, torch.nn.ReLU()))
+    model = torch.nn.Sequential(make(fast, torch.nn.PReLU()), make(fast, torch.nn.ReLU()))
+    assert pkg.fuse_blocks(model) == 1
+    assert model[0].forward.__func__ is blocks.adn_forward
