@@ -241,6 +241,52 @@ def run_model_calls(pkg, dev, tdt, reps=20):
     return out
 
 
+def run_next_rows(pkg, dev, tdt, n, c, s, peak):
+    """Measurement for the SURVEY.md 8(f) rows that are built: (1) the decoders' plain instance norm, (3) the PReLU
+    epilogue of C-UNet's ADN, both on the headline activation through the nn.Module + autograd (CUDA events over
+    back-to-back fwd+bwd, rotating inputs), and (4) the sliding-window driver's own overhead (windows/s with a
+    pass-through predictor on a 192 x 192 x 160 volume: enumeration, gather, blend)."""
+    import torch
+
+    es = torch.empty(0, dtype=tdt).element_size()
+    E = n * c * s ** 3
+    R = 3
+    xs = [(torch.randn(n, c, s, s, s, device=dev) * 2 + 1).to(tdt).requires_grad_(True) for _ in range(R)]
+    dy = torch.randn(n, c, s, s, s, device=dev).to(tdt)
+    styles = (torch.arange(n, device=dev) % 2).to(torch.int64)
+    plain = pkg.FastInstanceNorm3d(c, affine=True).to(dev)
+    cond = pkg.FastConditionalInstanceNorm3d(num_styles=2, num_features=c).to(dev)
+    act = torch.nn.PReLU(init=0.25).to(dev)
+
+    def timed(fn, reps=30):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps * 1e3
+
+    t_plain = timed(lambda i: plain(xs[i % R]).backward(dy))
+    t_prelu = timed(lambda i: cond.forward_fused(xs[i % R], styles, "lrelu", slope=act.weight).backward(dy))
+    vol = torch.randn(1, 1, 192, 192, 160, device=dev)
+    nwin = len(pkg.window_slices((192, 192, 160), (96, 96, 96), 0.5))
+    t_sw = timed(lambda i: pkg.sliding_window_inference(vol, 96, 4, lambda w, modalities=None: w, overlap=0.5,
+                                                        modalities=torch.tensor([1], device=dev)), reps=3)
+    out = {"plain_instance_norm": {"us_per_fwd_bwd": t_plain, "gbps": 5 * E * es / t_plain * 1e-3,
+                                   "frac": 5 * E * es / t_plain * 1e-3 / peak},
+           "prelu_epilogue": {"us_per_fwd_bwd": t_prelu, "gbps": 5 * E * es / t_prelu * 1e-3,
+                              "frac": 5 * E * es / t_prelu * 1e-3 / peak,
+                              "note": "slope gradient accumulated by the backward kernel (one partial per CTA), summed by one small torch op"},
+           "sliding_window_driver": {"windows": nwin, "ms_per_volume": t_sw * 1e-3, "windows_per_s": nwin / (t_sw * 1e-6),
+                                     "note": "pass-through predictor: the driver's own gather / blend cost, 1 GPU"},
+           "what": f"module-level (nn.Module + autograd, host overhead included) on {n}x{c}x{s}^3"}
+    return out
+
+
 def ncu_traffic(args, n, c, s):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the backward kernel, from the committed
     `ncu --set full` capture of this workload (profiles/); None for any other workload."""
@@ -630,6 +676,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_model_calls:
         line["swin_unetr_norm_calls"] = run_model_calls(pkg, dev, tdt)
+        line["next_rows"] = run_next_rows(pkg, dev, tdt, n, c, s, peak)
     if args.sweep and world == 1:
         del xs, dys, ys, dxs
         torch.cuda.empty_cache()

@@ -116,8 +116,9 @@ int micn_bwd(const void* dy, const void* x, const void* act_out,
  * the nn.PReLU that follows the norm in C-UNet's ADN block ("NDA": norm -> dropout(0) -> PReLU,
  * networks/blocks/acti_norm.py:104-110, convolutions.py:173-179), so prelu(norm(x)) and its input gradient are one
  * kernel each and no host read of the parameter is needed.  epilogue must be MICN_EPI_LRELU or MICN_EPI_ADD_LRELU.
- * The gradient of the slope itself, sum over pre < 0 of dy * pre, is a plain reduction over y and dy
- * (pre = y / slope there) that the host side leaves to the framework. */
+ * The gradient of the slope itself is sum over pre <= 0 of dy * pre: for MICN_EPI_LRELU micn_bwd_prelu accumulates it in
+ * the same pass and writes PARTIAL sums into `dslope_partial` (device fp32, at least max(N*C, 1024) entries,
+ * ZERO-FILLED by the caller; one entry per CTA or per slab is written, the total is the gradient; may be NULL). */
 int micn_fwd_prelu(const void* x, void* y, const void* residual,
                    const float* const* gamma, const float* const* beta, int num_styles,
                    const int64_t* styles,
@@ -135,6 +136,7 @@ int micn_bwd_prelu(const void* dy, const void* x, const void* act_out,
                    int64_t N, int64_t C, int64_t M,
                    int64_t x_stride_n, int64_t x_stride_c,
                    int dtype, int epilogue, const float* slope_dev,
+                   float* dslope_partial,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Host-buffer convenience path: x (and dy) live in HOST memory (pinned for full speed); the call

@@ -488,8 +488,10 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     bool use_cluster = can_cluster && slab_bytes >= 32 * 1024;
     if (fp == 0) use_cluster = false;
     if (fp == 1 && can_cluster) use_cluster = true;
+    const bool ds = EPI == MICN_EPI_LRELU && p.dslope != nullptr;
+    if (ds) use_cluster = false;  // the slope-gradient partials are produced by the flat and small kernels only
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
-        auto kernel = micn_bwd_flat_kernel<T, EPI>;
+        auto kernel = ds ? micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : micn_bwd_flat_kernel<T, EPI, false>;
         FlatPlan fpl = {};
         const int rc = plan_flat(kernel, NS, NS, slabs, p.C, slab_bytes, d, &fpl);
         if (rc == 0) {
@@ -699,7 +701,7 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
                     const float* const* beta, int num_styles, const int64_t* styles, const float* save_mean,
                     const float* save_rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C,
                     int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope,
-                    const float* slope_dev, void* workspace, size_t workspace_bytes, void* stream) {
+                    const float* slope_dev, float* dslope_partial, void* workspace, size_t workspace_bytes, void* stream) {
     const int es = elem_size(dtype);
     if (!es) return MICN_ERR_BAD_DTYPE;
     if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
@@ -763,6 +765,7 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
     p.num_styles = num_styles;
     p.slope = slope;
     p.slope_dev = slope_dev;
+    p.dslope = dslope_partial;
 
     const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(dy) && aligned16(dx) &&
                              (!p.act_out || aligned16(p.act_out)) && (!p.dres || aligned16(p.dres)) &&
@@ -791,17 +794,19 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
              int64_t x_stride_c, int dtype, int epilogue, float slope, void* workspace, size_t workspace_bytes,
              void* stream) {
     return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
-                    M, x_stride_n, x_stride_c, dtype, epilogue, slope, nullptr, workspace, workspace_bytes, stream);
+                    M, x_stride_n, x_stride_c, dtype, epilogue, slope, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 int micn_bwd_prelu(const void* dy, const void* x, const void* act_out, const float* const* gamma,
                    const float* const* beta, int num_styles, const int64_t* styles, const float* save_mean,
                    const float* save_rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C,
                    int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, const float* slope_dev,
-                   void* workspace, size_t workspace_bytes, void* stream) {
+                   float* dslope_partial, void* workspace, size_t workspace_bytes, void* stream) {
     if (!slope_dev || epilogue == MICN_EPI_NONE) return MICN_ERR_BAD_ARG;
+    if (dslope_partial && epilogue != MICN_EPI_LRELU) return MICN_ERR_BAD_ARG;
     return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
-                    M, x_stride_n, x_stride_c, dtype, epilogue, 0.f, slope_dev, workspace, workspace_bytes, stream);
+                    M, x_stride_n, x_stride_c, dtype, epilogue, 0.f, slope_dev, dslope_partial, workspace, workspace_bytes,
+                    stream);
 }
 
 // ------------------------------------------------------------------------------------------ host-buffer path

@@ -62,6 +62,8 @@ struct BwdParams {
     int affine;
     float slope;
     const float* slope_dev;
+    float* dslope;  // PReLU (EPI_LRELU with slope_dev): partial sums of dy * pre over pre <= 0, one entry per CTA
+                    // (flat path) or per slab (small path); the caller zero-fills the buffer and adds it up
 };
 
 // ---------------------------------------------------------------------------------------------

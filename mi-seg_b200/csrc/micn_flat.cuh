@@ -570,7 +570,9 @@ __device__ __forceinline__ float4 slab_consts(const P& p, unsigned slab, unsigne
     return make_float4(__ldg(p.save_mean + slab), __ldg(p.save_rstd + slab), gamma, beta);
 }
 
-template <typename T, int EPI>
+// DS (EPI_LRELU with a device slope only): also accumulate d(prelu)/d(slope) = sum over pre <= 0 of dy * pre; every
+// consumer thread carries its share across ALL of the CTA's pieces and the CTA writes one partial at the end
+template <typename T, int EPI, bool DS = false>
 __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
     constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
     constexpr int VN = VecT<T>::N;
@@ -713,6 +715,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
         // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
         Ring ra{0u, 0u}, rb{0u, 0u};
         const float slope = load_slope(p);
+        f32x2 ds2 = f2_splat(0.f);
         const uint32_t sb = c.stream_bytes;
         for (unsigned s = 0; s < nj + g.L; ++s) {
             if (s < nj) {
@@ -743,6 +746,16 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                         if (NS == 3) VecT<T>::unpack2(qo[i], of);
 #pragma unroll
                         for (int k = 0; k < VN / 2; k += 2) {
+                            if (DS) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const f32x2 pre = sizeof(T) == 4 ? f2_fma(f2_sub(xf[k + h], mean2), ca2, bq2)
+                                                                     : f2_fma(xf[k + h], ca2, bq2);
+                                    float p0, p1;
+                                    f2_split(pre, p0, p1);
+                                    ds2 = f2_fma(gf[k + h], f2_make(p0 > 0.f ? 0.f : p0, p1 > 0.f ? 0.f : p1), ds2);
+                                }
+                            }
                             const f32x2 g0 = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, ca2, bq2, slope);
                             const f32x2 g1 = bwd_masked2<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0ull, mean2, ca2, bq2, slope);
                             s1a = f2_add(s1a, g0);
@@ -804,6 +817,16 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
                 if (lane == 0) mbar_arrive(c.emptyB + 8 * rb.i);
                 if (tid == 0) flat_trace(g, j, TR_P2_END);
                 rb.next(g.KB);
+            }
+        }
+        if (DS) {  // one partial per CTA: warp sums in a fixed order (the control ring's partial area is free now)
+            const float w = warp_sum(f2_hsum(ds2));
+            if (lane == 0) c.warp_part[warp] = w;
+            bar_sync(1, kFlatConsumerThreads);
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int i = 0; i < kFlatConsumerWarps; ++i) tot += c.warp_part[i];
+                p.dslope[cta] = tot;
             }
         }
     }

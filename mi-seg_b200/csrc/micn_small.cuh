@@ -209,9 +209,14 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
         };
 
         // ---- pass 1
-        float s1 = 0.f, s2 = 0.f;
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const bool want_ds = EPI == MICN_EPI_LRELU && p.dslope != nullptr;
         auto acc = [&](float x, float g, float o) {
             const float d = x - mean;
+            if (want_ds) {  // d prelu / d slope = pre on the negative side
+                const float pre = fmaf(d, a, beta);
+                s3 += pre > 0.f ? 0.f : g * pre;
+            }
             g = masked(d, g, o);
             s1 += g;
             s2 = fmaf(g, d * rstd, s2);
@@ -235,6 +240,11 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
             acc(V::load1(xs + i), V::load1(gs + i), EPI == MICN_EPI_ADD_LRELU ? V::load1(os + i) : 0.f);
 
         group_reduce_sum2<TPS>(s1, s2, scratch);
+        if (want_ds) {
+            float zero = 0.f;
+            group_reduce_sum2<TPS>(s3, zero, scratch);
+            if (t == 0) p.dslope[slab] = s3;
+        }
         if (t == 0 && p.dgamma) {
             p.ws_sum_dy[slab] = s1;
             p.ws_sum_dyxh[slab] = s2;

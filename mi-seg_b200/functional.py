@@ -180,7 +180,7 @@ class _InstanceCondFn(torch.autograd.Function):
                                         mean.data_ptr(), rstd.data_ptr(), n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue,
                                         slope_t.data_ptr(), float(eps), ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "micn_fwd")
-        keep_y = epilogue == _lib.EPI_ADD_LRELU or slope_t is not None  # the PReLU slope gradient is read off y
+        keep_y = epilogue == _lib.EPI_ADD_LRELU  # (its LeakyReLU mask, and with a PReLU slope its gradient, come from y)
         ctx.save_for_backward(xs, styles_dev, mean, rstd, y if keep_y else None, slope_t, *weights, *biases)
         ctx.meta = (n, c, m, sn, sc, epilogue, None if slope_t is not None else float(slope), num_styles, affine, present,
                     residual is not None and epilogue == _lib.EPI_ADD_LRELU)
@@ -216,16 +216,22 @@ class _InstanceCondFn(torch.autograd.Function):
                       dx.data_ptr(), dres.data_ptr() if dres is not None else None,
                       dgamma.data_ptr() if dgamma is not None else None, dbeta.data_ptr() if dbeta is not None else None,
                       n, c, m, sn, sc, _DTYPES[xs.dtype], epilogue)
+            want_ds = slope_t is not None and ctx.needs_input_grad[5]
+            ds_part = None
             if slope_t is None:
                 rc = lib.micn_bwd(*common, slope, ws.data_ptr(), ws.numel(), stream)
             else:
-                rc = lib.micn_bwd_prelu(*common, slope_t.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                if want_ds and epilogue == _lib.EPI_LRELU:  # the kernels accumulate the slope gradient in the same pass
+                    ds_part = torch.zeros(max(n * c, 1024), dtype=torch.float32, device=dev)
+                rc = lib.micn_bwd_prelu(*common, slope_t.data_ptr(), ds_part.data_ptr() if ds_part is not None else None,
+                                        ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "micn_bwd")
         dslope = None
-        if slope_t is not None and ctx.needs_input_grad[5]:
-            # d/da prelu(pre) = pre where pre < 0, and there y = a * pre:  sum dy * pre = sum_{y<0} dy * y / a.
-            # (sign(y) = sign(pre) needs a > 0, which holds for the 0.25-initialised slopes of MI-Seg's nets; a
-            # slope of exactly 0 has no recoverable negative side and gets a zero gradient.)
+        if want_ds and ds_part is not None:
+            dslope = ds_part.sum().reshape(ctx.slope_shape)
+        elif want_ds:
+            # add_lrelu: d/da prelu(v) = v where v < 0, and there y = a * v:  sum dy * v = sum_{y<0} dy * y / a
+            # (sign(y) = sign(v) needs a > 0, which holds for the 0.25-initialised slopes of MI-Seg's nets)
             yf, gf = act_out.float(), dy.float()
             num = torch.where(yf < 0, gf * yf, torch.zeros((), device=dev)).sum()
             dslope = torch.where(slope_t != 0, num / slope_t, torch.zeros_like(slope_t)).reshape(ctx.slope_shape)
