@@ -189,6 +189,7 @@ def run_model_calls(pkg, dev, tdt, reps=20):
                     "dx": torch.empty(shape, device=dev, dtype=tdt), "stats": torch.empty(2, c, device=dev),
                     "grads": torch.empty(2, 2, c, device=dev), "ws": torch.zeros(wsb, dtype=torch.uint8, device=dev),
                     "wsb": wsb, "c": c, "m": m, "chlast": chlast,
+                    "cws": torch.zeros(lib.micn_cl_workspace_bytes(1, c, m), dtype=torch.uint8, device=dev),
                     "gp": (ctypes.c_void_p * 2)(*[n_.weight.data_ptr() for n_ in mod.norms]),
                     "bp": (ctypes.c_void_p * 2)(*[n_.bias.data_ptr() for n_ in mod.norms])})
         elems += c * m
@@ -206,15 +207,25 @@ def run_model_calls(pkg, dev, tdt, reps=20):
 
     def ours_cabi():
         for r in raw:
-            x = r["x"].contiguous() if r["chlast"] else r["x"]  # the copy a strided input costs is inside the clock
             c, m = r["c"], r["m"]
-            rc = lib.micn_fwd(x.data_ptr(), r["y"].data_ptr(), None, r["gp"], r["bp"], 2, styles.data_ptr(),
-                              r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), 1, c, m, c * m, m, code, 0, 0.01, 1e-5,
-                              r["ws"].data_ptr(), r["wsb"], stream)
-            rc = rc or lib.micn_bwd(r["dy"].data_ptr(), x.data_ptr(), None, r["gp"], r["bp"], 2, styles.data_ptr(),
-                                    r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), r["dx"].data_ptr(), None,
-                                    r["grads"][0].data_ptr(), r["grads"][1].data_ptr(), 1, c, m, c * m, m, code, 0, 0.01,
-                                    r["ws"].data_ptr(), r["wsb"], stream)
+            if r["chlast"]:  # token-major input: the channels-last kernels, no transposing copy
+                xcl = r["x"].permute(0, 2, 3, 4, 1)
+                rc = lib.micn_fwd_cl(xcl.data_ptr(), r["y"].data_ptr(), r["gp"], r["bp"], 2, styles.data_ptr(),
+                                     r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), 1, c, m, code, 1e-5,
+                                     r["cws"].data_ptr(), r["cws"].numel(), stream)
+                rc = rc or lib.micn_bwd_cl(r["dy"].data_ptr(), xcl.data_ptr(), r["gp"], r["bp"], 2, styles.data_ptr(),
+                                           r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), r["dx"].data_ptr(),
+                                           r["grads"][0].data_ptr(), r["grads"][1].data_ptr(), 1, c, m, code,
+                                           r["cws"].data_ptr(), r["cws"].numel(), stream)
+            else:
+                x = r["x"]
+                rc = lib.micn_fwd(x.data_ptr(), r["y"].data_ptr(), None, r["gp"], r["bp"], 2, styles.data_ptr(),
+                                  r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), 1, c, m, c * m, m, code, 0, 0.01,
+                                  1e-5, r["ws"].data_ptr(), r["wsb"], stream)
+                rc = rc or lib.micn_bwd(r["dy"].data_ptr(), x.data_ptr(), None, r["gp"], r["bp"], 2, styles.data_ptr(),
+                                        r["stats"][0].data_ptr(), r["stats"][1].data_ptr(), r["dx"].data_ptr(), None,
+                                        r["grads"][0].data_ptr(), r["grads"][1].data_ptr(), 1, c, m, c * m, m, code, 0,
+                                        0.01, r["ws"].data_ptr(), r["wsb"], stream)
             if rc:
                 raise RuntimeError(f"model call list: rc={rc}")
 

@@ -139,6 +139,26 @@ int micn_bwd_prelu(const void* dy, const void* x, const void* act_out,
                    float* dslope_partial,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Channels-last (token-major) variant: x, y, dy, dx are dense [N, M, C] tensors (C fastest, C even) - the layout in
+ * which PatchMerging's norms (networks/blocks/patch_merging.py:136-141) and the ViT token norms
+ * (transformer_block.py:87-92, vit.py:188-193) reach `_apply_instance_norm` as permuted views.  Same math, no
+ * epilogue; the output keeps the input's layout, so the transposing copies around the norm disappear.
+ * Workspace: micn_cl_workspace_bytes, no zero-fill needed. */
+size_t micn_cl_workspace_bytes(int64_t N, int64_t C, int64_t M);
+int micn_fwd_cl(const void* x, void* y,
+                const float* const* gamma, const float* const* beta, int num_styles,
+                const int64_t* styles,
+                float* save_mean, float* save_rstd,
+                int64_t N, int64_t C, int64_t M, int dtype, float eps,
+                void* workspace, size_t workspace_bytes, void* stream);
+int micn_bwd_cl(const void* dy, const void* x,
+                const float* const* gamma, const float* const* beta, int num_styles,
+                const int64_t* styles,
+                const float* save_mean, const float* save_rstd,
+                void* dx, float* dgamma, float* dbeta,
+                int64_t N, int64_t C, int64_t M, int dtype,
+                void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-buffer convenience path: x (and dy) live in HOST memory (pinned for full speed); the call
  * stages slab groups through `dev_scratch` (device, >= micn_host_scratch_bytes) with
  * H2D / kernels / D2H overlapped on internal streams, and BLOCKS until y (and dx, dgamma, dbeta)

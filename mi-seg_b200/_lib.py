@@ -40,6 +40,11 @@ SYMBOLS = {
     "micn_bwd_prelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "micn_cl_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "micn_fwd_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                            c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "micn_bwd_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "micn_host_scratch_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int, c_int]),
     "micn_fwd_bwd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_float,

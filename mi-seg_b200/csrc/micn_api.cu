@@ -18,6 +18,7 @@
 #include <mutex>
 #include <vector>
 
+#include "micn_cl.cuh"
 #include "micn_cluster.cuh"
 #include "micn_flat.cuh"
 #include "micn_small.cuh"
@@ -559,6 +560,71 @@ int elem_size(int dtype) { return dtype == MICN_F32 ? 4 : (dtype == MICN_BF16 ||
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// ------------------------------------------------------------------------------------------ channels-last path
+namespace {
+struct ClPlan {
+    int MS;
+    long long rps;
+    float4* part;
+    float2* slab;
+    int* status;
+};
+size_t cl_ws_bytes(int64_t N, int64_t C) {
+    return kWsHeader + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4) + (size_t)N * (size_t)C * sizeof(float2);
+}
+int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_bytes, const DeviceInfo& d, ClPlan* pl) {
+    if (!workspace || workspace_bytes < cl_ws_bytes(N, C)) return MICN_ERR_WORKSPACE;
+    const long long tiles = (C + kClTile - 1) / kClTile;
+    long long ms = (2LL * d.sm_count + N * tiles - 1) / (N * tiles);  // at least two CTAs per SM
+    ms = std::min<long long>(ms, kClMaxSplits);
+    ms = std::min<long long>(ms, (M + 31) / 32);  // at least four rows per warp
+    ms = std::max<long long>(ms, 1);
+    pl->rps = (M + ms - 1) / ms;
+    pl->MS = (int)((M + pl->rps - 1) / pl->rps);
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    pl->status = reinterpret_cast<int*>(w) + 1;
+    pl->part = reinterpret_cast<float4*>(w + kWsHeader);
+    pl->slab = reinterpret_cast<float2*>(w + kWsHeader + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4));
+    return 0;
+}
+template <typename T>
+int cl_fwd_typed(const ClParams& p, dim3 grid, cudaStream_t st) {
+    micn_cl_fwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+    micn_cl_fwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+template <typename T>
+int cl_bwd_typed(const ClParams& p, dim3 grid, cudaStream_t st) {
+    micn_cl_bwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+    micn_cl_bwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+    if (p.dgamma) {
+        const long long sc = (long long)p.num_styles * p.C;
+        micn_cl_param_grads_kernel<<<(unsigned)((sc + 255) / 256), 256, 0, st>>>(p);
+    }
+    return (int)cudaGetLastError();
+}
+int cl_fill(ClParams& p, const float* const* gamma, const float* const* beta, int num_styles, const int64_t* styles,
+            int64_t N, int64_t C, int64_t M, const ClPlan& pl) {
+    p.affine = (gamma && beta) ? 1 : 0;
+    for (int s = 0; s < kMaxStyles; ++s) {
+        p.gamma[s] = (p.affine && s < num_styles) ? gamma[s] : nullptr;
+        p.beta[s] = (p.affine && s < num_styles) ? beta[s] : nullptr;
+        if (p.affine && s < num_styles && (!p.gamma[s] || !p.beta[s])) return MICN_ERR_BAD_ARG;
+    }
+    p.styles = reinterpret_cast<const long long*>(styles);
+    p.status = pl.status;
+    p.ws_part = pl.part;
+    p.ws_slab = pl.slab;
+    p.N = N;
+    p.C = C;
+    p.M = M;
+    p.MS = pl.MS;
+    p.rows_per_split = pl.rps;
+    p.num_styles = num_styles;
+    return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int micn_version(void) { return MICN_VERSION; }
@@ -807,6 +873,95 @@ int micn_bwd_prelu(const void* dy, const void* x, const void* act_out, const flo
     return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
                     M, x_stride_n, x_stride_c, dtype, epilogue, 0.f, slope_dev, dslope_partial, workspace, workspace_bytes,
                     stream);
+}
+
+// ------------------------------------------------------------------------------------------ channels-last path (C ABI)
+size_t micn_cl_workspace_bytes(int64_t N, int64_t C, int64_t M) {
+    (void)M;
+    if (N <= 0 || C <= 0) return 0;
+    return (cl_ws_bytes(N, C) + 255) & ~(size_t)255;
+}
+
+int micn_fwd_cl(const void* x, void* y, const float* const* gamma, const float* const* beta, int num_styles,
+                const int64_t* styles, float* save_mean, float* save_rstd, int64_t N, int64_t C, int64_t M, int dtype,
+                float eps, void* workspace, size_t workspace_bytes, void* stream) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if (N == 0 || C == 0 || M == 0) return MICN_OK;
+    if (!x || !y || (C & 1) || N > 65535) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc) return rc;
+    ClPlan pl;
+    if ((rc = cl_plan(N, C, M, workspace, workspace_bytes, *d, &pl))) return rc;
+    ClParams p = {};
+    p.x = x;
+    p.y = y;
+    p.save_mean = save_mean;
+    p.save_rstd = save_rstd;
+    p.eps = eps;
+    if ((rc = cl_fill(p, gamma, beta, num_styles, styles, N, C, M, pl))) return rc;
+    const dim3 grid((unsigned)((C + kClTile - 1) / kClTile), (unsigned)pl.MS, (unsigned)N);
+    g_opt.last_path.store(3);
+    g_opt.last_cs.store(pl.MS);
+    g_opt.last_grid.store((long long)grid.x * grid.y * grid.z);
+    g_opt.launches.fetch_add(2);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case MICN_F32: return cl_fwd_typed<float>(p, grid, st);
+        case MICN_BF16: return cl_fwd_typed<__nv_bfloat16>(p, grid, st);
+        case MICN_F16: return cl_fwd_typed<__half>(p, grid, st);
+    }
+    return MICN_ERR_BAD_DTYPE;
+}
+
+int micn_bwd_cl(const void* dy, const void* x, const float* const* gamma, const float* const* beta, int num_styles,
+                const int64_t* styles, const float* save_mean, const float* save_rstd, void* dx, float* dgamma,
+                float* dbeta, int64_t N, int64_t C, int64_t M, int dtype, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if ((dgamma == nullptr) != (dbeta == nullptr)) return MICN_ERR_BAD_ARG;
+    if (N == 0 || C == 0 || M == 0) {
+        if (dgamma && C > 0) {
+            cudaMemsetAsync(dgamma, 0, sizeof(float) * num_styles * C, (cudaStream_t)stream);
+            cudaMemsetAsync(dbeta, 0, sizeof(float) * num_styles * C, (cudaStream_t)stream);
+        }
+        return MICN_OK;
+    }
+    if (!x || !dy || !dx || !save_mean || !save_rstd || (C & 1) || N > 65535) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc) return rc;
+    ClPlan pl;
+    if ((rc = cl_plan(N, C, M, workspace, workspace_bytes, *d, &pl))) return rc;
+    ClParams p = {};
+    p.x = x;
+    p.dy = dy;
+    p.y = dx;
+    p.save_mean = const_cast<float*>(save_mean);
+    p.save_rstd = const_cast<float*>(save_rstd);
+    p.dgamma = dgamma;
+    p.dbeta = dbeta;
+    if ((rc = cl_fill(p, gamma, beta, num_styles, styles, N, C, M, pl))) return rc;
+    const dim3 grid((unsigned)((C + kClTile - 1) / kClTile), (unsigned)pl.MS, (unsigned)N);
+    g_opt.last_path.store(3);
+    g_opt.last_cs.store(pl.MS);
+    g_opt.last_grid.store((long long)grid.x * grid.y * grid.z);
+    g_opt.launches.fetch_add(dgamma ? 3 : 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case MICN_F32: return cl_bwd_typed<float>(p, grid, st);
+        case MICN_BF16: return cl_bwd_typed<__nv_bfloat16>(p, grid, st);
+        case MICN_F16: return cl_bwd_typed<__half>(p, grid, st);
+    }
+    return MICN_ERR_BAD_DTYPE;
 }
 
 // ------------------------------------------------------------------------------------------ host-buffer path

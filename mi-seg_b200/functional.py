@@ -69,6 +69,7 @@ class _on_device:
 def reset_workspaces() -> None:
     """Drop every cached workspace (call after a CUDA error so stale control words cannot survive)."""
     _workspaces.clear()
+    _cl_workspaces.clear()
 
 
 def _ptr_array(tensors: Sequence[torch.Tensor]):
@@ -245,6 +246,103 @@ class _InstanceCondFn(torch.autograd.Function):
         return tuple(grads)
 
 
+# ------------------------------------------------------------------------------------------------ channels-last
+_cl_native = True
+_cl_workspaces = {}
+
+
+def set_channels_last_native(enabled: bool) -> None:
+    """Channels-last (stride_C == 1) inputs are normalised in place of their layout by default (the output keeps
+    the input's strides, as PyTorch's own memory-format propagation does).  `False` restores the reference's
+    behaviour of returning a fresh NC*-contiguous tensor at the cost of two transposing copies."""
+    global _cl_native
+    _cl_native = bool(enabled)
+
+
+def _channels_last_view(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """x as a dense [N, *spatial, C] tensor if it is laid out that way (and worth it), else None."""
+    if not _cl_native or x.dim() < 3 or x.shape[1] < 2 or (x.shape[1] & 1) or x.stride(1) != 1 or x.shape[0] > 65535:
+        return None
+    perm = [0] + list(range(2, x.dim())) + [1]
+    v = x.permute(perm)
+    return v if v.is_contiguous() else None
+
+
+def _cl_workspace(device, stream: int, n: int, c: int, m: int) -> torch.Tensor:
+    need = int(_lib.lib().micn_cl_workspace_bytes(n, c, m))
+    key = (device.index, stream)
+    ws = _cl_workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _cl_workspaces[key] = ws
+    return ws
+
+
+class _InstanceCondClFn(torch.autograd.Function):
+    """Channels-last route: forward(x_cl [N, *spatial, C] dense, styles_dev, eps, present, S, *weights, *biases)
+    -> y_cl in the same layout (micn_fwd_cl / micn_bwd_cl)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x_cl, styles_dev, eps, present, num_styles, *params):
+        lib = _lib.lib()
+        dev = x_cl.device
+        affine = len(params) > 0
+        weights = _f32_params(params[:num_styles], dev) if affine else []
+        biases = _f32_params(params[num_styles:], dev) if affine else []
+        n, c = x_cl.shape[0], x_cl.shape[-1]
+        m = x_cl.numel() // (n * c)
+        if affine and any(w.numel() != c for w in weights + biases):
+            raise ValueError("instance_cond: parameter length does not match the channel count")
+        y = torch.empty_like(x_cl)
+        stats = torch.empty(2, n * c, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _cl_workspace(dev, stream, n, c, m)
+        with _on_device(dev):
+            rc = lib.micn_fwd_cl(x_cl.data_ptr(), y.data_ptr(), _ptr_array(weights) if affine else None,
+                                 _ptr_array(biases) if affine else None, num_styles,
+                                 styles_dev.data_ptr() if styles_dev is not None else None, stats[0].data_ptr(),
+                                 stats[1].data_ptr(), n, c, m, _DTYPES[x_cl.dtype], float(eps), ws.data_ptr(), ws.numel(),
+                                 stream)
+        _lib.check(rc, "micn_fwd_cl")
+        ctx.save_for_backward(x_cl, styles_dev, stats, *weights, *biases)
+        ctx.meta = (n, c, m, num_styles, affine, present)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        n, c, m, num_styles, affine, present = ctx.meta
+        x_cl, styles_dev, stats, *params = ctx.saved_tensors
+        weights, biases = params[:num_styles], params[num_styles:]
+        lib = _lib.lib()
+        dev = x_cl.device
+        dy = dy.contiguous()
+        if dy.dtype != x_cl.dtype:
+            dy = dy.to(x_cl.dtype)
+        dx = torch.empty_like(x_cl)
+        need_param_grads = affine and any(ctx.needs_input_grad[5:])
+        pgrads = torch.empty((2, num_styles, c), dtype=torch.float32, device=dev) if need_param_grads else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _cl_workspace(dev, stream, n, c, m)
+        with _on_device(dev):
+            rc = lib.micn_bwd_cl(dy.data_ptr(), x_cl.data_ptr(), _ptr_array(weights) if affine else None,
+                                 _ptr_array(biases) if affine else None, num_styles,
+                                 styles_dev.data_ptr() if styles_dev is not None else None, stats[0].data_ptr(),
+                                 stats[1].data_ptr(), dx.data_ptr(), pgrads[0].data_ptr() if need_param_grads else None,
+                                 pgrads[1].data_ptr() if need_param_grads else None, n, c, m, _DTYPES[x_cl.dtype],
+                                 ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "micn_bwd_cl")
+        grads: List[Optional[torch.Tensor]] = [dx, None, None, None, None]
+        if affine:
+            for which in ((pgrads[0], pgrads[1]) if need_param_grads else (None, None)):
+                for s in range(num_styles):
+                    absent = present is not None and not present[s]
+                    grads.append(None if (which is None or absent) else which[s])
+        return tuple(grads)
+
+
 def instance_cond(x: torch.Tensor, styles_dev: Optional[torch.Tensor], weights: Sequence[torch.Tensor],
                   biases: Sequence[torch.Tensor], eps: float = 1e-5, epilogue: str = "none",
                   residual: Optional[torch.Tensor] = None, slope=0.01,
@@ -265,5 +363,11 @@ def instance_cond(x: torch.Tensor, styles_dev: Optional[torch.Tensor], weights: 
         if styles_dev.device != x.device or styles_dev.dtype != torch.int64 or styles_dev.numel() != x.shape[0]:
             raise ValueError("instance_cond: styles must be an int64 tensor [N] on the input's device")
         styles_dev = styles_dev.reshape(-1).contiguous()
+    if epilogue == "none" and x.is_cuda and x.dtype in _DTYPES:
+        x_cl = _channels_last_view(x)
+        if x_cl is not None:  # token-major input: reduce the strided columns in place, keep the layout
+            y_cl = _InstanceCondClFn.apply(x_cl, styles_dev, eps, tuple(present) if present is not None else None, s,
+                                           *weights, *biases)
+            return y_cl.permute([0, x.dim() - 1] + list(range(1, x.dim() - 1)))
     return _InstanceCondFn.apply(x, styles_dev, residual, eps, _EPILOGUES[epilogue], slope,
                                  tuple(present) if present is not None else None, s, *weights, *biases)

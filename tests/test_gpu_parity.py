@@ -215,16 +215,67 @@ def test_large_mean_small_std(pkg):
     _case(pkg, (2, 3, 32, 32, 32), [0, 1], 2, torch.float32, mean=50.0, std=0.1, seed=8)
 
 
-def test_channels_last_input_gives_contiguous_output(pkg):
-    """PatchMerging / ViT feed channels-last strided views (patch_merging.py:136-141); the result must
-    equal the contiguous computation and come back as a dense NC* tensor."""
+def test_channels_last_input_native_and_reference_layout(pkg):
+    """PatchMerging / ViT feed channels-last strided views (patch_merging.py:136-141).  By default the columns are
+    reduced in place and the output keeps the input's layout; with the native route off the
+    result comes back as a dense NC* tensor like the reference's torch.stack.  Same values either way."""
     mod = pkg.FastConditionalInstanceNorm3d(2, 16).cuda()
     xcl = torch.randn(2, 6, 6, 6, 16, device="cuda")
     xv = xcl.permute(0, 4, 1, 2, 3)
+    y_ref = mod(xv.contiguous(), [0, 1])
     y1 = mod(xv, [0, 1])
-    y2 = mod(xv.contiguous(), [0, 1])
-    assert y1.is_contiguous()
-    assert torch.equal(y1, y2)
+    assert pkg._lib.get_option("last_path") == 3
+    assert y1.shape == xv.shape and y1.stride() == xv.stride()
+    assert float((y1 - y_ref).abs().max()) < 1e-5
+    pkg.set_channels_last_native(False)
+    try:
+        y2 = mod(xv, [0, 1])
+        assert y2.is_contiguous() and torch.equal(y2, y_ref)
+    finally:
+        pkg.set_channels_last_native(True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("shape,name", [((2, 16, 6, 6, 6), "16x6^3"), ((1, 384, 8, 8, 8), "merge_384"),
+                                        ((3, 70, 5, 7, 3), "C70_ragged"), ((4, 768, 216), "vit_tokens"),
+                                        ((2, 10, 4000), "long_columns")], ids=lambda v: v if isinstance(v, str) else None)
+def test_channels_last_route_vs_oracle(pkg, shape, name, dtype):
+    gen = torch.Generator().manual_seed(len(name))
+    n, c = shape[0], shape[1]
+    styles = [(i * 5 + 1) % 3 for i in range(n)]
+    gamma = (1 + 0.3 * torch.randn(3, c, generator=gen)).numpy()
+    beta = (0.3 * torch.randn(3, c, generator=gen)).numpy()
+    x32 = torch.randn(*shape, generator=gen) * 2 + 1
+    dy32 = torch.randn(*shape, generator=gen)
+    xq, dyq = x32.to(dtype), dy32.to(dtype)
+    perm = [0] + list(range(2, len(shape))) + [1]
+    inv = [0, len(shape) - 1] + list(range(1, len(shape) - 1))
+    x = xq.permute(perm).contiguous().cuda().permute(inv).requires_grad_(True)  # logical NC*, channels-last memory
+    assert x.stride(1) == 1
+    w = [torch.from_numpy(gamma[s]).cuda().requires_grad_(True) for s in range(3)]
+    b = [torch.from_numpy(beta[s]).cuda().requires_grad_(True) for s in range(3)]
+    st = torch.tensor(styles, dtype=torch.int64, device="cuda")
+    y = pkg.instance_cond(x, st, w, b)
+    assert pkg._lib.get_option("last_path") == 3 and y.stride() == x.stride()
+    y.backward(dyq.cuda())
+    torch.cuda.synchronize()
+    xn, dyn = xq.float().numpy(), dyq.float().numpy()
+    yr, m_, r_ = O.fwd_f64(xn, styles, gamma, beta)
+    dxr, dgr, dbr, _ = O.bwd_f64(dyn, xn, styles, gamma, m_, r_)
+    tol = TOL[dtype]
+    assert rel_err(y.detach().float().cpu().numpy(), yr) < tol
+    assert rel_err(x.grad.float().cpu().numpy(), dxr) < tol
+    ptol = 5e-5 if dtype == torch.float32 else 5e-3
+    assert rel_err(np.stack([t.grad.cpu().numpy() for t in w]), dgr) < ptol
+    assert rel_err(np.stack([t.grad.cpu().numpy() for t in b]), dbr) < ptol
+
+
+def test_channels_last_odd_channel_count_takes_the_copy_route(pkg):
+    mod = pkg.FastConditionalInstanceNorm1d(2, 7).cuda()
+    x = torch.randn(3, 50, 7, device="cuda").permute(0, 2, 1)
+    y = mod(x, [0, 1, 1])
+    assert pkg._lib.get_option("last_path") != 3 and y.is_contiguous()
+    assert float((y - mod(x.contiguous(), [0, 1, 1])).abs().max()) == 0.0
 
 
 # ------------------------------------------------------------------------------------------------ behaviours
