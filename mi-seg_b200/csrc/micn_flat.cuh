@@ -160,21 +160,25 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
     c.coefv = c.warp_part + kFlatNB * kFlatConsumerWarps * 4;
     c.tagw = reinterpret_cast<volatile unsigned*>(c.coefv + kFlatNB * 8);
     c.tagbar = smem_u32(const_cast<unsigned*>(c.tagw) + 2);
-    if (threadIdx.x == 0) {
-        mbar_init(c.tagbar, 1);
-        for (unsigned i = 0; i < g.KA; ++i) {
-            mbar_init(c.fullA + 8 * i, 1);
-            mbar_init(c.emptyA + 8 * i, kFlatConsumerWarps);
+    // one barrier per thread (73 of them): a single thread doing all the inits costs ~0.4 us before the first TMA
+    {
+        const unsigned t = threadIdx.x;
+        if (t < kFlatMaxSlots) {
+            if (t < g.KA) {
+                mbar_init(c.fullA + 8 * t, 1);
+                mbar_init(c.emptyA + 8 * t, kFlatConsumerWarps);
+            }
+            if (t < g.KB) {
+                mbar_init(c.fullB + 8 * t, 1);
+                mbar_init(c.emptyB + 8 * t, kFlatConsumerWarps);
+            }
+        } else if (t < kFlatMaxSlots + kFlatNB) {
+            mbar_init(c.p1d0 + 8 * (t - kFlatMaxSlots), kFlatConsumerWarps);
+            mbar_init(c.coef0 + 8 * (t - kFlatMaxSlots), 1);
+        } else if (t == kFlatMaxSlots + kFlatNB) {
+            mbar_init(c.tagbar, 1);
         }
-        for (unsigned i = 0; i < g.KB; ++i) {
-            mbar_init(c.fullB + 8 * i, 1);
-            mbar_init(c.emptyB + 8 * i, kFlatConsumerWarps);
-        }
-        for (unsigned i = 0; i < kFlatNB; ++i) {
-            mbar_init(c.p1d0 + 8 * i, kFlatConsumerWarps);
-            mbar_init(c.coef0 + 8 * i, 1);
-        }
-        fence_mbar_init();
+        if (t <= kFlatMaxSlots + kFlatNB) fence_mbar_init();
     }
     __syncthreads();
     return c;
