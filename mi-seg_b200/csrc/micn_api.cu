@@ -35,7 +35,7 @@ struct Options {
     std::atomic<long long> flat_slots_b{-1};  // ring B slots (second touch, L2)
     std::atomic<long long> flat_lag{-1};      // steps P2 trails P1
     std::atomic<long long> flat_l2_mb{-1};    // L2 budget (MB) the lag is sized for
-    std::atomic<long long> flat_poll_delay_ns{-1}, flat_poll_backoff_ns{-1};
+    std::atomic<long long> flat_poll_delay_ns{-1}, flat_poll_backoff_ns{-1}, flat_poll_delay_tail_ns{-1};
     std::atomic<long long> flat_piece_vecs{-1};  // cap on vectors per piece
     std::atomic<long long> flat_min_bytes{-1};   // smallest slab the flat path takes
     std::atomic<long long> flat_grid{-1};     // cap on the persistent grid
@@ -66,7 +66,7 @@ const OptName kOptNames[] = {
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
     {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace},
     {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
-    {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
+    {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
 
 // ------------------------------------------------------------------------------------------ device
@@ -305,11 +305,13 @@ int flat_blocks_per_sm(K kernel, int smem, int smem_optin) {
 template <typename KernelT>
 int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, long long slab_bytes, const DeviceInfo& d,
               FlatPlan* fp) {
-    long long G = d.sm_count;
+    long long G = (long long)d.sm_count * kFlatCtasPerSm;
     const long long gcap = g_opt.flat_grid.load();
-    if (gcap > 0 && gcap < G) G = gcap;
+    if (gcap > 0 && gcap * kFlatCtasPerSm < G) G = gcap * kFlatCtasPerSm;
     const long long V = slab_bytes / 16;
-    const long long ring = (long long)d.smem_optin - flat_ctl_bytes() - 128;
+    // shared memory of one SM (228 KB, 1 KB reserved per resident CTA) split between the co-resident CTAs
+    const long long per_cta = kFlatCtasPerSm == 1 ? (long long)d.smem_optin : (233472LL / kFlatCtasPerSm - 1024);
+    const long long ring = per_cta - flat_ctl_bytes() - 128;
     long long ovh = g_opt.flat_ovh_vecs.load();
     if (ovh < 0) ovh = 2200;
 
@@ -332,7 +334,7 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     if (pvmax < kFlatMinPieceVecs) return 1;
     const long long slot_vecs = (pvmax + 7) & ~7LL;
     const int smem = (int)((KA * NS + KB * NSB) * slot_vecs * 16 + flat_ctl_bytes());
-    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < 1) return 1;
+    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < kFlatCtasPerSm) return 1;
 
     // a slab of P pieces spans R = ceil((P-1)/G)+1 rounds; P2 trails P1 by L >= R steps (L <= kFlatMaxLag)
     const long long pmax_hw = std::min<long long>(kFlatMaxPieces, (long long)(kFlatMaxLag - 1) * G + 1);
@@ -388,8 +390,10 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     fp->g.divP = fastdiv_make((unsigned)bestP);
     fp->g.divC = fastdiv_make((unsigned)C);
     const long long pd = g_opt.flat_poll_delay_ns.load(), pb = g_opt.flat_poll_backoff_ns.load();
-    fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 2000);
+    fp->g.poll_delay_ns = (unsigned)(pd >= 0 ? pd : 2500);
     fp->g.poll_backoff_ns = (unsigned)(pb >= 0 ? pb : 200);
+    const long long pt = g_opt.flat_poll_delay_tail_ns.load();
+    fp->g.poll_delay_tail_ns = (unsigned)(pt >= 0 ? pt : fp->g.poll_delay_ns / 4);
     fp->g.trace = reinterpret_cast<long long*>(g_opt.flat_trace.load());
     fp->grid = (int)std::min<long long>(G, (long long)fp->g.T);
     fp->smem = smem;

@@ -57,14 +57,24 @@
 
 namespace micn {
 
-constexpr int kFlatConsumerWarps = 16;
+#ifndef MICN_FLAT_CW
+#define MICN_FLAT_CW 16  // consumer warps per CTA
+#endif
+#ifndef MICN_FLAT_GW
+#define MICN_FLAT_GW 4   // gather warps per CTA
+#endif
+#ifndef MICN_FLAT_CPS
+#define MICN_FLAT_CPS 1  // persistent CTAs per SM
+#endif
+constexpr int kFlatConsumerWarps = MICN_FLAT_CW;
+constexpr int kFlatCtasPerSm = MICN_FLAT_CPS;
 constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512
 constexpr int kFlatProducerWarpA = kFlatConsumerWarps;
 constexpr int kFlatProducerWarpB = kFlatConsumerWarps + 1;
 constexpr int kFlatPublishWarp0 = kFlatConsumerWarps + 2;
 constexpr int kFlatPublishWarps = 1;
 constexpr int kFlatGatherWarp0 = kFlatPublishWarp0 + kFlatPublishWarps;
-constexpr int kFlatGatherWarps = 4;  // a gather is a multi-microsecond latency chain: keep several in flight
+constexpr int kFlatGatherWarps = MICN_FLAT_GW;  // a gather is a multi-microsecond latency chain: keep several in flight
 constexpr int kFlatThreads = (kFlatConsumerWarps + 2 + kFlatPublishWarps + kFlatGatherWarps) * 32;  // 736 -> 88 registers
 constexpr int kFlatMaxSlots = 8;     // per ring
 constexpr int kFlatNB = 32;          // per-piece control ring (partials, coefficients): piece j -> entry j % 32
@@ -83,7 +93,7 @@ struct FlatGeom {
     unsigned L;            // steps P2 trails P1
     unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
     unsigned* ws_ctl;      // workspace header: [0] launch epoch, [1] CTAs done (device-side, CUDA-graph safe)
-    unsigned poll_delay_ns, poll_backoff_ns;
+    unsigned poll_delay_ns, poll_delay_tail_ns, poll_backoff_ns;
     FastDiv divP, divC;    // piece index -> slab, slab -> sample
     uint4* ws_piece;       // [T] piece records
     uint4* ws_slab;        // [num_slabs] per-slab records (backward parameter gradients)
@@ -322,7 +332,7 @@ __device__ __forceinline__ void piece_sweep(unsigned pv, unsigned tid, Load load
 // forward
 // =================================================================================================
 template <typename T, int EPI>
-__global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const FwdParams p, const FlatGeom g) {
+__global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_kernel(const FwdParams p, const FlatGeom g) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VN = VecT<T>::N;
     constexpr int NSB = EPI == MICN_EPI_ADD_LRELU ? 2 : 1;  // ring B: x [, residual]
@@ -411,7 +421,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_fwd_flat_kernel(const Fw
             mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
             // ... and let their record stores land; the last L pieces of the CTA are the kernel's tail, where
             // nothing hides a late coefficient any more: poll eagerly there
-            __nanosleep(j + g.L >= nj ? g.poll_delay_ns / 4 : g.poll_delay_ns);
+            __nanosleep(j + g.L >= nj ? g.poll_delay_tail_ns : g.poll_delay_ns);
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float ref = 0.f, A = 0.f, B = 0.f;
             ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, tag, g.poll_backoff_ns, lane,
@@ -577,7 +587,7 @@ __device__ __forceinline__ float4 slab_consts(const P& p, unsigned slab, unsigne
 // DS (EPI_LRELU with a device slope only): also accumulate d(prelu)/d(slope) = sum over pre <= 0 of dy * pre; every
 // consumer thread carries its share across ALL of the CTA's pieces and the CTA writes one partial at the end
 template <typename T, int EPI, bool DS = false>
-__global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
+__global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
     constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
     constexpr int VN = VecT<T>::N;
     constexpr int U = NS == 3 ? 1 : 2;  // vectors per thread in flight per stream (register budget: 72)
@@ -659,7 +669,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) micn_bwd_flat_kernel(const Bw
             const float mean = pr.x, rstd = pr.y, gamma = pr.z, beta = pr.w;
             // no polling before this CTA's own piece is through P1 (the others are at the same point)
             mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
-            __nanosleep(j + g.L >= nj ? g.poll_delay_ns / 4 : g.poll_delay_ns);  // let the record stores land (tail: eager)
+            __nanosleep(j + g.L >= nj ? g.poll_delay_tail_ns : g.poll_delay_ns);  // let the record stores land (tail: eager)
             if (lane == 0) flat_trace(g, j, TR_GA_BEGIN);
             float S1 = 0.f, S2 = 0.f;
             ll_gather(g.ws_piece + (size_t)pc.slab * g.P, g.P, tag, g.poll_backoff_ns, lane, [](float, float) {},
