@@ -20,7 +20,26 @@
 
 #include "micn_cl.cuh"
 #include "micn_cluster.cuh"
+// the flat path in two CTA shapes: one 16-consumer-warp CTA per SM (fp32 forward, every backward) and two
+// 8-consumer-warp CTAs per SM, out of phase with each other (16-bit forward: 31.5 us instead of 33.5 us at 1x48x96^3)
+#define MICN_FLAT_NS flat1
+#define MICN_FLAT_CW 16
+#define MICN_FLAT_GW 4
+#define MICN_FLAT_CPS 1
 #include "micn_flat.cuh"
+#undef MICN_FLAT_NS
+#undef MICN_FLAT_CW
+#undef MICN_FLAT_GW
+#undef MICN_FLAT_CPS
+#define MICN_FLAT_NS flat2
+#define MICN_FLAT_CW 8
+#define MICN_FLAT_GW 2
+#define MICN_FLAT_CPS 2
+#include "micn_flat.cuh"
+#undef MICN_FLAT_NS
+#undef MICN_FLAT_CW
+#undef MICN_FLAT_GW
+#undef MICN_FLAT_CPS
 #include "micn_small.cuh"
 
 using namespace micn;
@@ -261,9 +280,9 @@ constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32), [8] fl
 // upper bound of the pieces the flat planner can cut one slab into
 long long flat_max_pieces(long long slab_bytes) {
     const long long V = slab_bytes / 16;
-    long long p = (V + kFlatMinPieceVecs - 1) / kFlatMinPieceVecs;
+    long long p = (V + flat1::Traits::kMinPieceVecs - 1) / flat1::Traits::kMinPieceVecs;
     if (p < 1) p = 1;
-    return p > kFlatMaxPieces ? kFlatMaxPieces : p;
+    return p > flat1::Traits::kMaxPieces ? flat1::Traits::kMaxPieces : p;
 }
 
 struct WsLayout {
@@ -280,19 +299,20 @@ WsLayout ws_layout(long long N, long long C, long long M, int es) {
     return w;
 }
 
+template <typename TR>
 struct FlatPlan {
-    FlatGeom g;
+    typename TR::Geom g;
     int grid, smem;
 };
 
 // occupancy of a flat kernel at its full shared-memory footprint (cached per kernel/device)
 template <typename K>
-int flat_blocks_per_sm(K kernel, int smem, int smem_optin) {
+int flat_blocks_per_sm(K kernel, int threads, int smem, int smem_optin) {
     KernelState* ks = nullptr;
     if (kernel_prepare(kernel, smem, smem_optin, &ks)) return 0;
     if (ks->occ[0] >= 0) return ks->occ[0];
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFlatThreads, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) {
         cudaGetLastError();
         nb = 0;
     }
@@ -302,9 +322,12 @@ int flat_blocks_per_sm(K kernel, int smem, int smem_optin) {
 
 // returns 0 and fills *fp when the flat path can take the problem, 1 when it cannot, < 0 / > 0 codes on error
 // NS = streams of a ring A slot (and, in L2, of a piece between its two touches); NSB = streams of a ring B slot
-template <typename KernelT>
+template <typename TR, typename KernelT>
 int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, long long slab_bytes, const DeviceInfo& d,
-              FlatPlan* fp) {
+              FlatPlan<TR>* fp) {
+    constexpr int kFlatCtasPerSm = TR::kCtasPerSm, kFlatMaxSlots = TR::kMaxSlots, kFlatMinPieceVecs = TR::kMinPieceVecs,
+                  kFlatMaxPieces = TR::kMaxPieces, kFlatMaxLag = TR::kMaxLag, kFlatConsumerThreads = TR::kConsumerThreads;
+    auto flat_ctl_bytes = [] { return (long long)TR::kCtlBytes; };
     long long G = (long long)d.sm_count * kFlatCtasPerSm;
     const long long gcap = g_opt.flat_grid.load();
     if (gcap > 0 && gcap * kFlatCtasPerSm < G) G = gcap * kFlatCtasPerSm;
@@ -334,7 +357,7 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     if (pvmax < kFlatMinPieceVecs) return 1;
     const long long slot_vecs = (pvmax + 7) & ~7LL;
     const int smem = (int)((KA * NS + KB * NSB) * slot_vecs * 16 + flat_ctl_bytes());
-    if (flat_blocks_per_sm(kernel, smem, d.smem_optin) < kFlatCtasPerSm) return 1;
+    if (flat_blocks_per_sm(kernel, TR::kThreads, smem, d.smem_optin) < kFlatCtasPerSm) return 1;
 
     // a slab of P pieces spans R = ceil((P-1)/G)+1 rounds; P2 trails P1 by L >= R steps (L <= kFlatMaxLag)
     const long long pmax_hw = std::min<long long>(kFlatMaxPieces, (long long)(kFlatMaxLag - 1) * G + 1);
@@ -400,11 +423,11 @@ int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, lon
     return 0;
 }
 
-template <typename K, typename P>
-int launch_flat(K kernel, const P& p, const FlatPlan& fp, cudaStream_t st) {
+template <typename TR, typename K, typename P>
+int launch_flat(K kernel, const P& p, const FlatPlan<TR>& fp, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)fp.grid);
-    cfg.blockDim = dim3(kFlatThreads);
+    cfg.blockDim = dim3(TR::kThreads);
     cfg.dynamicSmemBytes = fp.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -412,17 +435,40 @@ int launch_flat(K kernel, const P& p, const FlatPlan& fp, cudaStream_t st) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_opt.flat_coop.load() == 0 ? 0 : 1;
-    FlatGeom g = fp.g;
+    typename TR::Geom g = fp.g;
     return (int)cudaLaunchKernelEx(&cfg, kernel, p, g);
 }
 
-void record_flat(const FlatPlan& fp) {
+template <typename TR>
+void record_flat(const FlatPlan<TR>& fp) {
     g_opt.last_path.store(2);
     g_opt.last_cs.store(fp.g.P);
     g_opt.last_slots.store(fp.g.KA);
     g_opt.last_lag.store(fp.g.L);
     g_opt.last_grid.store(fp.grid);
     g_opt.launches.fetch_add(1);
+}
+
+// plan + launch of one flat kernel; kFlatNotTaken when the flat path declines (the caller tries the next path)
+constexpr int kFlatNotTaken = -1000;
+template <typename TR, typename KernelT, typename P>
+int flat_run(KernelT kernel, int NS, int NSB, const P& p, long long slabs, long long slab_bytes, const FlatWs* ws_flat,
+             const DeviceInfo& d, cudaStream_t st, int trace_mute) {
+    FlatPlan<TR> fpl = {};
+    const int rc = plan_flat<TR>(kernel, NS, NSB, slabs, p.C, slab_bytes, d, &fpl);
+    if (rc == 1) return kFlatNotTaken;
+    if (rc) return rc;
+    if (g_opt.flat_trace_which.load() == trace_mute) fpl.g.trace = nullptr;
+    fpl.g.ws_piece = ws_flat->piece;
+    fpl.g.ws_slab = ws_flat->slab;
+    fpl.g.ws_ctl = ws_flat->ctl;
+    record_flat(fpl);
+    const int lrc = launch_flat<TR>(kernel, p, fpl, st);
+    // a device that cannot hold the whole persistent grid right now (MPS share, another resident kernel) refuses
+    // the cooperative launch: take the cluster / small path instead of failing the call
+    if (lrc != (int)cudaErrorCooperativeLaunchTooLarge) return lrc;
+    cudaGetLastError();
+    return kFlatNotTaken;
 }
 
 long long flat_min_bytes() {
@@ -440,23 +486,15 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (fp == 0) use_cluster = false;
     if (fp == 1 && can_cluster) use_cluster = true;
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
-        auto kernel = micn_fwd_flat_kernel<T, EPI>;
-        FlatPlan fpl = {};
-        const int rc = plan_flat(kernel, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, p.C, slab_bytes, d, &fpl);
-        if (rc == 0) {
-            if (g_opt.flat_trace_which.load() == 2) fpl.g.trace = nullptr;
-            fpl.g.ws_piece = ws_flat->piece;
-            fpl.g.ws_slab = ws_flat->slab;
-            fpl.g.ws_ctl = ws_flat->ctl;
-            record_flat(fpl);
-            const int lrc = launch_flat(kernel, p, fpl, st);
-            // a device that cannot hold the whole persistent grid right now (MPS share, another resident kernel)
-            // refuses the cooperative launch: take the cluster / small path instead of failing the call
-            if (lrc != (int)cudaErrorCooperativeLaunchTooLarge) return lrc;
-            cudaGetLastError();
-        } else if (rc != 1) {
-            return rc;
-        }
+        // 16-bit I/O: two half-size CTAs per SM hide each other's per-piece latency chains; fp32: one CTA per SM
+        int frc;
+        if constexpr (sizeof(T) == 2)
+            frc = flat_run<flat2::Traits>(flat2::micn_fwd_flat_kernel<T, EPI>, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, p, slabs,
+                                          slab_bytes, ws_flat, d, st, 2);
+        else
+            frc = flat_run<flat1::Traits>(flat1::micn_fwd_flat_kernel<T, EPI>, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, p, slabs,
+                                          slab_bytes, ws_flat, d, st, 2);
+        if (frc != kFlatNotTaken) return frc;
     }
     if (use_cluster) {
         auto kernel = micn_fwd_cluster_kernel<T, EPI>;
@@ -496,21 +534,9 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     const bool ds = EPI == MICN_EPI_LRELU && p.dslope != nullptr;
     if (ds) use_cluster = false;  // the slope-gradient partials are produced by the flat and small kernels only
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
-        auto kernel = ds ? micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : micn_bwd_flat_kernel<T, EPI, false>;
-        FlatPlan fpl = {};
-        const int rc = plan_flat(kernel, NS, NS, slabs, p.C, slab_bytes, d, &fpl);
-        if (rc == 0) {
-            if (g_opt.flat_trace_which.load() == 1) fpl.g.trace = nullptr;
-            fpl.g.ws_piece = ws_flat->piece;
-            fpl.g.ws_slab = ws_flat->slab;
-            fpl.g.ws_ctl = ws_flat->ctl;
-            record_flat(fpl);
-            const int lrc = launch_flat(kernel, p, fpl, st);
-            if (lrc != (int)cudaErrorCooperativeLaunchTooLarge) return lrc;  // see fwd_typed
-            cudaGetLastError();
-        } else if (rc != 1) {
-            return rc;
-        }
+        auto kernel = ds ? flat1::micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : flat1::micn_bwd_flat_kernel<T, EPI, false>;
+        const int frc = flat_run<flat1::Traits>(kernel, NS, NS, p, slabs, slab_bytes, ws_flat, d, st, 1);
+        if (frc != kFlatNotTaken) return frc;
     }
     if (use_cluster) {
         auto kernel = micn_bwd_cluster_kernel<T, EPI>;

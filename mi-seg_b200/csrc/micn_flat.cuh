@@ -51,11 +51,16 @@
 //
 // Reference semantics: networks/norms/conditional_instance_norm.py:59-60 (+ ATen instance_norm:
 // biased variance, eps inside the sqrt), epilogues networks/blocks/dynunet_block.py:107-125.
-#pragma once
-
+// This header is included once per CTA SHAPE (micn_api.cu): MICN_FLAT_NS names the sub-namespace, MICN_FLAT_CW /
+// MICN_FLAT_GW / MICN_FLAT_CPS the consumer warps, gather warps and persistent CTAs per SM of that shape.
 #include "micn_common.cuh"
 
+#ifndef MICN_FLAT_NS
+#define MICN_FLAT_NS flat1
+#endif
+
 namespace micn {
+namespace MICN_FLAT_NS {
 
 #ifndef MICN_FLAT_CW
 #define MICN_FLAT_CW 16  // consumer warps per CTA
@@ -846,4 +851,13 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
     }
 }
 
+// what the host-side planner needs to know about this shape
+struct Traits {
+    using Geom = FlatGeom;
+    static constexpr int kThreads = kFlatThreads, kCtasPerSm = kFlatCtasPerSm, kConsumerThreads = kFlatConsumerThreads,
+                         kMaxSlots = kFlatMaxSlots, kMaxLag = kFlatMaxLag, kMaxPieces = kFlatMaxPieces,
+                         kMinPieceVecs = kFlatMinPieceVecs, kCtlBytes = flat_ctl_bytes();
+};
+
+}  // namespace MICN_FLAT_NS
 }  // namespace micn
