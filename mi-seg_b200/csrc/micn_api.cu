@@ -54,6 +54,7 @@ struct Options {
     std::atomic<long long> flat_slots_b{-1};  // ring B slots (second touch, L2)
     std::atomic<long long> flat_lag{-1};      // steps P2 trails P1
     std::atomic<long long> flat_l2_mb{-1};    // L2 budget (MB) the lag is sized for
+    std::atomic<long long> flat_shape_fwd{-1}, flat_shape_bwd{-1};  // experiments: force CTA shape 1 / 2
     std::atomic<long long> flat_poll_delay_ns{-1}, flat_poll_backoff_ns{-1}, flat_poll_delay_tail_ns{-1};
     std::atomic<long long> flat_piece_vecs{-1};  // cap on vectors per piece
     std::atomic<long long> flat_min_bytes{-1};   // smallest slab the flat path takes
@@ -85,7 +86,7 @@ const OptName kOptNames[] = {
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
     {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace},
     {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
-    {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
+    {"flat_shape_fwd", &g_opt.flat_shape_fwd}, {"flat_shape_bwd", &g_opt.flat_shape_bwd}, {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
 
 // ------------------------------------------------------------------------------------------ device
@@ -487,8 +488,9 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (fp == 1 && can_cluster) use_cluster = true;
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         // 16-bit I/O: two half-size CTAs per SM hide each other's per-piece latency chains; fp32: one CTA per SM
+        const long long shape = g_opt.flat_shape_fwd.load();
         int frc;
-        if constexpr (sizeof(T) == 2)
+        if (shape == 2 || (shape != 1 && sizeof(T) == 2))
             frc = flat_run<flat2::Traits>(flat2::micn_fwd_flat_kernel<T, EPI>, 1, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, p, slabs,
                                           slab_bytes, ws_flat, d, st, 2);
         else
@@ -534,8 +536,14 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     const bool ds = EPI == MICN_EPI_LRELU && p.dslope != nullptr;
     if (ds) use_cluster = false;  // the slope-gradient partials are produced by the flat and small kernels only
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
-        auto kernel = ds ? flat1::micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : flat1::micn_bwd_flat_kernel<T, EPI, false>;
-        const int frc = flat_run<flat1::Traits>(kernel, NS, NS, p, slabs, slab_bytes, ws_flat, d, st, 1);
+        int frc;
+        if (g_opt.flat_shape_bwd.load() == 2) {
+            auto kernel = ds ? flat2::micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : flat2::micn_bwd_flat_kernel<T, EPI, false>;
+            frc = flat_run<flat2::Traits>(kernel, NS, NS, p, slabs, slab_bytes, ws_flat, d, st, 1);
+        } else {
+            auto kernel = ds ? flat1::micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : flat1::micn_bwd_flat_kernel<T, EPI, false>;
+            frc = flat_run<flat1::Traits>(kernel, NS, NS, p, slabs, slab_bytes, ws_flat, d, st, 1);
+        }
         if (frc != kFlatNotTaken) return frc;
     }
     if (use_cluster) {
