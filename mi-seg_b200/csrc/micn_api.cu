@@ -12,9 +12,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -67,6 +69,10 @@ struct Options {
     std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
     std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
     std::atomic<long long> last_path{-1}, last_cs{-1}, last_slots{-1}, last_grid{-1}, last_lag{-1};  // read-back of the last plan
+    std::atomic<long long> host_groups{-1};   // channel groups of the host-buffer path (default 10)
+    std::atomic<long long> host_trace{0};     // 1: print a per-group timeline of the host-buffer path to stderr
+    std::atomic<long long> host_taper{-1};    // 0: equal channel groups, else small groups at both ends (short fill and drain)
+    std::atomic<long long> host_copy_2d{-1};  // 1: always 2-D copies (experiments)
     std::atomic<long long> launches{0};       // kernels launched by this library (bench "gpu_launches")
     std::atomic<long long> sm_bw_mbps{90000};   // per-SM bandwidth cap used by the planner (MB/s)
     std::atomic<long long> hbm_bw_mbps{6500000};
@@ -81,7 +87,7 @@ const OptName kOptNames[] = {
     {"cluster_size", &g_opt.cluster_size}, {"force_path", &g_opt.force_path}, {"slots", &g_opt.slots},
     {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps},   {"last_path", &g_opt.last_path},
     {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid}, {"last_lag", &g_opt.last_lag},
-    {"launches", &g_opt.launches},         {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
+    {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
     {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace},
@@ -122,7 +128,7 @@ struct KernelState {
     int smem_set;
     int occ[16];  // co-resident clusters for CS = 1..16 at smem_set bytes (-1 unknown)
 };
-std::vector<KernelState> g_kstate;
+std::deque<KernelState> g_kstate;  // a deque: entries never move, callers keep pointers to them
 
 int cs_index(int cs) { return cs - 1; }
 
@@ -141,7 +147,6 @@ int kernel_prepare(K kernel, int smem, int smem_optin, KernelState** out) {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return (int)e;
-    g_kstate.reserve(256);  // pointers into the vector stay valid below this many entries
     KernelState ks_new{fn, dev, smem, {}};
     for (int& o : ks_new.occ) o = -1;
     g_kstate.push_back(ks_new);
@@ -152,6 +157,7 @@ int kernel_prepare(K kernel, int smem, int smem_optin, KernelState** out) {
 template <typename K>
 int cluster_occupancy(K kernel, KernelState* ks, int cs, int smem) {
     const int ci = cs_index(cs);
+    std::lock_guard<std::mutex> lk(g_mu);
     if (ks->occ[ci] >= 0) return ks->occ[ci];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs * 64);
@@ -311,6 +317,7 @@ template <typename K>
 int flat_blocks_per_sm(K kernel, int threads, int smem, int smem_optin) {
     KernelState* ks = nullptr;
     if (kernel_prepare(kernel, smem, smem_optin, &ks)) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
     if (ks->occ[0] >= 0) return ks->occ[0];
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) {
@@ -809,6 +816,9 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
     const int es = elem_size(dtype);
     if (!es) return MICN_ERR_BAD_DTYPE;
     if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if ((dgamma == nullptr) != (dbeta == nullptr)) return MICN_ERR_BAD_ARG;
     if (N == 0 || C == 0 || M == 0) {
         if (dgamma && C > 0) {
             cudaStream_t st = (cudaStream_t)stream;
@@ -964,6 +974,8 @@ int micn_bwd_cl(const void* dy, const void* x, const float* const* gamma, const 
     if (!es) return MICN_ERR_BAD_DTYPE;
     if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
     if ((dgamma == nullptr) != (dbeta == nullptr)) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
     if (N == 0 || C == 0 || M == 0) {
         if (dgamma && C > 0) {
             cudaMemsetAsync(dgamma, 0, sizeof(float) * num_styles * C, (cudaStream_t)stream);
@@ -1005,15 +1017,59 @@ int micn_bwd_cl(const void* dy, const void* x, const float* const* gamma, const 
 // ------------------------------------------------------------------------------------------ host-buffer path
 namespace {
 constexpr int kHostStreams = 3;
-cudaStream_t g_hs[kHostStreams] = {nullptr, nullptr, nullptr};
-std::vector<cudaEvent_t> g_hev;  // per-group hand-off events of the host path (created once, reused)
+struct HostState {  // per device: role streams and per-group hand-off events, created once and reused
+    cudaStream_t hs[kHostStreams] = {};
+    std::vector<cudaEvent_t> hev;
+};
+HostState g_host[64];
 std::mutex g_host_mu;
 
 inline size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-int host_groups(int64_t C) {
-    int g = C >= 12 ? 12 : (int)C;
-    return g < 1 ? 1 : g;
+// Channel-group boundaries b[0..G] of the host-buffer path.  Tapered: groups weighted 1,2,3,4,...,4,3,2,1 so the
+// first upload (nothing to overlap it with) and the last download are short.
+int host_bounds(int64_t C, std::vector<int64_t>* b) {
+    long long want = g_opt.host_groups.load();
+    if (want <= 0) want = 10;  // measured at 1x48x96^3 bf16: 6..12 groups within 3 %, 24 and more clearly slower
+    int G = (int)std::min<long long>(want, C);
+    if (G < 1) G = 1;
+    b->assign(1, 0);
+    if (g_opt.host_taper.load() == 0 || G < 4) {
+        const int64_t cg = (C + G - 1) / G;
+        for (int64_t c = cg; c < C; c += cg) b->push_back(c);
+    } else {
+        auto wt = [&](int g) { return std::min(std::min(g + 1, G - g), 4); };
+        long long wsum = 0, acc = 0;
+        for (int g = 0; g < G; ++g) wsum += wt(g);
+        for (int g = 0; g + 1 < G; ++g) {
+            acc += wt(g);
+            int64_t c = (C * acc + wsum / 2) / wsum;
+            c = std::max<int64_t>(c, b->back() + 1);          // at least one channel per group
+            c = std::min<int64_t>(c, C - (G - 1 - g));        // ... and for every group still to come
+            b->push_back(c);
+        }
+    }
+    b->push_back(C);
+    return (int)b->size() - 1;
+}
+
+int64_t host_max_group(const std::vector<int64_t>& b) {
+    int64_t m = 1;
+    for (size_t g = 0; g + 1 < b.size(); ++g) m = std::max(m, b[g + 1] - b[g]);
+    return m;
+}
+
+// [N rows of `width` bytes] between a pitched host tensor and a dense device block.  Few rows: one plain copy per
+// row (a 1-D copy runs at the full PCIe rate; the pitched 2-D form is for many short rows).
+cudaError_t host_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int64_t rows,
+                      cudaMemcpyKind kind, cudaStream_t st) {
+    if (rows > 8 || g_opt.host_copy_2d.load() == 1) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+    for (int64_t r = 0; r < rows; ++r) {
+        cudaError_t e = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + r * dpitch,
+                                        static_cast<const unsigned char*>(src) + r * spitch, width, kind, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 }  // namespace
 
@@ -1021,13 +1077,14 @@ size_t micn_host_scratch_bytes(int64_t N, int64_t C, int64_t M, int dtype, int n
     const int es = elem_size(dtype);
     if (!es || N <= 0 || C <= 0 || M <= 0 || num_styles < 1) return 0;
     const size_t E = (size_t)N * C * M * es;
-    const int G = host_groups(C);
+    std::vector<int64_t> cb;
+    const int G = host_bounds(C, &cb);
     size_t b = 0;
     b += up256(E) * (with_backward ? 4 : 2);                        // x, y [, dy, dx]
     b += up256((size_t)N * C * 4) * 2;                              // mean, rstd
     b += up256((size_t)num_styles * C * 4) * 4;                     // gamma, beta, dgamma, dbeta
     b += up256((size_t)N * 8);                                      // styles
-    b += (size_t)G * micn_workspace_bytes(N, (C + G - 1) / G + 1, M, dtype, num_styles);
+    b += (size_t)G * micn_workspace_bytes(N, host_max_group(cb), M, dtype, num_styles);
     return b + 4096;
 }
 
@@ -1048,8 +1105,13 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
 
     std::lock_guard<std::mutex> lk(g_host_mu);
     cudaError_t e;
+    int dev = -1;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return MICN_ERR_NO_DEVICE;
+    cudaStream_t* hs = g_host[dev].hs;
+    std::vector<cudaEvent_t>& hev = g_host[dev].hev;
     for (int i = 0; i < kHostStreams; ++i)
-        if (!g_hs[i] && (e = cudaStreamCreateWithFlags(&g_hs[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if (!hs[i] && (e = cudaStreamCreateWithFlags(&hs[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
 
     // carve the scratch
     unsigned char* w = reinterpret_cast<unsigned char*>(dev_scratch);
@@ -1071,15 +1133,15 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
     float* dgd = reinterpret_cast<float*>(take(SCb));
     float* dbd = reinterpret_cast<float*>(take(SCb));
     int64_t* sd = reinterpret_cast<int64_t*>(take((size_t)N * 8));
-    const int G = host_groups(C);
-    const int64_t cg = (C + G - 1) / G;
-    const size_t ws_each = micn_workspace_bytes(N, cg + 1, M, dtype, num_styles);
+    std::vector<int64_t> cb;
+    const int G = host_bounds(C, &cb);
+    const size_t ws_each = micn_workspace_bytes(N, host_max_group(cb), M, dtype, num_styles);
     unsigned char* ws0 = take((size_t)G * ws_each);
 
     // Three role streams: uploads (H2D), kernels, downloads (D2H).  The upload engine never idles (x and dy of
     // group g, then group g+1, ...), the kernels of group g start as soon as its x has landed, and the download of
     // y / dx trails the kernels: PCIe runs full duplex for the whole call.
-    cudaStream_t s_up = g_hs[0], s_comp = g_hs[1], s_down = g_hs[2];
+    cudaStream_t s_up = hs[0], s_comp = hs[1], s_down = hs[2];
     const bool affine = gamma_host != nullptr;
     if (affine) {
         if ((e = cudaMemcpyAsync(gd, gamma_host, SCb, cudaMemcpyHostToDevice, s_comp)) != cudaSuccess) return (int)e;
@@ -1089,11 +1151,25 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
         return (int)e;
     if ((e = cudaMemsetAsync(ws0, 0, (size_t)G * ws_each, s_comp)) != cudaSuccess) return (int)e;
     const size_t need_ev = (size_t)G * 4;
-    while (g_hev.size() < need_ev) {
+    while (hev.size() < need_ev) {
         cudaEvent_t ev;
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-        g_hev.push_back(ev);
+        hev.push_back(ev);
     }
+
+    // bring-up aid: timestamps after every stage of every group (host_trace = 1)
+    const bool trace = g_opt.host_trace.load() == 1;
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, s);
+        tev.push_back(ev);
+    };
+    stamp(s_up);
+    const auto host_t0 = std::chrono::steady_clock::now();
+    double host_queued_us = 0.0;
 
     // channel groups: sub-tensors [N, cg, M] staged densely on the device, 2-D copies on the host side
     int rc = 0;
@@ -1101,28 +1177,29 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
     std::vector<const float*> gp(num_styles), bp(num_styles);
     size_t dev_off = 0;  // dense sub-tensors are packed one after the other
     for (int g = 0; g < G && !rc; ++g) {
-        const int64_t c0 = g * cg, c1 = std::min<int64_t>(C, c0 + cg);
-        if (c0 >= c1) break;
+        const int64_t c0 = cb[g], c1 = cb[g + 1];
         const int64_t cc = c1 - c0;
-        cudaEvent_t ev_x = g_hev[4 * g], ev_dy = g_hev[4 * g + 1], ev_y = g_hev[4 * g + 2], ev_dx = g_hev[4 * g + 3];
+        cudaEvent_t ev_x = hev[4 * g], ev_dy = hev[4 * g + 1], ev_y = hev[4 * g + 2], ev_dx = hev[4 * g + 3];
         const size_t width = (size_t)cc * M * es;
         const size_t sub = (size_t)N * width;
         const unsigned char* xh = reinterpret_cast<const unsigned char*>(x_host) + (size_t)c0 * M * es;
         unsigned char* yh = reinterpret_cast<unsigned char*>(y_host) + (size_t)c0 * M * es;
         // ---- uploads
-        if ((e = cudaMemcpy2DAsync(xd + dev_off, width, xh, row_pitch, width, N, cudaMemcpyHostToDevice, s_up)) != cudaSuccess) {
+        if ((e = host_copy(xd + dev_off, width, xh, row_pitch, width, N, cudaMemcpyHostToDevice, s_up)) != cudaSuccess) {
             rc = (int)e;
             break;
         }
         cudaEventRecord(ev_x, s_up);
+        stamp(s_up);
         if (bwd) {
             const unsigned char* dyh = reinterpret_cast<const unsigned char*>(dy_host) + (size_t)c0 * M * es;
-            if ((e = cudaMemcpy2DAsync(dyd + dev_off, width, dyh, row_pitch, width, N, cudaMemcpyHostToDevice, s_up)) !=
+            if ((e = host_copy(dyd + dev_off, width, dyh, row_pitch, width, N, cudaMemcpyHostToDevice, s_up)) !=
                 cudaSuccess) {
                 rc = (int)e;
                 break;
             }
             cudaEventRecord(ev_dy, s_up);
+            stamp(s_up);
         }
         // ---- kernels
         for (int s = 0; s < num_styles; ++s) {
@@ -1138,6 +1215,7 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
                       ws, ws_each, s_comp);
         if (rc) break;
         cudaEventRecord(ev_y, s_comp);
+        stamp(s_comp);
         if (bwd) {
             // group-dense [S, cc] gradient blocks, scattered into [S, C] on the host afterwards
             float* gdg = dgamma_host ? dgd + (size_t)num_styles * c0 : nullptr;
@@ -1148,35 +1226,37 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
                           cc * M, M, dtype, epilogue, slope, ws, ws_each, s_comp);
             if (rc) break;
             cudaEventRecord(ev_dx, s_comp);
+            stamp(s_comp);
         }
         // ---- downloads
         cudaStreamWaitEvent(s_down, ev_y, 0);
-        if ((e = cudaMemcpy2DAsync(yh, row_pitch, yd + dev_off, width, width, N, cudaMemcpyDeviceToHost, s_down)) != cudaSuccess) {
+        if ((e = host_copy(yh, row_pitch, yd + dev_off, width, width, N, cudaMemcpyDeviceToHost, s_down)) != cudaSuccess) {
             rc = (int)e;
             break;
         }
+        stamp(s_down);
         if (bwd) {
             unsigned char* dxh = reinterpret_cast<unsigned char*>(dx_host) + (size_t)c0 * M * es;
             cudaStreamWaitEvent(s_down, ev_dx, 0);
-            if ((e = cudaMemcpy2DAsync(dxh, row_pitch, dxd + dev_off, width, width, N, cudaMemcpyDeviceToHost, s_down)) !=
+            if ((e = host_copy(dxh, row_pitch, dxd + dev_off, width, width, N, cudaMemcpyDeviceToHost, s_down)) !=
                 cudaSuccess) {
                 rc = (int)e;
                 break;
             }
+            stamp(s_down);
         }
         dev_off += sub;  // dense packing: the groups tile [0, E) exactly
     }
+    if (trace) host_queued_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
     std::vector<float> tg, tb;
     if (!rc && bwd && dgamma_host) {
         tg.resize((size_t)num_styles * C);
         tb.resize((size_t)num_styles * C);
-        for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(g_hs[i]);
+        for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(hs[i]);
         if ((e = cudaMemcpy(tg.data(), dgd, SCb, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = (int)e;
         if (!rc && (e = cudaMemcpy(tb.data(), dbd, SCb, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = (int)e;
         for (int g = 0; g < G && !rc; ++g) {
-            const int64_t c0 = g * cg, c1 = std::min<int64_t>(C, c0 + cg);
-            if (c0 >= c1) break;
-            const int64_t cc = c1 - c0;
+            const int64_t c0 = cb[g], cc = cb[g + 1] - cb[g];
             for (int s = 0; s < num_styles; ++s)
                 for (int64_t c = 0; c < cc; ++c) {
                     dgamma_host[(size_t)s * C + c0 + c] = tg[(size_t)num_styles * c0 + (size_t)s * cc + c];
@@ -1185,9 +1265,22 @@ int micn_fwd_bwd_host(const void* x_host, const void* dy_host, void* y_host, voi
         }
     }
     for (int i = 0; i < kHostStreams; ++i) {
-        e = cudaStreamSynchronize(g_hs[i]);
+        e = cudaStreamSynchronize(hs[i]);
         if (e != cudaSuccess && !rc) rc = (int)e;
     }
+    if (trace && !rc && bwd && tev.size() == 1 + 6 * (size_t)G) {
+        std::fprintf(stderr, "micn host timeline (us after the first upload was queued; the host had queued everything after %.0f us): group x_up dy_up fwd bwd y_down dx_down\n", host_queued_us);
+        for (int g = 0; g < G; ++g) {
+            std::fprintf(stderr, "  %2d", g);
+            for (int k = 0; k < 6; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, tev[0], tev[1 + 6 * g + k]);
+                std::fprintf(stderr, " %8.1f", ms * 1e3f);
+            }
+            std::fprintf(stderr, "\n");
+        }
+    }
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
     return rc;
 }
 
