@@ -81,7 +81,9 @@ class FastForwardMixin:
     class for `_check_input_dim`, `_check_input_styles`, `_get_no_batch_dim`, `norms`, `num_styles`."""
 
     def _params(self) -> Tuple[List[Tensor], List[Tensor]]:
-        return [n.weight for n in self.norms], [n.bias for n in self.norms]
+        # (straight from the registries: nn.Module.__getattr__ costs ~0.5 us per lookup, four to six per call here)
+        mods = self._modules["norms"]._modules.values()
+        return [n._parameters["weight"] for n in mods], [n._parameters["bias"] for n in mods]
 
     def forward(self, input: Tensor, styles: Union[List, Tensor, int]) -> Tensor:
         """y = IN_{styles[n]}(input[n]) for every sample: the reference's forward (:62-68)."""
