@@ -160,7 +160,8 @@ SWIN_UNETR_CALLS = (  # the 31 instance_cond calls of one C-Swi
 
 def run_model_calls(pkg, dev, tdt, reps=20):
     """The hot path at model scale: every instance_cond call of one C-Swin-UNETR training step (forward + backward),
-    timed as one sequence three ways: (1) raw C-ABI launches back to back (what the GPU needs), (2) through the
+    timed as one sequence four ways: (1) raw C-ABI launches back to back from Python (host-bound for the small calls),
+    (1b) the same launches replayed from a CUDA graph (what the GPU needs), (2) through the
     drop-in nn.Module + autograd (what a training script calls; ~250 us of Python / autograd-engine time per call,
     which a real step hides behind its convolutions), (3) the reference's call sequence (per-sample F.instance_norm
     + torch.stack) through PyTorch/ATen on the same GPU.  PatchMerging inputs arrive channels-last (stride_C = 1)."""
@@ -205,7 +206,7 @@ def run_model_calls(pkg, dev, tdt, reps=20):
             torch.stack([F.instance_norm(x[i].unsqueeze(0), None, None, w, b, True, 0.1, 1e-5).squeeze(0)
                          for i in range(x.shape[0])]).backward(dy)
 
-    def ours_cabi():
+    def ours_cabi(stream=stream):
         for r in raw:
             c, m = r["c"], r["m"]
             if r["chlast"]:  # token-major input: the channels-last kernels, no transposing copy
@@ -229,8 +230,20 @@ def run_model_calls(pkg, dev, tdt, reps=20):
             if rc:
                 raise RuntimeError(f"model call list: rc={rc}")
 
+    # the same 62 launches captured once into a CUDA graph and replayed (the calls keep no per-launch state on the
+    # host, micn.h): what the GPU needs when the host is out of the way
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ours_cabi(side.cuda_stream)  # (first launches outside the capture: function attributes are set once)
+        with torch.cuda.graph(graph, stream=side):
+            ours_cabi(side.cuda_stream)
+    torch.cuda.current_stream().wait_stream(side)
+
     out = {}
-    for key, fn in (("ours_cabi_ms", ours_cabi), ("ours_module_ms", ours_module), ("torch_module_ms", torch_module)):
+    for key, fn in (("ours_cabi_ms", ours_cabi), ("ours_cabi_graph_ms", graph.replay), ("ours_module_ms", ours_module),
+                    ("torch_module_ms", torch_module)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -244,6 +257,7 @@ def run_model_calls(pkg, dev, tdt, reps=20):
     es = torch.empty(0, dtype=tdt).element_size()
     out.update({"calls": len(calls), "elements_per_forward": elems, "algorithmic_bytes": 5 * elems * es,
                 "ours_cabi_gbps": 5 * elems * es / (out["ours_cabi_ms"] * 1e-3) / 1e9,
+                "ours_cabi_graph_gbps": 5 * elems * es / (out["ours_cabi_graph_ms"] * 1e-3) / 1e9,
                 "patch_voxels_per_s_norm_only": 96 ** 3 / (out["ours_cabi_ms"] * 1e-3),
                 "speedup_vs_torch_gpu_module_level": out["torch_module_ms"] / out["ours_module_ms"],
                 "speedup_vs_torch_gpu_device_level": out["torch_module_ms"] / out["ours_cabi_ms"],

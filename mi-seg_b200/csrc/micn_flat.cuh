@@ -131,8 +131,8 @@ __device__ __forceinline__ void flat_trace(const FlatGeom& g, unsigned j, int ev
 // All of this happens off the critical path, during the first piece's load; nothing is added at kernel end.
 __device__ __forceinline__ unsigned flat_epoch_tag(const FlatGeom& g) {
     const unsigned e0 = *reinterpret_cast<const volatile unsigned*>(g.ws_ctl);
-    // the data dependency on e0 orders the read before the arrival
-    if (atomicAdd(g.ws_ctl + 1, 1u + (e0 & 0u)) == gridDim.x - 1) {
+    __threadfence();  // the read of e0 is performed before the arrival below can be observed (one lane, off the critical path)
+    if (atomicAdd(g.ws_ctl + 1, 1u) == gridDim.x - 1) {
         g.ws_ctl[1] = 0u;
         __threadfence();
         atomicAdd(g.ws_ctl, 1u);

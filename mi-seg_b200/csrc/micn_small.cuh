@@ -130,7 +130,18 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_fwd_small_kernel(co
     for (long long i = t; i < pl.head; i += TPS) acc(V::load1(xs + i));
     {
         const uint4* xv = reinterpret_cast<const uint4*>(xs + pl.head);
-        for (long long i = t; i < pl.nvec; i += TPS) {
+        long long i = t;
+        for (; i + TPS < pl.nvec; i += 2 * TPS) {  // two loads in flight per thread
+            const uint4 q0 = __ldg(xv + i), q1 = __ldg(xv + i + TPS);
+            float f[VN];
+            V::unpack(q0, f);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc(f[e]);
+            V::unpack(q1, f);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc(f[e]);
+        }
+        if (i < pl.nvec) {
             float f[VN];
             V::unpack(__ldg(xv + i), f);
 #pragma unroll
@@ -246,9 +257,17 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
             if (t == 0) p.dslope[slab] = s3;
         }
         if (t == 0 && p.dgamma) {
-            p.ws_sum_dy[slab] = s1;
-            p.ws_sum_dyxh[slab] = s2;
-            __threadfence();
+            if (p.N == 1) {
+                // one sample: this slab's sums ARE the gradients of its style's row (no cross-CTA fold, no tail)
+                for (int s = 0; s < p.num_styles; ++s) {
+                    p.dbeta[(long long)s * p.C + ch] = s == style ? s1 : 0.f;
+                    p.dgamma[(long long)s * p.C + ch] = s == style ? s2 : 0.f;
+                }
+            } else {
+                p.ws_sum_dy[slab] = s1;
+                p.ws_sum_dyxh[slab] = s2;
+                __threadfence();
+            }
         }
         const float invM = 1.f / (float)p.M;
         const float B0 = -a * s1 * invM;
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
     }
 
     // ---- per-style parameter gradients by the last CTA (fixed order, deterministic)
-    if (p.dgamma) {
+    if (p.dgamma && p.N > 1) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();

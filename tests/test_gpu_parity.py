@@ -641,3 +641,58 @@ def test_prelu_epilogue_vs_oracle(pkg, shape, dtype):
     act2 = torch.nn.PReLU(init=0.25).cuda().to(dtype)  # torch's own PReLU wants the weight in the I/O dtype
     y2 = act2(mod(x2, styles))
     assert float((y2.float() - y.float()).abs().max()) <= (1e-5 if dtype == torch.float32 else 4e-2)
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer entry point
+HOST_CASES = [
+    ((1, 48, 16 * 16 * 16), "bf16", 1, "one_sample_tapered_groups"),   # the bench layout in small: 10 channel groups
+    ((3, 5, 7 * 9 * 11), "fp32", 0, "odd_lengths_fewer_channels_than_groups"),
+    ((9, 4, 1024), "fp16", 1, "many_rows_pitched_copies"),              # N > 8: the 2-D copy branch
+    ((2, 13, 4096), "fp32", 0, "forward_only"),
+]
+
+
+@pytest.mark.parametrize("shape,dt,epi,name", HOST_CASES, ids=[c[3] for c in HOST_CASES])
+def test_host_buffer_call_vs_oracle(pkg, shape, dt, epi, name):
+    """micn_fwd_bwd_host: host tensors in, host tensors out (what bench.py's `e2e` times), against the oracle."""
+    lib = pkg._lib.lib()
+    n, c, m = shape
+    S = 3
+    tdt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[dt]
+    code = {"fp32": 0, "bf16": 1, "fp16": 2}[dt]
+    gen = torch.Generator().manual_seed(7)
+    x = (torch.randn(n, c, m, generator=gen) * 2 + 1).to(tdt).pin_memory()
+    dy = torch.randn(n, c, m, generator=gen).to(tdt).pin_memory()
+    y, dx = torch.empty_like(x).pin_memory(), torch.empty_like(x).pin_memory()
+    gam = (1 + 0.3 * torch.randn(S, c, generator=gen)).contiguous()
+    bet = (0.3 * torch.randn(S, c, generator=gen)).contiguous()
+    styles = [(2 * i + 1) % S for i in range(n)]
+    st = torch.tensor(styles, dtype=torch.int64)
+    dg, db = torch.full((S, c), 9.0), torch.full((S, c), 9.0)
+    bwd = name != "forward_only"
+    nb = lib.micn_host_scratch_bytes(n, c, m, code, S, 1 if bwd else 0)
+    assert nb > 0
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    for _ in range(2):  # the second call reuses the scratch and the cached streams / events
+        rc = lib.micn_fwd_bwd_host(x.data_ptr(), dy.data_ptr() if bwd else None, y.data_ptr(), dx.data_ptr() if bwd else None,
+                                   gam.data_ptr(), bet.data_ptr(), S, st.data_ptr(), dg.data_ptr() if bwd else None,
+                                   db.data_ptr() if bwd else None, n, c, m, code, epi, 0.01, 1e-5, scratch.data_ptr(), nb)
+        assert rc == 0, pkg._lib.lib().micn_error_string(rc)
+    xn, dyn = x.float().numpy(), dy.float().numpy()
+    tol = TOL[tdt]
+    if epi == 0:
+        yr, m_, r_ = O.fwd_f64(xn, styles, gam.numpy(), bet.numpy())
+        assert rel_err(y.float().numpy(), yr) < tol
+        if bwd:
+            dxr, dgr, dbr, _ = O.bwd_f64(dyn, xn, styles, gam.numpy(), m_, r_)
+    else:
+        yr, pre, m_, r_ = O.fwd_epilogue_f64(xn, styles, gam.numpy(), bet.numpy())
+        assert rel_err(y.float().numpy(), yr) < tol
+        dxr, _, dgr, dbr, _ = O.bwd_epilogue_f64(dyn, pre, xn, styles, gam.numpy(), m_, r_, has_residual=False)
+    if bwd:
+        ptol = 5e-5 if tdt == torch.float32 else 5e-3
+        assert rel_err(dx.float().numpy(), dxr) < tol
+        assert rel_err(dg.numpy(), dgr) < ptol and rel_err(db.numpy(), dbr) < ptol
+    # a scratch that is too small is refused, not overrun
+    assert lib.micn_fwd_bwd_host(x.data_ptr(), None, y.data_ptr(), None, gam.data_ptr(), bet.data_ptr(), S, st.data_ptr(),
+                                 None, None, n, c, m, code, epi, 0.01, 1e-5, scratch.data_ptr(), 1024) == -4
