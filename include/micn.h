@@ -76,8 +76,9 @@ long long micn_get_option(const char* key);
  * then be reused by any number of calls of any shape that fits: exchange records are tagged with a
  * launch epoch that lives in the workspace header and is advanced by the kernels themselves, so the calls
  * are safe to capture in a CUDA graph and replay (no per-launch state on the host).  Calls that may
- * overlap in time (different streams) need different workspaces.  Without a workspace (or with one that is
- * too small) the large-slab fast path is not used. */
+ * overlap in time (different streams) need different workspaces.  The pointer must be 16-byte aligned
+ * (MICN_ERR_UNALIGNED otherwise).  Without a workspace (or with one that is too small) the large-slab fast
+ * path is not used. */
 size_t micn_workspace_bytes(int64_t N, int64_t C, int64_t M, int dtype, int num_styles);
 
 /* Host-blocking read (cudaMemcpy) of the sticky status word: bit 0 = a style index was out of

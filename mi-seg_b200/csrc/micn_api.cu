@@ -280,9 +280,9 @@ int launch_cluster(K kernel, const P& p, const Plan& pl, int NS, cudaStream_t st
 struct FlatWs {
     uint4* piece;
     uint4* slab;
-    unsigned* ctl;  // header words [2] epoch, [3] CTAs done
+    unsigned* ctl;  // header bytes 8..15: one 64-bit word, low half = CTAs arrived, high half = launch epoch
 };
-constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32), [8] flat launch epoch (u32), [12] flat CTAs done (u32)
+constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32), [8] flat CTAs arrived (u32), [12] flat launch epoch (u32)
 
 // upper bound of the pieces the flat planner can cut one slab into
 long long flat_max_pieces(long long slab_bytes) {
@@ -611,6 +611,7 @@ int elem_size(int dtype) { return dtype == MICN_F32 ? 4 : (dtype == MICN_BF16 ||
 // ------------------------------------------------------------------------------------------ channels-last path
 namespace {
 struct ClPlan {
+    bool fused;  // short columns: statistics and apply in one launch (micn_cl_*_fused_kernel)
     int MS;
     long long rps;
     float4* part;
@@ -623,10 +624,12 @@ size_t cl_ws_bytes(int64_t N, int64_t C) {
 int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_bytes, const DeviceInfo& d, ClPlan* pl) {
     if (!workspace || workspace_bytes < cl_ws_bytes(N, C)) return MICN_ERR_WORKSPACE;
     const long long tiles = (C + kClTile - 1) / kClTile;
+    pl->fused = M <= kClFusedMaxRows;
     long long ms = (2LL * d.sm_count + N * tiles - 1) / (N * tiles);  // at least two CTAs per SM
     ms = std::min<long long>(ms, kClMaxSplits);
     ms = std::min<long long>(ms, (M + 31) / 32);  // at least four rows per warp
     ms = std::max<long long>(ms, 1);
+    if (pl->fused) ms = 1;
     pl->rps = (M + ms - 1) / ms;
     pl->MS = (int)((M + pl->rps - 1) / pl->rps);
     unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
@@ -636,16 +639,24 @@ int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_b
     return 0;
 }
 template <typename T>
-int cl_fwd_typed(const ClParams& p, dim3 grid, cudaStream_t st) {
+int cl_fwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
+    if (fused) {
+        micn_cl_fwd_fused_kernel<T><<<grid, kClFusedThreads, 0, st>>>(p);
+        return (int)cudaGetLastError();
+    }
     micn_cl_fwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
     micn_cl_fwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 template <typename T>
-int cl_bwd_typed(const ClParams& p, dim3 grid, cudaStream_t st) {
-    micn_cl_bwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
-    micn_cl_bwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);
-    if (p.dgamma) {
+int cl_bwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
+    if (fused) {
+        micn_cl_bwd_fused_kernel<T><<<grid, kClFusedThreads, 0, st>>>(p);
+    } else {
+        micn_cl_bwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+        micn_cl_bwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+    }
+    if (p.dgamma && !(fused && p.N == 1)) {
         const long long sc = (long long)p.num_styles * p.C;
         micn_cl_param_grads_kernel<<<(unsigned)((sc + 255) / 256), 256, 0, st>>>(p);
     }
@@ -745,6 +756,7 @@ static int fwd_impl(const void* x, void* y, const void* residual, const float* c
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & (es - 1))
         return MICN_ERR_UNALIGNED;
     if (workspace && workspace_bytes < kWsHeader) return MICN_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MICN_ERR_UNALIGNED;  // 16-byte records, 64-bit header word
 
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
@@ -843,6 +855,7 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
         (es - 1))
         return MICN_ERR_UNALIGNED;
     if (dgamma && (!workspace || workspace_bytes < kWsHeader + (size_t)N * (size_t)C * 2 * sizeof(float))) return MICN_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MICN_ERR_UNALIGNED;  // 16-byte records, 64-bit header word
 
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
@@ -959,12 +972,12 @@ int micn_fwd_cl(const void* x, void* y, const float* const* gamma, const float* 
     g_opt.last_path.store(3);
     g_opt.last_cs.store(pl.MS);
     g_opt.last_grid.store((long long)grid.x * grid.y * grid.z);
-    g_opt.launches.fetch_add(2);
+    g_opt.launches.fetch_add(pl.fused ? 1 : 2);
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-        case MICN_F32: return cl_fwd_typed<float>(p, grid, st);
-        case MICN_BF16: return cl_fwd_typed<__nv_bfloat16>(p, grid, st);
-        case MICN_F16: return cl_fwd_typed<__half>(p, grid, st);
+        case MICN_F32: return cl_fwd_typed<float>(p, grid, pl.fused, st);
+        case MICN_BF16: return cl_fwd_typed<__nv_bfloat16>(p, grid, pl.fused, st);
+        case MICN_F16: return cl_fwd_typed<__half>(p, grid, pl.fused, st);
     }
     return MICN_ERR_BAD_DTYPE;
 }
@@ -1007,12 +1020,12 @@ int micn_bwd_cl(const void* dy, const void* x, const float* const* gamma, const 
     g_opt.last_path.store(3);
     g_opt.last_cs.store(pl.MS);
     g_opt.last_grid.store((long long)grid.x * grid.y * grid.z);
-    g_opt.launches.fetch_add(dgamma ? 3 : 2);
+    g_opt.launches.fetch_add((pl.fused ? 1 : 2) + ((dgamma && !(pl.fused && N == 1)) ? 1 : 0));
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-        case MICN_F32: return cl_bwd_typed<float>(p, grid, st);
-        case MICN_BF16: return cl_bwd_typed<__nv_bfloat16>(p, grid, st);
-        case MICN_F16: return cl_bwd_typed<__half>(p, grid, st);
+        case MICN_F32: return cl_bwd_typed<float>(p, grid, pl.fused, st);
+        case MICN_BF16: return cl_bwd_typed<__nv_bfloat16>(p, grid, pl.fused, st);
+        case MICN_F16: return cl_bwd_typed<__half>(p, grid, pl.fused, st);
     }
     return MICN_ERR_BAD_DTYPE;
 }

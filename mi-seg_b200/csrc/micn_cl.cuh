@@ -102,9 +102,10 @@ __device__ __forceinline__ ClTile cl_tile(const ClParams& p) {
     return t;
 }
 
-// rows r0 + warp, + 8, ... of the CTA's range, four in flight; f(x pair, second pair or dummy)
-template <typename T, bool TWO, typename F>
+// rows r0 + warp, + W, ... of the CTA's range (W warps), four in flight; f(x pair, second pair or dummy)
+template <typename T, bool TWO, int W = kClWarps, typename F>
 __device__ __forceinline__ void cl_rows(const ClParams& p, const ClTile& t, const void* a, const void* b, F f) {
+    constexpr int kClWarps = W;  // (shadows the two-kernel path's CTA shape inside this function)
     const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
     long long r = t.r0 + t.warp;
     for (; r + 3 * kClWarps < t.r1; r += 4 * kClWarps) {
@@ -126,14 +127,15 @@ __device__ __forceinline__ void cl_rows(const ClParams& p, const ClTile& t, cons
     }
 }
 
-// sum the 8 warps' (a0, b0, a1, b1) of every lane in a fixed order; the result is valid in warp 0
+// sum the W warps' (a0, b0, a1, b1) of every lane in a fixed order; the result is valid in warp 0
+template <int W = kClWarps>
 __device__ __forceinline__ float4 cl_block_sum(float4 v, float4* sm, int warp, int lane) {
     sm[warp * 32 + lane] = v;
     __syncthreads();
     float4 t = sm[lane];
     if (warp == 0) {
 #pragma unroll
-        for (int w = 1; w < kClWarps; ++w) {
+        for (int w = 1; w < W; ++w) {
             const float4 o = sm[w * 32 + lane];
             t.x += o.x;
             t.y += o.y;
@@ -282,6 +284,125 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_apply_kernel(const ClP
     const float4 c0 = coefA[t.lane], c1 = coefB[t.lane];
     const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
     cl_rows<T, true>(p, t, p.x, p.dy, [&](long long r, float2 v, float2 g) {
+        ClPair<T>::store(p.y, base + (size_t)r * (size_t)p.C, fmaf(c0.x, g.x, fmaf(c0.y, v.x, c0.z)),
+                         fmaf(c1.x, g.y, fmaf(c1.y, v.y, c1.z)));
+    });
+}
+
+// ---------------------------------------------------------------- fused kernels: short columns (M <= kClFusedMaxRows)
+// The 25 ViT token norms of C-UNETR ([B,768,216]) and the deep PatchMerging norms ([1,1536,6^3], [1,3072,3^3]) are
+// launch-bound: one 32-warp CTA per (sample, 64-channel tile) reduces its columns and applies the result in the same
+// launch (second pass from L1/L2); with one sample the parameter gradients are the slab sums themselves, so a
+// forward + backward pair is 2 launches instead of 5.
+constexpr int kClFusedThreads = 1024;
+constexpr int kClFusedWarps = kClFusedThreads / 32;
+constexpr int kClFusedMaxRows = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kClFusedThreads) micn_cl_fwd_fused_kernel(const ClParams p) {
+    __shared__ float4 sm[kClFusedThreads];
+    __shared__ float4 coef[32];
+    const ClTile t = cl_tile(p);  // MS == 1: the CTA's row range is the whole column
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 K = make_float2(0.f, 0.f);
+    if (t.valid) {
+        K = ClPair<T>::load(p.x, (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c);
+        cl_rows<T, false, kClFusedWarps>(p, t, p.x, nullptr, [&](long long, float2 v, float2) {
+            const float d0 = v.x - K.x, d1 = v.y - K.y;
+            acc.x += d0;
+            acc.y = fmaf(d0, d0, acc.y);
+            acc.z += d1;
+            acc.w = fmaf(d1, d1, acc.w);
+        });
+    }
+    acc = cl_block_sum<kClFusedWarps>(acc, sm, t.warp, t.lane);
+    if (t.warp == 0) {
+        float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t.valid) {
+            const int style = load_style(p.styles, t.n, p.num_styles, p.status);
+            const float cnt = (float)p.M;
+            const float s[2] = {acc.x, acc.z}, q[2] = {acc.y, acc.w}, k[2] = {K.x, K.y};
+            float ab[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float m = s[j] / cnt, mean = k[j] + m, M2 = fmaxf(q[j] - s[j] * m, 0.f);
+                const float rstd = 1.f / sqrtf(M2 / cnt + p.eps);  // biased variance, eps inside the sqrt
+                float gamma, beta;
+                load_affine(p, style, t.c + j, gamma, beta);
+                const float a = rstd * gamma;
+                ab[2 * j] = a;
+                ab[2 * j + 1] = fmaf(-mean, a, beta);
+                if (p.save_mean) {
+                    p.save_mean[t.n * p.C + t.c + j] = mean;
+                    p.save_rstd[t.n * p.C + t.c + j] = rstd;
+                }
+            }
+            cf = make_float4(ab[0], ab[1], ab[2], ab[3]);
+        }
+        coef[t.lane] = cf;
+    }
+    __syncthreads();
+    if (!t.valid) return;
+    const float4 cf = coef[t.lane];
+    const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
+    cl_rows<T, false, kClFusedWarps>(p, t, p.x, nullptr, [&](long long r, float2 v, float2) {
+        ClPair<T>::store(p.y, base + (size_t)r * (size_t)p.C, fmaf(v.x, cf.x, cf.y), fmaf(v.y, cf.z, cf.w));
+    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(const ClParams p) {
+    __shared__ float4 sm[kClFusedThreads];
+    __shared__ float4 coefA[32];
+    __shared__ float4 coefB[32];
+    const ClTile t = cl_tile(p);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // (S1_0, S2_0, S1_1, S2_1)
+    float m[2] = {0.f, 0.f};
+    if (t.valid) {
+        m[0] = __ldg(p.save_mean + t.n * p.C + t.c);
+        m[1] = __ldg(p.save_mean + t.n * p.C + t.c + 1);
+        cl_rows<T, true, kClFusedWarps>(p, t, p.x, p.dy, [&](long long, float2 v, float2 g) {
+            acc.x += g.x;
+            acc.y = fmaf(g.x, v.x - m[0], acc.y);
+            acc.z += g.y;
+            acc.w = fmaf(g.y, v.y - m[1], acc.w);
+        });
+    }
+    acc = cl_block_sum<kClFusedWarps>(acc, sm, t.warp, t.lane);
+    if (t.warp == 0) {
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        if (t.valid) {
+            const int style = load_style(p.styles, t.n, p.num_styles, p.status);
+            const float invM = 1.f / (float)p.M;
+            const float S1v[2] = {acc.x, acc.z}, S2v[2] = {acc.y, acc.w};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float rstd = __ldg(p.save_rstd + t.n * p.C + t.c + k);
+                float gamma, beta;
+                load_affine(p, style, t.c + k, gamma, beta);
+                const float a = rstd * gamma, S1 = S1v[k], S2r = S2v[k] * rstd;
+                const float B1 = -a * S2r * invM * rstd, B0 = fmaf(-B1, m[k], -a * S1 * invM);
+                (k == 0 ? c0 : c1) = make_float4(a, B1, B0, 0.f);
+                if (p.dgamma) {
+                    if (p.N == 1) {  // one sample: the slab sums are the gradients of its style's row
+                        for (int s = 0; s < p.num_styles; ++s) {
+                            p.dbeta[(long long)s * p.C + t.c + k] = s == style ? S1 : 0.f;
+                            p.dgamma[(long long)s * p.C + t.c + k] = s == style ? S2r : 0.f;
+                        }
+                    } else {
+                        p.ws_slab[t.n * p.C + t.c + k] = make_float2(S1, S2r);
+                    }
+                }
+            }
+        }
+        coefA[t.lane] = c0;
+        coefB[t.lane] = c1;
+    }
+    __syncthreads();
+    if (!t.valid) return;
+    const float4 c0 = coefA[t.lane], c1 = coefB[t.lane];
+    const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
+    cl_rows<T, true, kClFusedWarps>(p, t, p.x, p.dy, [&](long long r, float2 v, float2 g) {
         ClPair<T>::store(p.y, base + (size_t)r * (size_t)p.C, fmaf(c0.x, g.x, fmaf(c0.y, v.x, c0.z)),
                          fmaf(c1.x, g.y, fmaf(c1.y, v.y, c1.z)));
     });

@@ -125,18 +125,16 @@ __device__ __forceinline__ void flat_trace(const FlatGeom& g, unsigned j, int ev
 }
 
 // The tag of this launch's records comes from the workspace itself, not from the host: a captured CUDA graph
-// replays the same kernel parameters, and records left by the previous replay must not look current.  One lane
-// per CTA reads the epoch word e0 and THEN arrives on a counter in the header; the last CTA to arrive (all CTAs
-// are co-resident) resets the counter and bumps the epoch for the next launch - after every CTA has read e0.
-// All of this happens off the critical path, during the first piece's load; nothing is added at kernel end.
+// replays the same kernel parameters, and records left by the previous replay must not look current.  The header
+// holds one 64-bit word {epoch : arrivals}; one lane per CTA adds 1 to it, which reads the epoch and registers the
+// arrival in a single atomic (nothing to order).  The last CTA to arrive (all CTAs are co-resident) clears the
+// arrivals and bumps the epoch for the next launch - by then every CTA has read it.  All of this happens off the
+// critical path, during the first piece's load; nothing is added at kernel end.
 __device__ __forceinline__ unsigned flat_epoch_tag(const FlatGeom& g) {
-    const unsigned e0 = *reinterpret_cast<const volatile unsigned*>(g.ws_ctl);
-    __threadfence();  // the read of e0 is performed before the arrival below can be observed (one lane, off the critical path)
-    if (atomicAdd(g.ws_ctl + 1, 1u) == gridDim.x - 1) {
-        g.ws_ctl[1] = 0u;
-        __threadfence();
-        atomicAdd(g.ws_ctl, 1u);
-    }
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(g.ws_ctl);  // low word: arrivals, high word: epoch
+    const unsigned long long old = atomicAdd(w, 1ull);
+    const unsigned e0 = (unsigned)(old >> 32);
+    if ((unsigned)old == gridDim.x - 1) atomicAdd(w, (1ull << 32) - (unsigned long long)gridDim.x);
     return (e0 + 1u) | 0x80000000u;  // never 0: a zero-filled workspace holds no valid record
 }
 

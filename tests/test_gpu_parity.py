@@ -238,7 +238,9 @@ def test_channels_last_input_native_and_reference_layout(pkg):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("shape,name", [((2, 16, 6, 6, 6), "16x6^3"), ((1, 384, 8, 8, 8), "merge_384"),
                                         ((3, 70, 5, 7, 3), "C70_ragged"), ((4, 768, 216), "vit_tokens"),
-                                        ((2, 10, 4000), "long_columns")], ids=lambda v: v if isinstance(v, str) else None)
+                                        ((2, 10, 4000), "long_columns"),
+                                        ((1, 100, 3, 3, 3), "one_sample_27_rows_ragged_tile"),
+                                        ((1, 48, 1100), "one_sample_two_kernel_route")], ids=lambda v: v if isinstance(v, str) else None)
 def test_channels_last_route_vs_oracle(pkg, shape, name, dtype):
     gen = torch.Generator().manual_seed(len(name))
     n, c = shape[0], shape[1]
