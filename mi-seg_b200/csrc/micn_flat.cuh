@@ -97,7 +97,7 @@ struct FlatGeom {
     unsigned KA, KB;       // shared-memory slots of ring A (P1) and ring B (P2)
     unsigned L;            // steps P2 trails P1
     unsigned slot_vecs;    // vectors reserved per stream per slot (>= PV, multiple of 8)
-    unsigned* ws_ctl;      // workspace header: [0] launch epoch, [1] CTAs done (device-side, CUDA-graph safe)
+    unsigned* ws_ctl;      // workspace header: 64-bit word {launch epoch : CTAs arrived} (device-side, CUDA-graph safe)
     unsigned poll_delay_ns, poll_delay_tail_ns, poll_backoff_ns;
     FastDiv divP, divC;    // piece index -> slab, slab -> sample
     uint4* ws_piece;       // [T] piece records

@@ -690,7 +690,8 @@ int main(int argc, char** argv) {
         const long long M = oS * oS * oS;
         Case c = mk("trace", oN, oC, M, odt, oepi);
         c.force_path = opath; c.fslots = ofslots; c.flag = oflag; c.fpv = ofpv; c.fgrid = ofgrid; c.fovh = ofovh; c.fcoop = ofcoop; c.fpd = ofpd; c.fpb = ofpb;
-        const size_t tb = (size_t)prop.multiProcessorCount * 64 * 16 * sizeof(long long);
+        const int trace_ctas = 2 * prop.multiProcessorCount;  // the two-CTA-per-SM shape launches 2 x SMs CTAs
+        const size_t tb = (size_t)trace_ctas * 64 * 16 * sizeof(long long);
         long long* dtrace = nullptr;
         CK(cudaMalloc(&dtrace, tb));
         CK(cudaMemset(dtrace, 0, tb));
@@ -702,7 +703,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(ht.data(), dtrace, tb, cudaMemcpyDeviceToHost));
         printf("trace fwd_us %.2f bwd_us %.2f P=%lld KA=%lld L=%lld\n", r.fwd_us, r.bwd_us, r.f_cs, r.f_slots, micn_get_option("last_lag"));
         const char* names[12] = {"load", "p1b", "p1e", "pubb", "pube", "gab", "gapoll", "gae", "p2wait", "p2b", "p2e", "loadwait"};
-        const int nsm = prop.multiProcessorCount;
+        const int nsm = trace_ctas;
         long long t0 = 0;  // earliest stamp of the launch (%globaltimer is one clock for all SMs)
         for (size_t i = 0; i < ht.size(); ++i) if (ht[i] && (!t0 || ht[i] < t0)) t0 = ht[i];
         // per round: when was the LAST record of the round published, and when did the gathers finish
@@ -719,7 +720,7 @@ int main(int argc, char** argv) {
             if (!lp1) break;
             printf("%5d %9lld %9lld %9lld %9lld %9lld\n", j, lp1, lpub, fga, lga, lp2);
         }
-        const int ctas[3] = {0, 73, nsm - 1};
+        const int ctas[3] = {0, 73, (int)micn_get_option("last_grid") - 1};
         for (int ci = 0; ci < 3; ++ci) {
             const long long* t = ht.data() + (size_t)ctas[ci] * 64 * 16;
             printf("cta %d (ns since the launch's first stamp)\n  j ", ctas[ci]);
