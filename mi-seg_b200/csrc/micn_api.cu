@@ -244,7 +244,9 @@ int plan_cluster(K kernel, int NS_in, int NS_out, long long slabs, long long sla
 int small_tps(long long slab_bytes) {
     const long long f = g_opt.small_tps.load();
     if (f == 32 || f == 256 || f == 1024) return (int)f;
-    if (slab_bytes <= 2048) return 32;
+    // a warp per slab (8 slabs per CTA, no block barriers) up to 4 KB: [8,384,12^3] bf16 forward 10.3 us against
+    // 23.1 us with a 256-thread CTA per slab; from 8 KB on the CTA per slab wins
+    if (slab_bytes <= 4096) return 32;
     if (slab_bytes <= 128 * 1024) return 256;
     return 1024;
 }
@@ -282,6 +284,11 @@ struct FlatWs {
     uint4* slab;
     unsigned* ctl;  // header bytes 8..15: one 64-bit word, low half = CTAs arrived, high half = launch epoch
 };
+// Fixed prefix of every workspace, the same for all shapes (so a zero-filled workspace stays valid when calls of
+// different shapes share it): the header words, then one arrival counter per channel (self-resetting).  The
+// shape-dependent regions (per-slab sums, exchange records, channels-last partials) start at kWsData.
+constexpr size_t kWsChanCounters = 16384;
+constexpr size_t kWsData = 64 + kWsChanCounters * sizeof(unsigned);
 constexpr size_t kWsHeader = 64;  // [0] counter (u32), [4] status (i32), [8] flat CTAs arrived (u32), [12] flat launch epoch (u32)
 
 // upper bound of the pieces the flat planner can cut one slab into
@@ -298,7 +305,7 @@ struct WsLayout {
 WsLayout ws_layout(long long N, long long C, long long M, int es) {
     WsLayout w;
     const size_t slabs = (size_t)N * (size_t)C;
-    w.sums_off = kWsHeader;
+    w.sums_off = kWsData;
     w.slab_off = (w.sums_off + slabs * 2 * sizeof(float) + 15) & ~(size_t)15;
     w.piece_off = w.slab_off + slabs * 16;
     w.total = w.piece_off + slabs * (size_t)flat_max_pieces(M * es) * 16;
@@ -619,7 +626,7 @@ struct ClPlan {
     int* status;
 };
 size_t cl_ws_bytes(int64_t N, int64_t C) {
-    return kWsHeader + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4) + (size_t)N * (size_t)C * sizeof(float2);
+    return kWsData + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4) + (size_t)N * (size_t)C * sizeof(float2);
 }
 int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_bytes, const DeviceInfo& d, ClPlan* pl) {
     if (!workspace || workspace_bytes < cl_ws_bytes(N, C)) return MICN_ERR_WORKSPACE;
@@ -634,8 +641,8 @@ int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_b
     pl->MS = (int)((M + pl->rps - 1) / pl->rps);
     unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
     pl->status = reinterpret_cast<int*>(w) + 1;
-    pl->part = reinterpret_cast<float4*>(w + kWsHeader);
-    pl->slab = reinterpret_cast<float2*>(w + kWsHeader + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4));
+    pl->part = reinterpret_cast<float4*>(w + kWsData);
+    pl->slab = reinterpret_cast<float2*>(w + kWsData + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4));
     return 0;
 }
 template <typename T>
@@ -854,7 +861,7 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
          reinterpret_cast<uintptr_t>(act_out) | reinterpret_cast<uintptr_t>(dresidual)) &
         (es - 1))
         return MICN_ERR_UNALIGNED;
-    if (dgamma && (!workspace || workspace_bytes < kWsHeader + (size_t)N * (size_t)C * 2 * sizeof(float))) return MICN_ERR_WORKSPACE;
+    if (dgamma && (!workspace || workspace_bytes < ws_layout(N, C, 0, es).slab_off)) return MICN_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MICN_ERR_UNALIGNED;  // 16-byte records, 64-bit header word
 
     DeviceInfo* d = nullptr;
@@ -883,8 +890,9 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
         p.ws_counter = reinterpret_cast<unsigned int*>(w);
         p.status = reinterpret_cast<int*>(w) + 1;
         if (dgamma) {
-            p.ws_sum_dy = reinterpret_cast<float*>(w + kWsHeader);
+            p.ws_sum_dy = reinterpret_cast<float*>(w + kWsData);
             p.ws_sum_dyxh = p.ws_sum_dy + N * C;
+            p.ws_chan_cnt = (size_t)C <= kWsChanCounters ? reinterpret_cast<unsigned int*>(w + kWsHeader) : nullptr;
         }
     }
     p.N = N;

@@ -55,6 +55,7 @@ struct BwdParams {
     float* ws_sum_dy;    // [N*C] per-slab sum(g)
     float* ws_sum_dyxh;  // [N*C] per-slab sum(g*xhat)
     unsigned int* ws_counter;
+    unsigned int* ws_chan_cnt;  // [C] samples of a channel that have delivered their sums (small path, N > 1; self-resetting)
     int* status;
     long long N, C, M;
     long long x_sN, x_sC;

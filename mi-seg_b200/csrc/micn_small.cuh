@@ -188,6 +188,38 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_fwd_small_kernel(co
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
+// d(gamma)/d(beta) of one channel: fold the per-slab sums of its N samples per style, samples in order (deterministic);
+// four samples' loads in flight, non-matching styles add 0
+__device__ __forceinline__ void small_fold_channel(const BwdParams& p, long long ch) {
+    for (int s = 0; s < p.num_styles; ++s) {
+        float acc_b = 0.f, acc_g = 0.f;
+        long long k = 0;
+        for (; k + 4 <= p.N; k += 4) {
+            float vb[4], vg[4];
+            int st[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                st[q] = load_style(p.styles, k + q, p.num_styles, nullptr);
+                vb[q] = __ldcg(p.ws_sum_dy + (k + q) * p.C + ch);
+                vg[q] = __ldcg(p.ws_sum_dyxh + (k + q) * p.C + ch);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc_b += st[q] == s ? vb[q] : 0.f;
+                acc_g += st[q] == s ? vg[q] : 0.f;
+            }
+        }
+        for (; k < p.N; ++k) {
+            if (load_style(p.styles, k, p.num_styles, nullptr) == s) {
+                acc_b += __ldcg(p.ws_sum_dy + k * p.C + ch);
+                acc_g += __ldcg(p.ws_sum_dyxh + k * p.C + ch);
+            }
+        }
+        p.dbeta[(long long)s * p.C + ch] = acc_b;
+        p.dgamma[(long long)s * p.C + ch] = acc_g;
+    }
+}
+
 template <typename T, int EPI, int TPS>
 __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(const BwdParams p) {
     using V = VecT<T>;
@@ -264,9 +296,16 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
                     p.dgamma[(long long)s * p.C + ch] = s == style ? s2 : 0.f;
                 }
             } else {
+                // the last sample of a channel to deliver its sums folds the channel, samples in order (deterministic,
+                // and spread over the grid: no serial tail in one CTA)
                 p.ws_sum_dy[slab] = s1;
                 p.ws_sum_dyxh[slab] = s2;
                 __threadfence();
+                if (p.ws_chan_cnt && atomicAdd(p.ws_chan_cnt + ch, 1u) == (unsigned)p.N - 1u) {
+                    p.ws_chan_cnt[ch] = 0u;  // reusable by the next launch
+                    __threadfence();
+                    small_fold_channel(p, ch);
+                }
             }
         }
         const float invM = 1.f / (float)p.M;
@@ -311,8 +350,8 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
         }
     }
 
-    // ---- per-style parameter gradients by the last CTA (fixed order, deterministic)
-    if (p.dgamma && p.N > 1) {
+    // ---- more channels than the workspace has arrival counters for: the last CTA folds every channel
+    if (p.dgamma && p.N > 1 && !p.ws_chan_cnt) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -322,20 +361,7 @@ __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(co
         __syncthreads();
         if (is_last) {
             __threadfence();
-            const long long SC = (long long)p.num_styles * p.C;
-            for (long long idx = threadIdx.x; idx < SC; idx += blockDim.x) {
-                const int s = (int)(idx / p.C);
-                const long long ch = idx - (long long)s * p.C;
-                float acc_b = 0.f, acc_g = 0.f;
-                for (long long n = 0; n < p.N; ++n) {
-                    if (load_style(p.styles, n, p.num_styles, nullptr) == s) {
-                        acc_b += __ldcg(p.ws_sum_dy + n * p.C + ch);
-                        acc_g += __ldcg(p.ws_sum_dyxh + n * p.C + ch);
-                    }
-                }
-                p.dbeta[idx] = acc_b;
-                p.dgamma[idx] = acc_g;
-            }
+            for (long long ch = threadIdx.x; ch < p.C; ch += blockDim.x) small_fold_channel(p, ch);
             if (threadIdx.x == 0) *p.ws_counter = 0u;
         }
     }

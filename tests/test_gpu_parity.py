@@ -202,6 +202,17 @@ def test_epilogues_vs_oracle(pkg, shape, epilogue, dtype):
     _case(pkg, shape, [1, 0], 2, dtype, epilogue=epilogue, seed=11)
 
 
+def test_one_workspace_serves_calls_of_different_shapes(pkg):
+    """micn.h: a zero-filled workspace is reusable by calls of any shape.  The module path shares one workspace per
+    stream, so interleave shapes whose shape-dependent regions overlap (small path with N > 1: per-channel arrival
+    counters; flat path: exchange records) and check every call."""
+    for rep in range(2):
+        _case(pkg, (3, 5, 6, 6, 6), [0, 1, 0], 2, torch.float32, seed=rep)
+        _case(pkg, (2, 40, 4, 4, 4), [1, 1], 2, torch.float32, seed=10 + rep)
+        _case(pkg, (2, 3, 40, 40, 40), [1, 0], 2, torch.bfloat16, seed=20 + rep)
+        _case(pkg, (5, 7, 300), [0, 1, 1, 0, 1], 2, torch.float16, seed=30 + rep)
+
+
 def test_strided_channel_view(pkg):
     _case(pkg, (2, 5, 16, 16, 16), [0, 1], 2, torch.float32, stride_pad=3, seed=5)
     _case(pkg, (2, 5, 48, 48, 48), [1, 1], 2, torch.bfloat16, stride_pad=2, seed=6)
