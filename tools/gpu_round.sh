@@ -9,9 +9,6 @@ python -m pytest tests -m gpu -x -q > $o/${tag}_pytest.log 2>&1; echo "pytest ex
 python -c "import __graft_entry__ as g; g.smoke()" > $o/${tag}_smoke.log 2>&1; echo "smoke exit $?" >> $o/${tag}_smoke.log
 python bench.py > $o/${tag}_bench.log 2>&1; echo "bench exit $?" >> $o/${tag}_bench.log
 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_ref.log 2>&1; echo "ref exit $?" >> $o/${tag}_bench_ref.log
-ONE="tools/micn_selftest --suite one --N 1 --C 48 --S 96 --dtype bf16"
-$ONE > $o/${tag}_one.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:flat -s 2 -c 2 -o $o/${tag}_flat_bf16 -f $ONE > $o/${tag}_ncu_full.log 2>&1
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-torch-ref --no-model-calls"
 $B > $o/${tag}_bench_short.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches.csv $B > $o/${tag}_ncu_launches.log 2>&1
