@@ -119,7 +119,7 @@ def run_sweep(lib, pkg, dev, peak, out_path=None, budget_bytes=120e9):
                         if rc:
                             raise RuntimeError(f"micn_bwd rc={rc}")
 
-                    iters = max(3, min(30, int(3e9 // (5 * E * es)) + 1))
+                    iters = max(10, min(30, int(3e9 // (5 * E * es)) + 1))
                     res = {}
                     for name, fn in (("fwd", fwd), ("bwd", bwd)):
                         for i in range(3):
