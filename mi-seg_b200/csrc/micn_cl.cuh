@@ -102,24 +102,34 @@ __device__ __forceinline__ ClTile cl_tile(const ClParams& p) {
     return t;
 }
 
-// rows r0 + warp, + W, ... of the CTA's range (W warps), four in flight; f(x pair, second pair or dummy)
-template <typename T, bool TWO, int W = kClWarps, typename F>
+// rows r0 + warp, + W, ... of the CTA's range (W warps), kClInFlight rows in flight per lane (the loads are 4-8 bytes:
+// memory-level parallelism, not load width, is what keeps the SM fed); f(x pair, second pair or dummy)
+constexpr int kClInFlight = 8;
+template <typename T, bool TWO, int W = kClWarps, int INF = kClInFlight, typename F>
 __device__ __forceinline__ void cl_rows(const ClParams& p, const ClTile& t, const void* a, const void* b, F f) {
-    constexpr int kClWarps = W;  // (shadows the two-kernel path's CTA shape inside this function)
+    constexpr int kClInFlight = INF;  // (shadows the default inside this function)
     const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
     long long r = t.r0 + t.warp;
-    for (; r + 3 * kClWarps < t.r1; r += 4 * kClWarps) {
-        float2 va[4], vb[4];
+    for (; r + (kClInFlight - 1) * W < t.r1; r += kClInFlight * W) {
+        float2 va[kClInFlight], vb[kClInFlight];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const size_t e = base + (size_t)(r + i * kClWarps) * (size_t)p.C;
+        for (int i = 0; i < kClInFlight; ++i) {
+            const size_t e = base + (size_t)(r + i * W) * (size_t)p.C;
             va[i] = ClPair<T>::load(a, e);
             if (TWO) vb[i] = ClPair<T>::load(b, e);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f(r + i * kClWarps, va[i], TWO ? vb[i] : make_float2(0.f, 0.f));
+        for (int i = 0; i < kClInFlight; ++i) f(r + i * W, va[i], TWO ? vb[i] : make_float2(0.f, 0.f));
     }
-    for (; r < t.r1; r += kClWarps) {
+    for (; r + W < t.r1; r += 2 * W) {  // remainder, two rows at a time
+        const size_t e0 = base + (size_t)r * (size_t)p.C, e1 = base + (size_t)(r + W) * (size_t)p.C;
+        const float2 a0 = ClPair<T>::load(a, e0), a1 = ClPair<T>::load(a, e1);
+        const float2 b0 = TWO ? ClPair<T>::load(b, e0) : make_float2(0.f, 0.f);
+        const float2 b1 = TWO ? ClPair<T>::load(b, e1) : make_float2(0.f, 0.f);
+        f(r, a0, b0);
+        f(r + W, a1, b1);
+    }
+    for (; r < t.r1; r += W) {
         const size_t e = base + (size_t)r * (size_t)p.C;
         const float2 va = ClPair<T>::load(a, e);
         const float2 vb = TWO ? ClPair<T>::load(b, e) : make_float2(0.f, 0.f);
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_fwd_fused_kernel(cons
     float2 K = make_float2(0.f, 0.f);
     if (t.valid) {
         K = ClPair<T>::load(p.x, (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c);
-        cl_rows<T, false, kClFusedWarps>(p, t, p.x, nullptr, [&](long long, float2 v, float2) {
+        cl_rows<T, false, kClFusedWarps, 4>(p, t, p.x, nullptr, [&](long long, float2 v, float2) {
             const float d0 = v.x - K.x, d1 = v.y - K.y;
             acc.x += d0;
             acc.y = fmaf(d0, d0, acc.y);
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_fwd_fused_kernel(cons
     if (!t.valid) return;
     const float4 cf = coef[t.lane];
     const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
-    cl_rows<T, false, kClFusedWarps>(p, t, p.x, nullptr, [&](long long r, float2 v, float2) {
+    cl_rows<T, false, kClFusedWarps, 4>(p, t, p.x, nullptr, [&](long long r, float2 v, float2) {
         ClPair<T>::store(p.y, base + (size_t)r * (size_t)p.C, fmaf(v.x, cf.x, cf.y), fmaf(v.y, cf.z, cf.w));
     });
 }
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(cons
     if (t.valid) {
         m[0] = __ldg(p.save_mean + t.n * p.C + t.c);
         m[1] = __ldg(p.save_mean + t.n * p.C + t.c + 1);
-        cl_rows<T, true, kClFusedWarps>(p, t, p.x, p.dy, [&](long long, float2 v, float2 g) {
+        cl_rows<T, true, kClFusedWarps, 4>(p, t, p.x, p.dy, [&](long long, float2 v, float2 g) {
             acc.x += g.x;
             acc.y = fmaf(g.x, v.x - m[0], acc.y);
             acc.z += g.y;
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(cons
     if (!t.valid) return;
     const float4 c0 = coefA[t.lane], c1 = coefB[t.lane];
     const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
-    cl_rows<T, true, kClFusedWarps>(p, t, p.x, p.dy, [&](long long r, float2 v, float2 g) {
+    cl_rows<T, true, kClFusedWarps, 4>(p, t, p.x, p.dy, [&](long long r, float2 v, float2 g) {
         ClPair<T>::store(p.y, base + (size_t)r * (size_t)p.C, fmaf(c0.x, g.x, fmaf(c0.y, v.x, c0.z)),
                          fmaf(c1.x, g.y, fmaf(c1.y, v.y, c1.z)));
     });
