@@ -213,6 +213,39 @@ def test_one_workspace_serves_calls_of_different_shapes(pkg):
         _case(pkg, (5, 7, 300), [0, 1, 1, 0, 1], 2, torch.float16, seed=30 + rep)
 
 
+def _random_cases(count, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(count):
+        n, c = int(rng.randint(1, 6)), int(rng.randint(1, 41))
+        nd = int(rng.randint(1, 4))
+        target = int(np.exp(rng.uniform(np.log(2), np.log(60000))))  # slab lengths from 2 to ~60 k elements, log-uniform
+        dims = []
+        for d in range(nd - 1):
+            f = int(rng.randint(1, max(2, int(round(target ** (1.0 / nd))) * 2)))
+            dims.append(f)
+            target = max(1, target // f)
+        dims.append(max(2 if nd == 1 else 1, target))
+        if int(np.prod(dims)) < 2:
+            dims[-1] = 2
+        num_styles = int(rng.randint(1, 5))
+        styles = [int(rng.randint(-num_styles, num_styles)) for _ in range(n)]
+        styles = [s + num_styles if s < 0 else s for s in styles]
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.randint(0, 3))]
+        epilogue = ["none", "lrelu", "add_lrelu"][int(rng.randint(0, 3))]
+        pad = int(rng.randint(0, 3)) if epilogue == "none" else 0
+        out.append(((n, c) + tuple(dims), styles, num_styles, dtype, epilogue, pad, k))
+    return out
+
+
+@pytest.mark.parametrize("shape,styles,num_styles,dtype,epilogue,pad,k", _random_cases(36, 20261018),
+                         ids=lambda v: None if not isinstance(v, int) else None)
+def test_seeded_random_shapes_vs_oracle(pkg, shape, styles, num_styles, dtype, epilogue, pad, k):
+    """Ragged shapes nobody picked by hand: 1-3 spatial dims, slab lengths 2 ... 60 k elements (every path and every
+    head / tail peeling case), 1-4 styles, all dtypes and epilogues, channel-padded views."""
+    _case(pkg, shape, styles, num_styles, dtype, epilogue=epilogue, seed=100 + k, stride_pad=pad)
+
+
 def test_strided_channel_view(pkg):
     _case(pkg, (2, 5, 16, 16, 16), [0, 1], 2, torch.float32, stride_pad=3, seed=5)
     _case(pkg, (2, 5, 48, 48, 48), [1, 1], 2, torch.bfloat16, stride_pad=2, seed=6)
