@@ -68,6 +68,7 @@ struct Options {
     std::atomic<long long> slots{-1};         // force ring slots S
     std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
     std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
+    std::atomic<long long> small_reg{-1};     // 0: never the register-resident small kernels (experiments)
     std::atomic<long long> last_path{-1}, last_cs{-1}, last_slots{-1}, last_grid{-1}, last_lag{-1};  // read-back of the last plan
     std::atomic<long long> host_groups{-1};   // channel groups of the host-buffer path (default 10)
     std::atomic<long long> host_trace{0};     // 1: print a per-group timeline of the host-buffer path to stderr
@@ -85,7 +86,7 @@ struct OptName {
 };
 const OptName kOptNames[] = {
     {"cluster_size", &g_opt.cluster_size}, {"force_path", &g_opt.force_path}, {"slots", &g_opt.slots},
-    {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps},   {"last_path", &g_opt.last_path},
+    {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps}, {"small_reg", &g_opt.small_reg},   {"last_path", &g_opt.last_path},
     {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid}, {"last_lag", &g_opt.last_lag},
     {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
@@ -524,15 +525,24 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     }
     pl.path = 0;
     pl.tps = small_tps(slab_bytes);
+    // a CTA per slab with more than two 16-byte vectors per thread: the register-resident instantiation
+    // (micn_small.cuh).  Measured neutral to slightly negative for the warp-per-slab shape, so not used there.
+    const bool reg = pl.tps == 256 && slab_bytes / 16 > 2 * pl.tps && g_opt.small_reg.load() != 0;
     if (pl.tps == 32) {
         const unsigned grid = (unsigned)((slabs + 7) / 8);
         pl.grid_clusters = (int)grid;
         record_plan(pl);
-        micn_fwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+        if (reg)
+            micn_fwd_small_kernel<T, EPI, 32, true><<<grid, 256, 0, st>>>(p);
+        else
+            micn_fwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
     } else if (pl.tps == 256) {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
-        micn_fwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
+        if (reg)
+            micn_fwd_small_kernel<T, EPI, 256, true><<<(unsigned)slabs, 256, 0, st>>>(p);
+        else
+            micn_fwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
     } else {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
@@ -572,15 +582,24 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     }
     pl.path = 0;
     pl.tps = small_tps(slab_bytes);
+    // a CTA per slab with more than two 16-byte vectors per thread: the register-resident instantiation
+    // (micn_small.cuh).  Measured neutral to slightly negative for the warp-per-slab shape, so not used there.
+    const bool reg = pl.tps == 256 && slab_bytes / 16 > 2 * pl.tps && g_opt.small_reg.load() != 0;
     if (pl.tps == 32) {
         const unsigned grid = (unsigned)((slabs + 7) / 8);
         pl.grid_clusters = (int)grid;
         record_plan(pl);
-        micn_bwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+        if (reg)
+            micn_bwd_small_kernel<T, EPI, 32, true><<<grid, 256, 0, st>>>(p);
+        else
+            micn_bwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
     } else if (pl.tps == 256) {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
-        micn_bwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
+        if (reg)
+            micn_bwd_small_kernel<T, EPI, 256, true><<<(unsigned)slabs, 256, 0, st>>>(p);
+        else
+            micn_bwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
     } else {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
