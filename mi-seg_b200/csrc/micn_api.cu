@@ -532,10 +532,7 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
         const unsigned grid = (unsigned)((slabs + 7) / 8);
         pl.grid_clusters = (int)grid;
         record_plan(pl);
-        if (reg)
-            micn_fwd_small_kernel<T, EPI, 32, true><<<grid, 256, 0, st>>>(p);
-        else
-            micn_fwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+        micn_fwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
     } else if (pl.tps == 256) {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
@@ -589,10 +586,7 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
         const unsigned grid = (unsigned)((slabs + 7) / 8);
         pl.grid_clusters = (int)grid;
         record_plan(pl);
-        if (reg)
-            micn_bwd_small_kernel<T, EPI, 32, true><<<grid, 256, 0, st>>>(p);
-        else
-            micn_bwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+        micn_bwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
     } else if (pl.tps == 256) {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
