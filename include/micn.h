@@ -144,7 +144,7 @@ int micn_bwd_prelu(const void* dy, const void* x, const void* act_out,
  * which PatchMerging's norms (networks/blocks/patch_merging.py:136-141) and the ViT token norms
  * (transformer_block.py:87-92, vit.py:188-193) reach `_apply_instance_norm` as permuted views.  Same math, no
  * epilogue; the output keeps the input's layout, so the transposing copies around the norm disappear.
- * Workspace: micn_cl_workspace_bytes, no zero-fill needed. */
+ * Workspace: micn_cl_workspace_bytes, zero-filled once when allocated (16-byte aligned), then reusable forever. */
 size_t micn_cl_workspace_bytes(int64_t N, int64_t C, int64_t M);
 int micn_fwd_cl(const void* x, void* y,
                 const float* const* gamma, const float* const* beta, int num_styles,

@@ -637,6 +637,7 @@ struct ClPlan {
     float4* part;
     float2* slab;
     int* status;
+    unsigned* tile_cnt;
 };
 size_t cl_ws_bytes(int64_t N, int64_t C) {
     return kWsData + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4) + (size_t)N * (size_t)C * sizeof(float2);
@@ -654,6 +655,7 @@ int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_b
     pl->MS = (int)((M + pl->rps - 1) / pl->rps);
     unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
     pl->status = reinterpret_cast<int*>(w) + 1;
+    pl->tile_cnt = (size_t)tiles <= kWsChanCounters ? reinterpret_cast<unsigned*>(w + kWsHeader) : nullptr;
     pl->part = reinterpret_cast<float4*>(w + kWsData);
     pl->slab = reinterpret_cast<float2*>(w + kWsData + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4));
     return 0;
@@ -676,7 +678,7 @@ int cl_bwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
         micn_cl_bwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
         micn_cl_bwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);
     }
-    if (p.dgamma && !(fused && p.N == 1)) {
+    if (p.dgamma && p.N > 1 && !p.tile_cnt) {  // (otherwise the backward kernels fold the parameter gradients themselves)
         const long long sc = (long long)p.num_styles * p.C;
         micn_cl_param_grads_kernel<<<(unsigned)((sc + 255) / 256), 256, 0, st>>>(p);
     }
@@ -694,6 +696,7 @@ int cl_fill(ClParams& p, const float* const* gamma, const float* const* beta, in
     p.status = pl.status;
     p.ws_part = pl.part;
     p.ws_slab = pl.slab;
+    p.tile_cnt = pl.tile_cnt;
     p.N = N;
     p.C = C;
     p.M = M;
@@ -1041,7 +1044,7 @@ int micn_bwd_cl(const void* dy, const void* x, const float* const* gamma, const 
     g_opt.last_path.store(3);
     g_opt.last_cs.store(pl.MS);
     g_opt.last_grid.store((long long)grid.x * grid.y * grid.z);
-    g_opt.launches.fetch_add((pl.fused ? 1 : 2) + ((dgamma && !(pl.fused && N == 1)) ? 1 : 0));
+    g_opt.launches.fetch_add((pl.fused ? 1 : 2) + ((dgamma && N > 1 && !pl.tile_cnt) ? 1 : 0));
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
         case MICN_F32: return cl_bwd_typed<float>(p, grid, pl.fused, st);

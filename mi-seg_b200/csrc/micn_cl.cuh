@@ -43,6 +43,7 @@ struct ClParams {
     int* status;
     float4* ws_part;   // [N][MS][C]
     float2* ws_slab;   // [N][C]  backward: (sum g, sum g*xhat)
+    unsigned* tile_cnt;  // [channel tiles] samples of a tile that delivered their sums (workspace prefix, self-resetting)
     long long N, C, M, rows_per_split;
     int MS, num_styles, affine;
     float eps;
@@ -234,6 +235,47 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_fwd_apply_kernel(const ClP
     });
 }
 
+// Parameter gradients from warp 0 of the CTA that owns (sample, channel tile).  One sample: the slab sums are the
+// gradients of its style's rows.  More: every sample delivers its sums, the last one of the tile to arrive (arrival
+// counter in the workspace prefix) folds the tile, samples in order - deterministic, no extra launch.  Without a
+// counter (more tiles than the prefix holds) micn_cl_param_grads_kernel does the fold.
+__device__ __forceinline__ void cl_param_grads(const ClParams& p, const ClTile& t, const float* S1, const float* S2r, int style) {
+    if (!p.dgamma) return;
+    if (p.N == 1) {
+        if (t.valid)
+            for (int k = 0; k < 2; ++k)
+                for (int s = 0; s < p.num_styles; ++s) {
+                    p.dbeta[(long long)s * p.C + t.c + k] = s == style ? S1[k] : 0.f;
+                    p.dgamma[(long long)s * p.C + t.c + k] = s == style ? S2r[k] : 0.f;
+                }
+        return;
+    }
+    if (t.valid)
+        for (int k = 0; k < 2; ++k) p.ws_slab[t.n * p.C + t.c + k] = make_float2(S1[k], S2r[k]);
+    if (!p.tile_cnt) return;
+    __threadfence();
+    __syncwarp();
+    unsigned prev = 0u;
+    if (t.lane == 0) prev = atomicAdd(p.tile_cnt + blockIdx.x, 1u);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev != (unsigned)p.N - 1u) return;
+    if (t.lane == 0) p.tile_cnt[blockIdx.x] = 0u;  // reusable by the next launch
+    __threadfence();
+    if (!t.valid) return;
+    for (int k = 0; k < 2; ++k)
+        for (int s = 0; s < p.num_styles; ++s) {
+            float db = 0.f, dg = 0.f;
+            for (long long n = 0; n < p.N; ++n) {
+                const float2 v = __ldcg(p.ws_slab + n * p.C + t.c + k);
+                const bool mine = load_style(p.styles, n, p.num_styles, nullptr) == s;
+                db += mine ? v.x : 0.f;
+                dg += mine ? v.y : 0.f;
+            }
+            p.dbeta[(long long)s * p.C + t.c + k] = db;
+            p.dgamma[(long long)s * p.C + t.c + k] = dg;
+        }
+}
+
 // ---------------------------------------------------------------- backward
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_stats_kernel(const ClParams p) {
@@ -264,8 +306,10 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_apply_kernel(const ClP
     const ClTile t = cl_tile(p);
     if (t.warp == 0) {
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        float S1v[2] = {0.f, 0.f}, S2rv[2] = {0.f, 0.f};
+        int style = 0;
         if (t.valid) {
-            const int style = load_style(p.styles, t.n, p.num_styles, p.status);
+            style = load_style(p.styles, t.n, p.num_styles, p.status);
             const float invM = 1.f / (float)p.M;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -283,11 +327,13 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_apply_kernel(const ClP
                 // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
                 const float B1 = -a * S2r * invM * rstd, B0 = fmaf(-B1, mean, -a * S1 * invM);
                 (k == 0 ? c0 : c1) = make_float4(a, B1, B0, 0.f);
-                if (t.split == 0) p.ws_slab[t.n * p.C + t.c + k] = make_float2(S1, S2r);
+                S1v[k] = S1;
+                S2rv[k] = S2r;
             }
         }
         coefA[t.lane] = c0;
         coefB[t.lane] = c1;
+        if (t.split == 0) cl_param_grads(p, t, S1v, S2rv, style);
     }
     __syncthreads();
     if (!t.valid) return;
@@ -381,10 +427,12 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(cons
     acc = cl_block_sum<kClFusedWarps>(acc, sm, t.warp, t.lane);
     if (t.warp == 0) {
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        float S2rv[2] = {0.f, 0.f};
+        const float S1v[2] = {acc.x, acc.z}, S2v[2] = {acc.y, acc.w};
+        int style = 0;
         if (t.valid) {
-            const int style = load_style(p.styles, t.n, p.num_styles, p.status);
+            style = load_style(p.styles, t.n, p.num_styles, p.status);
             const float invM = 1.f / (float)p.M;
-            const float S1v[2] = {acc.x, acc.z}, S2v[2] = {acc.y, acc.w};
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const float rstd = __ldg(p.save_rstd + t.n * p.C + t.c + k);
@@ -393,20 +441,12 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(cons
                 const float a = rstd * gamma, S1 = S1v[k], S2r = S2v[k] * rstd;
                 const float B1 = -a * S2r * invM * rstd, B0 = fmaf(-B1, m[k], -a * S1 * invM);
                 (k == 0 ? c0 : c1) = make_float4(a, B1, B0, 0.f);
-                if (p.dgamma) {
-                    if (p.N == 1) {  // one sample: the slab sums are the gradients of its style's row
-                        for (int s = 0; s < p.num_styles; ++s) {
-                            p.dbeta[(long long)s * p.C + t.c + k] = s == style ? S1 : 0.f;
-                            p.dgamma[(long long)s * p.C + t.c + k] = s == style ? S2r : 0.f;
-                        }
-                    } else {
-                        p.ws_slab[t.n * p.C + t.c + k] = make_float2(S1, S2r);
-                    }
-                }
+                S2rv[k] = S2r;
             }
         }
         coefA[t.lane] = c0;
         coefB[t.lane] = c1;
+        cl_param_grads(p, t, S1v, S2rv, style);
     }
     __syncthreads();
     if (!t.valid) return;
