@@ -11,7 +11,8 @@ Prints ONE JSON line (rank 0):
   value     algorithmic GB/s, (2 + 3) * E * s bytes per step per GPU, inputs resident in HBM, CUDA events
   e2e       the same metric through `micn_fwd_bwd_host` (host pinned buffers in, host buffers out;
             H2D / D2H inside the timed region)
-  roofline  the dominant kernel (backward: 3 * E * s bytes per launch) against MEASURED_PEAKS.json
+  roofline  the dominant kernel (backward: 3 * E * s bytes per launch, average duration over a region of
+            back-to-back launches of that kernel, CUDA events on its stream) against MEASURED_PEAKS.json
   cpu_baseline  the oracle's torch-CPU port of the reference call sequence on the box's host cores
 `--impl reference` times that CPU port alone (the reference's own path: per-sample F.instance_norm +
 torch.stack + autograd) on the same config.
