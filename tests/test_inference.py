@@ -143,3 +143,33 @@ def test_sharded_windows_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+def test_window_slices_properties_hold_for_random_geometries():
+    """Size-independent properties of the window enumeration (MONAI `dense_patch_slices`): every window has the roi's
+    size and lies inside the volume, every voxel is covered, the count per dimension is MONAI's
+    ceil((size - roi) / interval) + 1, and the order is first-dimension-slowest."""
+    rng = np.random.RandomState(5)
+    for _ in range(200):
+        nd = int(rng.randint(1, 4))
+        roi = tuple(int(rng.randint(1, 9)) for _ in range(nd))
+        size = tuple(int(r + rng.randint(0, 14)) for r in roi)
+        overlap = float(rng.choice([0.0, 0.25, 0.5, 0.75, 0.9]))
+        sl = inference.window_slices(size, roi, overlap)
+        expect = 1
+        for s_, r_ in zip(size, roi):
+            iv = r_ if r_ == s_ else max(int(r_ * (1 - overlap)), 1)
+            expect *= int(math.ceil((s_ - r_) / iv)) + 1
+        assert len(sl) == expect
+        cover = np.zeros(size, dtype=np.int32)
+        for w in sl:
+            assert all(0 <= a.start and a.stop <= s_ and a.stop - a.start == r_ for a, s_, r_ in zip(w, size, roi))
+            cover[w] += 1
+        assert cover.min() >= 1
+        starts = [tuple(a.start for a in w) for w in sl]
+        assert starts == sorted(starts)  # lexicographic = first dimension slowest
+
+
+def test_full_size_window_count_of_the_inference_config():
+    """BASELINE.json configs[4] / SURVEY.md 8(d): 512 x 512 x 300 volume, roi 96^3, overlap 0.5 -> 10 * 10 * 6 windows."""
+    assert len(inference.window_slices((512, 512, 300), (96, 96, 96), 0.5)) == 600
