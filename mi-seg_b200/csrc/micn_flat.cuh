@@ -25,11 +25,11 @@
 //
 //   producer A / B (1 lane each)  1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), KA / KB slots ahead;
 //                           B issues P2(j)'s copy as soon as P1(j) is through, so it is in the slot long before use.
-//   16 consumer warps       each warp owns a fixed 1/16 of every piece: fp32 shifted sums + warp shuffle in P1;
+//   16 (8) consumer warps   each warp owns a fixed 1/16 (1/8) of every piece: fp32 shifted sums + warp shuffle in P1;
 //                           FMA + pack + st.global.v4 in P2.  Every wait parks the warp (try_wait + suspend hint).
 //   1 publish warp          folds the 16 warp partials of a piece and write the piece record to the workspace as
 //                           soon as its P1 is done; never wait on another CTA.
-//   4 gather warps          poll the P records of the piece's slab (batches of loads in flight, re-polled in
+//   4 (2) gather warps      poll the P records of the piece's slab (batches of loads in flight, re-polled in
 //                           parallel), fold them in a fixed order (bit-identical in every CTA, no atomics)
 //                           and publish the per-slab coefficients P2 needs; backward: also the per-slab
 //                           sums and, for the last sample of a channel, d(gamma)/d(beta) per style.
@@ -40,8 +40,9 @@
 // which is exact algebra, well conditioned because |mean_q - ref| is of the order of the spread, and uses one
 // division per fold.
 //
-// Cross-CTA exchange is by 16-byte self-validating records {a, tag, b, tag} (tag = per-launch epoch): no
-// counters to reset, an aborted launch cannot poison the next one.  Deadlock freedom: a slab of P pieces
+// Cross-CTA exchange is by 16-byte self-validating records {a, tag, b, tag}; the tag is a per-launch epoch kept in
+// the workspace header and advanced by the kernel itself (flat_epoch_tag), so records of an earlier launch - or of
+// an earlier replay of a captured CUDA graph - never look current and nothing has to be cleared.  Deadlock freedom: a slab of P pieces
 // spans R <= ceil((P-1)/G)+1 rounds and the planner keeps L >= R, so every P1 a record depends on runs
 // before anyone can block in a P2; publishes never block.  Every wait is bounded and traps instead of hanging.
 //
@@ -52,7 +53,8 @@
 // Reference semantics: networks/norms/conditional_instance_norm.py:59-60 (+ ATen instance_norm:
 // biased variance, eps inside the sqrt), epilogues networks/blocks/dynunet_block.py:107-125.
 // This header is included once per CTA SHAPE (micn_api.cu): MICN_FLAT_NS names the sub-namespace, MICN_FLAT_CW /
-// MICN_FLAT_GW / MICN_FLAT_CPS the consumer warps, gather warps and persistent CTAs per SM of that shape.
+// MICN_FLAT_GW / MICN_FLAT_CPS the consumer warps, gather warps and persistent CTAs per SM of that shape
+// (flat1: 16 / 4 / 1, fp32 forward and every backward; flat2: 8 / 2 / 2, 16-bit forward - the numbers in brackets above).
 #include "micn_common.cuh"
 
 #ifndef MICN_FLAT_NS
@@ -73,14 +75,14 @@ namespace MICN_FLAT_NS {
 #endif
 constexpr int kFlatConsumerWarps = MICN_FLAT_CW;
 constexpr int kFlatCtasPerSm = MICN_FLAT_CPS;
-constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512
+constexpr int kFlatConsumerThreads = kFlatConsumerWarps * 32;  // 512 (flat1) / 256 (flat2)
 constexpr int kFlatProducerWarpA = kFlatConsumerWarps;
 constexpr int kFlatProducerWarpB = kFlatConsumerWarps + 1;
 constexpr int kFlatPublishWarp0 = kFlatConsumerWarps + 2;
 constexpr int kFlatPublishWarps = 1;
 constexpr int kFlatGatherWarp0 = kFlatPublishWarp0 + kFlatPublishWarps;
 constexpr int kFlatGatherWarps = MICN_FLAT_GW;  // a gather is a multi-microsecond latency chain: keep several in flight
-constexpr int kFlatThreads = (kFlatConsumerWarps + 2 + kFlatPublishWarps + kFlatGatherWarps) * 32;  // 736 -> 88 registers
+constexpr int kFlatThreads = (kFlatConsumerWarps + 2 + kFlatPublishWarps + kFlatGatherWarps) * 32;  // 736 (flat1: 88 registers) / 416 (flat2)
 constexpr int kFlatMaxSlots = 8;     // per ring
 constexpr int kFlatNB = 32;          // per-piece control ring (partials, coefficients): piece j -> entry j % 32
 constexpr int kFlatMaxLag = 30;      // L <= kFlatNB - 1: an entry is recycled only after its piece's P2 is done
