@@ -4,7 +4,9 @@
 // size) owns one (n, c) slab.  The deep levels of the MI-Seg encoders produce thousands of tiny slabs
 // ([1,192,12^3], [1,384,6^3], [1,768,3^3]) and the ViT/PatchMerging calls produce odd lengths
 // (27, 216 tokens): the cluster/TMA machinery does not pay there, parallelism comes from the number
-// of slabs instead.  Pass 2 re-reads the slab from L1/L2 (<= 64 KB per group, 8 groups per SM).
+// of slabs instead.  Pass 2 re-reads the slab from L1/L2 (<= 64 KB per group, 8 groups per SM), or - REG
+// instantiation, 8-32 KB slabs with a CTA each - takes it from registers.  Parameter gradients: one sample writes
+// them directly; several samples fold per channel when its last sample arrives (no tail in one CTA).
 //
 // Any alignment is accepted: when source and destination slabs share the same misalignment modulo
 // 16 bytes the body is peeled into scalar head / 128-bit body / scalar tail, otherwise all-scalar.
