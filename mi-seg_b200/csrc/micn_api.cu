@@ -68,6 +68,7 @@ struct Options {
     std::atomic<long long> slots{-1};         // force ring slots S
     std::atomic<long long> max_clusters{-1};  // cap on co-resident clusters used
     std::atomic<long long> small_tps{-1};     // force 32 / 256 / 1024
+    std::atomic<long long> cl_wide{-1};       // 0: never the 16-byte-load channels-last kernels (experiments)
     std::atomic<long long> small_reg{-1};     // 0: never the register-resident small kernels (experiments)
     std::atomic<long long> last_path{-1}, last_cs{-1}, last_slots{-1}, last_grid{-1}, last_lag{-1};  // read-back of the last plan
     std::atomic<long long> host_groups{-1};   // channel groups of the host-buffer path (default 10)
@@ -86,7 +87,7 @@ struct OptName {
 };
 const OptName kOptNames[] = {
     {"cluster_size", &g_opt.cluster_size}, {"force_path", &g_opt.force_path}, {"slots", &g_opt.slots},
-    {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps}, {"small_reg", &g_opt.small_reg},   {"last_path", &g_opt.last_path},
+    {"max_clusters", &g_opt.max_clusters}, {"small_tps", &g_opt.small_tps}, {"small_reg", &g_opt.small_reg}, {"cl_wide", &g_opt.cl_wide},   {"last_path", &g_opt.last_path},
     {"last_cs", &g_opt.last_cs},           {"last_slots", &g_opt.last_slots}, {"last_grid", &g_opt.last_grid}, {"last_lag", &g_opt.last_lag},
     {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
@@ -660,10 +661,22 @@ int cl_plan(int64_t N, int64_t C, int64_t M, void* workspace, size_t workspace_b
     pl->slab = reinterpret_cast<float2*>(w + kWsData + (size_t)N * kClMaxSplits * (size_t)C * sizeof(float4));
     return 0;
 }
+// 16-byte row loads need whole vectors of channels per lane and aligned tensors (micn_cl.cuh, wide variant)
+template <typename T>
+bool cl_wide_ok(const ClParams& p) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.dy);
+    return g_opt.cl_wide.load() != 0 && p.C % ClWide<T>::CPL == 0 && (bits & 15u) == 0;
+}
+
 template <typename T>
 int cl_fwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
     if (fused) {
         micn_cl_fwd_fused_kernel<T><<<grid, kClFusedThreads, 0, st>>>(p);
+        return (int)cudaGetLastError();
+    }
+    if (cl_wide_ok<T>(p)) {
+        micn_cl_fwd_stats_wide_kernel<T><<<grid, kClThreads, 0, st>>>(p);
+        micn_cl_fwd_apply_wide_kernel<T><<<grid, kClThreads, 0, st>>>(p);
         return (int)cudaGetLastError();
     }
     micn_cl_fwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);

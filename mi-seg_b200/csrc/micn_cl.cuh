@@ -345,6 +345,185 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_apply_kernel(const ClP
     });
 }
 
+// ---------------------------------------------------------------- wide variant of the two-kernel path
+// Same tiles, same partials, same folds, but the rows are streamed with 16-byte loads: a lane owns CPL = 8 (16-bit) or
+// 4 (fp32) adjacent channels, LPR = 64 / CPL lanes cover a row of the tile and a warp instruction covers 32 / LPR
+// rows, four instructions in flight (64 bytes per lane instead of 32 in eight 4-byte loads).  Needs C % CPL == 0
+// and 16-byte aligned tensors; the host falls back to the pair kernels above otherwise.  Forward only: measured on
+// [8,384,24^3] bf16 the forward gains 14 % (74 -> 64 us), the two-stream backward loses (95 -> 113 us) and keeps the
+// pair kernels.
+template <typename T>
+struct ClWide {
+    static constexpr int CPL = 16 / (int)sizeof(T);
+    static constexpr int LPR = kClTile / CPL;
+    static constexpr int RPI = 32 / LPR;
+};
+
+struct ClWideTile {
+    long long n, r0, r1, c;  // sample, row range, first of this lane's CPL channels
+    bool valid;
+    int warp, rsub, cg, split;
+};
+template <typename T>
+__device__ __forceinline__ ClWideTile cl_wide_tile(const ClParams& p) {
+    using W = ClWide<T>;
+    ClWideTile t;
+    const int lane = threadIdx.x & 31;
+    t.warp = threadIdx.x >> 5;
+    t.cg = lane % W::LPR;
+    t.rsub = lane / W::LPR;
+    t.n = blockIdx.z;
+    t.split = blockIdx.y;
+    t.c = (long long)blockIdx.x * kClTile + (long long)t.cg * W::CPL;
+    t.valid = t.c < p.C;  // C % CPL == 0: the whole vector is inside
+    t.r0 = (long long)t.split * p.rows_per_split;
+    t.r1 = t.r0 + p.rows_per_split < p.M ? t.r0 + p.rows_per_split : p.M;
+    return t;
+}
+
+template <typename T, bool TWO, typename F>
+__device__ __forceinline__ void cl_rows_wide(const ClParams& p, const ClWideTile& t, const void* a, const void* b, F f) {
+    using W = ClWide<T>;
+    constexpr long long step = (long long)kClWarps * W::RPI;
+    const T* pa = reinterpret_cast<const T*>(a);
+    const T* pb = reinterpret_cast<const T*>(b);
+    const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
+    long long r = t.r0 + (long long)t.warp * W::RPI + t.rsub;
+    for (; r + 3 * step < t.r1; r += 4 * step) {
+        uint4 va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t e = base + (size_t)(r + i * step) * (size_t)p.C;
+            va[i] = __ldg(reinterpret_cast<const uint4*>(pa + e));
+            if (TWO) vb[i] = __ldg(reinterpret_cast<const uint4*>(pb + e));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f(r + i * step, va[i], TWO ? vb[i] : make_uint4(0u, 0u, 0u, 0u));
+    }
+    for (; r < t.r1; r += step) {
+        const size_t e = base + (size_t)r * (size_t)p.C;
+        const uint4 va = __ldg(reinterpret_cast<const uint4*>(pa + e));
+        const uint4 vb = TWO ? __ldg(reinterpret_cast<const uint4*>(pb + e)) : make_uint4(0u, 0u, 0u, 0u);
+        f(r, va, vb);
+    }
+}
+
+// per-lane (u[j], v[j]) of CPL channels -> per-channel sums of the CTA in a fixed order; thread ch < 64 gets (U, V)
+template <typename T>
+__device__ __forceinline__ float2 cl_wide_block_sum(float* u, float* v, float2 (*sm)[kClTile], const ClWideTile& t) {
+    using W = ClWide<T>;
+#pragma unroll
+    for (int off = W::LPR; off < 32; off <<= 1)
+#pragma unroll
+        for (int j = 0; j < W::CPL; ++j) {
+            u[j] += __shfl_xor_sync(0xffffffffu, u[j], off);
+            v[j] += __shfl_xor_sync(0xffffffffu, v[j], off);
+        }
+    if (t.rsub == 0)
+#pragma unroll
+        for (int j = 0; j < W::CPL; ++j) sm[t.warp][t.cg * W::CPL + j] = make_float2(u[j], v[j]);
+    __syncthreads();
+    float2 tot = make_float2(0.f, 0.f);
+    if (threadIdx.x < kClTile) {
+#pragma unroll
+        for (int w = 0; w < kClWarps; ++w) {
+            tot.x += sm[w][threadIdx.x].x;
+            tot.y += sm[w][threadIdx.x].y;
+        }
+    }
+    return tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kClThreads) micn_cl_fwd_stats_wide_kernel(const ClParams p) {
+    using W = ClWide<T>;
+    using V = VecT<T>;
+    __shared__ float2 sm[kClWarps][kClTile];
+    const ClWideTile t = cl_wide_tile<T>(p);
+    float s[W::CPL], q[W::CPL], K[W::CPL];
+#pragma unroll
+    for (int j = 0; j < W::CPL; ++j) s[j] = q[j] = K[j] = 0.f;
+    if (t.valid && t.r0 < t.r1) {
+        const T* px = reinterpret_cast<const T*>(p.x);
+        V::unpack(__ldg(reinterpret_cast<const uint4*>(px + (size_t)t.n * (size_t)p.M * (size_t)p.C +
+                                                       (size_t)t.r0 * (size_t)p.C + (size_t)t.c)), K);
+        cl_rows_wide<T, false>(p, t, p.x, nullptr, [&](long long, const uint4& xv, const uint4&) {
+            float f[W::CPL];
+            V::unpack(xv, f);
+#pragma unroll
+            for (int j = 0; j < W::CPL; ++j) {
+                const float d = f[j] - K[j];
+                s[j] += d;
+                q[j] = fmaf(d, d, q[j]);
+            }
+        });
+    }
+    const float2 tot = cl_wide_block_sum<T>(s, q, sm, t);
+    const long long ch = (long long)blockIdx.x * kClTile + threadIdx.x;
+    if (threadIdx.x < kClTile && ch < p.C) {
+        const float cnt = (float)(t.r1 > t.r0 ? t.r1 - t.r0 : 0);
+        float Kc = 0.f;
+        if (cnt > 0.f)
+            Kc = V::load1(reinterpret_cast<const T*>(p.x) + (size_t)t.n * (size_t)p.M * (size_t)p.C +
+                          (size_t)t.r0 * (size_t)p.C + (size_t)ch);
+        const float m = cnt > 0.f ? tot.x / cnt : 0.f;
+        p.ws_part[((size_t)t.n * p.MS + t.split) * (size_t)p.C + (size_t)ch] =
+            make_float4(cnt, Kc + m, fmaxf(tot.y - tot.x * m, 0.f), 0.f);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kClThreads) micn_cl_fwd_apply_wide_kernel(const ClParams p) {
+    using W = ClWide<T>;
+    using V = VecT<T>;
+    __shared__ float4 coef[32];  // (a0, b0, a1, b1) per channel pair
+    const ClTile t2 = cl_tile(p);  // the pair mapping, for the fold by warp 0
+    if (t2.warp == 0) {
+        float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t2.valid) {
+            const int style = load_style(p.styles, t2.n, p.num_styles, p.status);
+            const float4* part = p.ws_part + (size_t)t2.n * p.MS * (size_t)p.C + (size_t)t2.c;
+            float ab[4];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float2 st = cl_fold_stats(part + k, p.MS, (size_t)p.C, (float)p.M);
+                const float rstd = 1.f / sqrtf(st.y / (float)p.M + p.eps);
+                float gamma, beta;
+                load_affine(p, style, t2.c + k, gamma, beta);
+                const float a = rstd * gamma;
+                ab[2 * k] = a;
+                ab[2 * k + 1] = fmaf(-st.x, a, beta);
+                if (t2.split == 0 && p.save_mean) {
+                    p.save_mean[t2.n * p.C + t2.c + k] = st.x;
+                    p.save_rstd[t2.n * p.C + t2.c + k] = rstd;
+                }
+            }
+            cf = make_float4(ab[0], ab[1], ab[2], ab[3]);
+        }
+        coef[t2.lane] = cf;
+    }
+    __syncthreads();
+    const ClWideTile t = cl_wide_tile<T>(p);
+    if (!t.valid) return;
+    float ca[W::CPL], cb[W::CPL];
+#pragma unroll
+    for (int j = 0; j < W::CPL; ++j) {
+        const int ci = t.cg * W::CPL + j;
+        const float4 c4 = coef[ci >> 1];
+        ca[j] = (ci & 1) ? c4.z : c4.x;
+        cb[j] = (ci & 1) ? c4.w : c4.y;
+    }
+    T* py = reinterpret_cast<T*>(p.y);
+    const size_t base = (size_t)t.n * (size_t)p.M * (size_t)p.C + (size_t)t.c;
+    cl_rows_wide<T, false>(p, t, p.x, nullptr, [&](long long r, const uint4& xv, const uint4&) {
+        float f[W::CPL];
+        V::unpack(xv, f);
+#pragma unroll
+        for (int j = 0; j < W::CPL; ++j) f[j] = fmaf(f[j], ca[j], cb[j]);
+        *reinterpret_cast<uint4*>(py + base + (size_t)r * (size_t)p.C) = V::pack(f);
+    });
+}
+
 // ---------------------------------------------------------------- fused kernels: short columns (M <= kClFusedMaxRows)
 // The 25 ViT token norms of C-UNETR ([B,768,216]) and the deep PatchMerging norms ([1,1536,6^3], [1,3072,3^3]) are
 // launch-bound: one 32-warp CTA per (sample, 64-channel tile) reduces its columns and applies the result in the same

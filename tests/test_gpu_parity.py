@@ -284,7 +284,10 @@ def test_channels_last_input_native_and_reference_layout(pkg):
                                         ((3, 70, 5, 7, 3), "C70_ragged"), ((4, 768, 216), "vit_tokens"),
                                         ((2, 10, 4000), "long_columns"),
                                         ((1, 100, 3, 3, 3), "one_sample_27_rows_ragged_tile"),
-                                        ((1, 48, 1100), "one_sample_two_kernel_route")], ids=lambda v: v if isinstance(v, str) else None)
+                                        ((1, 48, 1100), "one_sample_two_kernel_route"),
+                                        ((2, 96, 2000), "wide_loads_two_samples"),
+                                        ((3, 136, 1500), "wide_loads_ragged_tile"),
+                                        ((2, 20, 1300), "wide_fp32_only_c20")], ids=lambda v: v if isinstance(v, str) else None)
 def test_channels_last_route_vs_oracle(pkg, shape, name, dtype):
     gen = torch.Generator().manual_seed(len(name))
     n, c = shape[0], shape[1]
