@@ -41,6 +41,29 @@ def test_library_loads_and_exports_every_header_symbol():
     assert lib.micn_set_option(b"no_such_option", 1) != 0
 
 
+def test_workspace_sizes_and_knobs_without_a_gpu():
+    """Pure host arithmetic of the C ABI: workspace sizes grow with the problem, carry the fixed prefix (header +
+    per-channel arrival counters) that lets one zero-filled workspace serve calls of any shape, and every knob the
+    tools and the docs name is accepted (read back, then restored)."""
+    lib = pkg._lib.lib()
+    prefix = 64 + 16384 * 4
+    small = lib.micn_workspace_bytes(1, 4, 27, 0, 2)
+    big = lib.micn_workspace_bytes(8, 384, 96 ** 3, 1, 2)
+    assert prefix <= small < big
+    assert lib.micn_workspace_bytes(0, 4, 27, 0, 2) >= 0 and lib.micn_workspace_bytes(1, 4, 27, 9, 2) == 0
+    assert lib.micn_cl_workspace_bytes(2, 768, 216) >= prefix + 2 * 768 * 8
+    assert lib.micn_host_scratch_bytes(1, 48, 96 ** 3, 1, 2, 1) > 4 * 48 * 96 ** 3 * 2
+    assert lib.micn_host_scratch_bytes(1, 48, 96 ** 3, 9, 2, 1) == 0
+    for knob in ("force_path", "flat_slots", "flat_slots_b", "flat_lag", "flat_l2_mb", "flat_piece_vecs", "flat_grid",
+                 "flat_min_bytes", "flat_shape_fwd", "flat_shape_bwd", "small_tps", "small_reg", "cl_wide",
+                 "host_groups", "host_taper", "host_trace", "cluster_size"):
+        before = lib.micn_get_option(knob.encode())
+        assert lib.micn_set_option(knob.encode(), 3) == 0, knob
+        assert lib.micn_get_option(knob.encode()) == 3
+        assert lib.micn_set_option(knob.encode(), before) == 0
+    assert lib.micn_get_option(b"launches") >= 0
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     L = importlib.import_module("mi-seg_b200._lib")
     monkeypatch.setattr(L, "_lib", None)
