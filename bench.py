@@ -163,7 +163,7 @@ def run_model_calls(pkg, dev, tdt, reps=20):
     """The hot path at model scale: every instance_cond call of one C-Swin-UNETR training step (forward + backward),
     timed as one sequence four ways: (1) raw C-ABI launches back to back from Python (host-bound for the small calls),
     (1b) the same launches replayed from a CUDA graph (what the GPU needs), (2) through the
-    drop-in nn.Module + autograd (what a training script calls; ~250 us of Python / autograd-engine time per call,
+    drop-in nn.Module + autograd (what a training script calls; ~190 us of Python / autograd-engine time per call,
     which a real step hides behind its convolutions), (3) the reference's call sequence (per-sample F.instance_norm
     + torch.stack) through PyTorch/ATen on the same GPU.  PatchMerging inputs arrive channels-last (stride_C = 1)."""
     import torch
