@@ -99,10 +99,11 @@ class FastForwardMixin:
         unbatched = input.dim() == self._get_no_batch_dim()
         x = input.unsqueeze(0) if unbatched else input
         host = _host_styles(styles, self.num_styles)
-        if x.shape[1] != self.norms[0].num_features:
+        first = self._modules["norms"]._modules["0"]  # (norms[0] without three trips through __getattr__ / __getitem__)
+        if x.shape[1] != first.num_features:
             # nn.InstanceNorm*d._check_input_dim's message (affine norms check the channel count)
             raise ValueError(f"expected input's size at dim=1 to match num_features "
-                             f"({self.norms[0].num_features}), but got: {x.shape[1]}.")
+                             f"({first.num_features}), but got: {x.shape[1]}.")
         m = 1
         for s in x.shape[2:]:
             m *= s
@@ -112,12 +113,12 @@ class FastForwardMixin:
             styles_dev = _device_styles(host, x.device)
             present = [s in host for s in range(self.num_styles)]
         else:
-            styles_dev = styles.reshape(-1).to(torch.int64)
+            styles_dev = styles if (styles.dim() == 1 and styles.dtype == torch.int64) else styles.reshape(-1).to(torch.int64)
             present = None  # unknown without a device sync: absent styles get zero grads instead of None
         if residual is not None and unbatched:
             residual = residual.unsqueeze(0)
         w, b = self._params()
-        y = instance_cond(x, styles_dev, w, b, eps=self.norms[0].eps, epilogue=epilogue, residual=residual,
+        y = instance_cond(x, styles_dev, w, b, eps=first.eps, epilogue=epilogue, residual=residual,
                           slope=slope, present=present)
         return y.squeeze(0) if unbatched else y
 
