@@ -104,3 +104,55 @@ def test_port_matches_f64_oracle():
 
 def test_lrelu_grad_at_zero_uses_slope():
     assert O.lrelu_grad(np.array([0.0]))[0] == O.LRELU_SLOPE
+
+
+def test_oracle_gradients_match_finite_differences_and_invariants():
+    """The closed-form backward of the oracle against central finite differences of its own forward (float64), for
+    the plain norm and both epilogues; plus the invariants of the math: sum(dx) = 0 and sum(dx * xhat) ~ 0 per slab
+    for the plain norm, and shift invariance of the output in x."""
+    rng = np.random.RandomState(3)
+    n, c, shape = 3, 4, (5, 3)
+    x = rng.randn(n, c, *shape) * 2 + 1
+    dy = rng.randn(n, c, *shape)
+    res = rng.randn(n, c, *shape)
+    gamma, beta = 1 + 0.3 * rng.randn(2, c), 0.3 * rng.randn(2, c)
+    styles = [1, 0, 1]
+
+    def fd(fn, v, h=1e-6):
+        g = np.zeros_like(v)
+        it = np.nditer(v, flags=["multi_index"])
+        for _ in it:
+            i = it.multi_index
+            vp, vm = v.copy(), v.copy()
+            vp[i] += h
+            vm[i] -= h
+            g[i] = (fn(vp) - fn(vm)) / (2 * h)
+        return g
+
+    # plain norm
+    y, mean, rstd = O.fwd_f64(x, styles, gamma, beta)
+    dx, dg, db, _ = O.bwd_f64(dy, x, styles, gamma, mean, rstd)
+    assert np.allclose(dx, fd(lambda v: float((O.fwd_f64(v, styles, gamma, beta)[0] * dy).sum()), x), atol=1e-6)
+    assert np.allclose(dg, fd(lambda g_: float((O.fwd_f64(x, styles, g_, beta)[0] * dy).sum()), gamma), atol=1e-6)
+    assert np.allclose(db, fd(lambda b_: float((O.fwd_f64(x, styles, gamma, b_)[0] * dy).sum()), beta), atol=1e-6)
+    xm = x.reshape(n, c, -1)
+    xhat = (xm - mean[:, :, None]) * rstd[:, :, None]
+    assert np.abs(dx.reshape(n, c, -1).sum(-1)).max() < 1e-12
+    # (zero only up to eps / var, because xhat is scaled by 1 / sqrt(var + eps), not 1 / sqrt(var))
+    assert np.abs((dx.reshape(n, c, -1) * xhat).sum(-1)).max() < 1e-4
+    # (shift invariance holds up to the eps inside the sqrt only when the spread is unchanged: exactly so for a shift)
+    assert np.allclose(O.fwd_f64(x + 123.0, styles, gamma, beta)[0], y, atol=1e-9)
+
+    # epilogues (inputs kept away from the LeakyReLU kink so the finite difference is well defined)
+    for has_res in (False, True):
+        r = res if has_res else None
+        out, pre, m_, r_ = O.fwd_epilogue_f64(x, styles, gamma, beta, residual=r)
+        assert np.abs(pre).min() > 1e-4
+        dxe, dre, dge, dbe, _ = O.bwd_epilogue_f64(dy, pre, x, styles, gamma, m_, r_, has_residual=has_res)
+        assert np.allclose(dxe, fd(lambda v: float((O.fwd_epilogue_f64(v, styles, gamma, beta, residual=r)[0] * dy).sum()), x),
+                           atol=1e-6)
+        assert np.allclose(dge, fd(lambda g_: float((O.fwd_epilogue_f64(x, styles, g_, beta, residual=r)[0] * dy).sum()),
+                                   gamma), atol=1e-6)
+        if has_res:
+            assert np.allclose(dre, fd(lambda v: float((O.fwd_epilogue_f64(x, styles, gamma, beta, residual=v)[0] * dy).sum()),
+                                       res), atol=1e-6)
