@@ -156,3 +156,23 @@ def test_oracle_gradients_match_finite_differences_and_invariants():
         if has_res:
             assert np.allclose(dre, fd(lambda v: float((O.fwd_epilogue_f64(x, styles, gamma, beta, residual=v)[0] * dy).sum()),
                                        res), atol=1e-6)
+
+
+def test_prelu_oracle_gradients_match_finite_differences():
+    """ADN "NDA" (acti_norm.py:104-110): prelu(norm(x)) with one learnable slope - dx and the slope gradient of the
+    oracle against central differences of its own forward."""
+    rng = np.random.RandomState(11)
+    x = rng.randn(2, 3, 7) * 1.5 - 0.5
+    dy = rng.randn(2, 3, 7)
+    gamma, beta = 1 + 0.3 * rng.randn(2, 3), 0.3 * rng.randn(2, 3)
+    styles, a, h = [0, 1], 0.25, 1e-6
+    out, pre, mean, rstd = O.fwd_prelu_f64(x, styles, gamma, beta, a)
+    assert np.abs(pre).min() > 1e-4
+    dx, dg, db, da, _ = O.bwd_prelu_f64(dy, pre, x, styles, gamma, mean, rstd, a)
+    loss = lambda xv, av: float((O.fwd_prelu_f64(xv, styles, gamma, beta, av)[0] * dy).sum())
+    assert abs(da - (loss(x, a + h) - loss(x, a - h)) / (2 * h)) < 1e-6
+    for i in [(0, 0, 0), (1, 2, 6), (0, 1, 3)]:
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h
+        xm[i] -= h
+        assert abs(dx[i] - (loss(xp, a) - loss(xm, a)) / (2 * h)) < 1e-6
