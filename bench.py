@@ -13,9 +13,17 @@ Prints ONE JSON line (rank 0):
             H2D / D2H inside the timed region)
   roofline  the dominant kernel (backward: 3 * E * s bytes per launch, average duration over a region of
             back-to-back launches of that kernel, CUDA events on its stream) against MEASURED_PEAKS.json
-  cpu_baseline  the oracle's torch-CPU port of the reference call sequence on the box's host cores
-`--impl reference` times that CPU port alone (the reference's own path: per-sample F.instance_norm +
-torch.stack + autograd) on the same config.
+  cpu_baseline  the reference's own ConditionalInstanceNorm3d (unmodified, from the git-ignored copy oracle/_ref/ that
+            baseline/make_ref.py makes; kind "reference") on the box's host cores; the oracle's torch-CPU port of the same
+            call sequence (kind "port") only when that copy is absent
+`--impl reference` times that CPU module alone on the same config.
+
+Timing of `value`: the clocks sampler starts, then an untimed pre-warm of >= 50 steps (more with --warmup) brings the GPU
+to its load clocks, then `--regions` (default 5) timed regions of EXACTLY --steps steps each, every one bracketed by a
+barrier + synchronize and CUDA events, max over ranks per region; the MEDIAN region is reported (all of them are listed
+under "regions_ms").  Extra keys: model-level steps of the reference's own nets ("model_step": C-Swin-UNETR B=1/GPU,
+DDP over NCCL for N > 1; C-UNETR B=4 and the C-UNet CPU config at N=1) and the sharded sliding-window volume
+("sliding_window", BASELINE.json configs[4]) - see baseline/model_bench.py.
 """
 from __future__ import annotations
 
@@ -51,6 +59,12 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
     ap.add_argument("--no-model-calls", action="store_true", help="skip the C-Swin-UNETR norm-call-list leg")
+    ap.add_argument("--regions", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
+    ap.add_argument("--launch", default="stream", choices=["stream", "graph"],
+                    help="stream: the C-ABI calls are issued every step; graph: one step per buffer set captured once and replayed")
+    ap.add_argument("--model-steps", default="auto", help="comma list of swin_unetr,unetr,unet_cpu,sliding_window; auto = "
+                    "swin_unetr + sliding_window at every N, plus unetr and unet_cpu at N=1; none = skip")
+    ap.add_argument("--model-step-iters", type=int, default=8)
     ap.add_argument("--sweep", action="store_true", help="also time the BASELINE.json microbench sweep (extra key)")
     ap.add_argument("--sweep-out", default=None, help="append every sweep point to this file as JSON lines")
     return ap.parse_args()
@@ -379,13 +393,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU port (reference arm / cpu_baseline)
-def cpu_port_time(n, c, s, dtype_name, budget_s, warmup, steps=None):
-    """The reference's call sequence (per-sample F.instance_norm + torch.stack, autograd backward) on the host
-    cores, through oracle.port_fwd_bwd.  Returns (seconds per fwd+bwd, iterations, cores)."""
-    import torch
+# ------------------------------------------------------------------------------------------------ CPU reference (reference arm / cpu_baseline)
+def workload_config(n, c, s, dtype_name, world, epilogue="none"):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": f"instance_cond fwd+bwd, {n}x{c}x{s}^3 {dtype_name} per GPU (C-Swin-UNETR f=48 encoder1 norm; "
+                        f"BASELINE.json configs[1] hot path), epilogue={epilogue}",
+            "global_batch": n * world, "parallelism": f"dp{world}"}
 
-    from oracle import micn_oracle as O
+
+def load_reference_module():
+    """The reference's own hot-path module, unmodified: the git-ignored copy oracle/_ref/conditional_instance_norm.py
+    (baseline/make_ref.py copies it from /root/reference/networks/norms/ in the build container; it needs only torch and
+    travels to the GPU box with the snapshot).  None when the copy is absent."""
+    import importlib.util
+
+    path = os.path.join(ROOT, "oracle", "_ref", "conditional_instance_norm.py")
+    if not os.path.isfile(path):
+        return None
+    spec = importlib.util.spec_from_file_location("micn_reference_conditional_instance_norm", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_time(n, c, s, dtype_name, budget_s, warmup, steps=None):
+    """Forward + autograd backward of the reference's ConditionalInstanceNorm3d (conditional_instance_norm.py:59-68) on
+    the host cores, all threads; falls back to the oracle's torch-CPU port of the same call sequence (per-sample
+    F.instance_norm + torch.stack) when oracle/_ref is absent.  Returns (seconds per fwd+bwd, iterations, cores, kind)."""
+    import torch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -396,20 +431,40 @@ def cpu_port_time(n, c, s, dtype_name, budget_s, warmup, steps=None):
     w = [1 + 0.3 * torch.randn(c, generator=g) for _ in range(2)]
     b = [0.3 * torch.randn(c, generator=g) for _ in range(2)]
     styles = [i % 2 for i in range(n)]
+    ref = load_reference_module()
+    if ref is not None:
+        kind = "reference"
+        mod = ref.ConditionalInstanceNorm3d(num_styles=2, num_features=c)
+        with torch.no_grad():
+            for k in range(2):
+                mod.norms[k].weight.copy_(w[k])
+                mod.norms[k].bias.copy_(b[k])
+        xr = x.clone().requires_grad_(True)
+
+        def one():
+            xr.grad = None
+            mod.zero_grad(set_to_none=True)
+            mod(xr, styles).backward(dy)
+    else:
+        kind = "port"
+        from oracle import micn_oracle as O
+
+        def one():
+            O.port_fwd_bwd(x, dy, styles, w, b)
     for _ in range(max(1, warmup)):
-        O.port_fwd_bwd(x, dy, styles, w, b)
+        one()
     times = []
     t_start = time.perf_counter()
     while True:
         t0 = time.perf_counter()
-        O.port_fwd_bwd(x, dy, styles, w, b)
+        one()
         times.append(time.perf_counter() - t0)
         if steps is not None:
             if len(times) >= steps:
                 break
         elif len(times) >= 3 and time.perf_counter() - t_start > budget_s:
             break
-    return sum(times) / len(times), len(times), cores
+    return sum(times) / len(times), len(times), cores, kind
 
 
 def run_reference(args):
@@ -418,21 +473,60 @@ def run_reference(args):
         return
     n, c, s, m = workload(args)
     es = DT_BYTES[args.dtype]
-    steps = min(args.steps, 40)  # bounded sample: each step is one full fwd+bwd of the workload on the CPU
-    sec, iters, cores = cpu_port_time(n, c, s, args.dtype, 0, min(args.warmup, 3), steps=steps)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps = min(args.steps, 100)  # bounded sample: each step is one full fwd+bwd of the workload on the CPU (~30 ms)
+    sec, iters, cores, kind = cpu_reference_time(n, c, s, args.dtype, 0, min(args.warmup, 20), steps=steps)
     gbps = 5.0 * n * c * m * es / sec / 1e9
+    what = ("the reference's unmodified ConditionalInstanceNorm3d (oracle/_ref copy) forward + autograd backward"
+            if kind == "reference" else "the oracle's torch-CPU port of the reference call sequence")
     line = {
         "impl": "reference", "metric": METRIC, "value": gbps, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
-        "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": min(args.warmup, 20), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"instance_cond fwd+bwd {n}x{c}x{s}^3 {args.dtype} (C-Swin-UNETR encoder1 norm), "
-                               "reference call sequence on host CPU"},
-        "cpu_baseline": {"value": gbps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{iters} full fwd+bwd passes of the workload, torch CPU, {cores} threads"},
+        "config": workload_config(n, c, s, args.dtype, world, args.epilogue),
+        "cpu_baseline": {"value": gbps, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{iters} full fwd+bwd passes of the workload on the host CPU, {cores} threads: {what}"},
         "e2e": {"value": gbps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "voxels_per_s": n * m / sec,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ model-level legs
+def run_model_legs(args, pkg, dev, world, rank):
+    """BASELINE.json metric, second half ("C-SwinUNETR voxels/s @1-8 GPU") and configs[0], [2], [4]: whole steps of the
+    reference's own nets, reference norms vs this repo's drop-in, on the same GPU(s).  Returns extra keys for the line."""
+    which = args.model_steps
+    if which == "none":
+        return {}
+    if which == "auto":
+        legs = ["swin_unetr", "sliding_window"] + (["unetr", "unet_cpu"] if world == 1 else [])
+    else:
+        legs = [w for w in which.split(",") if w]
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import model_bench as MB
+    except Exception as e:  # noqa: BLE001
+        return {"model_step": {"unavailable": repr(e)[:300]}}
+    if not MB.reference_available():
+        return {"model_step": {"unavailable": "no importable copy of the reference's networks/ package (baseline/_ref "
+                                              "is made by baseline/make_ref.py where /root/reference exists)"}}
+    out = {}
+    K, W = args.model_step_iters, 3
+    try:
+        if "swin_unetr" in legs:
+            out["model_step"] = MB.model_step_leg("swin_unetr", pkg, dev, world, rank, K, W, batch=1)
+        if "unetr" in legs:
+            out["model_step_unetr"] = MB.model_step_leg("unetr", pkg, dev, world, rank, K, W, batch=4)
+        if "unet" in legs:
+            out["model_step_unet"] = MB.model_step_leg("unet", pkg, dev, world, rank, K, W, batch=1)
+        if "sliding_window" in legs:
+            out["sliding_window"] = MB.sliding_window_leg(pkg, dev, world, rank)
+        if "unet_cpu" in legs and rank == 0:
+            out["model_step_unet_cpu"] = MB.unet_cpu_leg()
+    except Exception as e:  # noqa: BLE001 - the headline line must survive a failing extra leg
+        out["model_legs_error"] = repr(e)[:400]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -526,32 +620,83 @@ def run_ours(args):
 
     for i in range(R):  # statistics for every set
         fwd(i)
-    for i in range(args.warmup):
+    torch.cuda.synchronize()
+
+    # ---- N > 1: prove once that the collective delivers the right numbers (sum over ranks of the rank-local dgamma/dbeta)
+    allreduce_check = None
+    if world > 1:
+        bwd(0, grads2[0])
+        local = grads2[0].clone()
+        dist.all_reduce(grads2[0])
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        expect = torch.stack(parts).double().sum(0)
+        allreduce_check = float((grads2[0].double() - expect).abs().max() / expect.abs().max())
+        if not allreduce_check < 5e-3:
+            raise RuntimeError(f"all-reduced dgamma/dbeta differ from the sum of the rank-local gradients: {allreduce_check}")
+
+    # ---- optional: one step per buffer set captured into a CUDA graph and replayed (what a captured training step does)
+    graphs = None
+    bwd(0, grads2[0])  # (first launch of every kernel outside any capture: function attributes are set once)
+    if args.launch == "graph":
+        if world > 1:
+            raise SystemExit("bench.py: --launch graph is a single-GPU option (the collective is issued from the host)")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graphs = []
+        with torch.cuda.stream(side):
+            stream = side.cuda_stream
+            for i in range(R):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=side):
+                    fwd(i % R)
+                    bwd((i + 1) % R, grads2[i & 1])
+                graphs.append(g_)
+        torch.cuda.current_stream().wait_stream(side)
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def step(i):  # noqa: F811 - replaces the stream-launch step
+            graphs[i % R].replay()
+
+    sampler = ClockSampler(local)
+    if rank == 0:  # BEFORE the pre-warm: nvidia-smi takes ~0.2 s to produce its first sample
+        sampler.start()
+        time.sleep(0.25)
+    # untimed pre-warm, independent of --warmup: the GPU drops to its idle clocks within a fraction of a second of
+    # inactivity (the sampler start above is one), and a 20-step region lasts 1.7 ms - shorter than the clock ramp
+    prewarm = max(50, args.warmup, 10 * args.steps)
+    for i in range(prewarm):
         step(i)
     drain()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:  # BEFORE the barrier: a rank that starts late would be waited for inside the others' timed region
-        sampler.start()
-        time.sleep(0.25)
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    launches0 = pkg._lib.get_option("launches")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_region = None
+    region_ms = []
     t_wall0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    drain()  # every step's collective completes inside the timed region
-    e1.record()
-    torch.cuda.synchronize()
-    t_wall1 = time.perf_counter()
-    if world > 1:
-        dist.barrier()
+    for r in range(max(1, args.regions)):
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-    launches = pkg._lib.get_option("launches") - launches0
-    ms_total = e0.elapsed_time(e1)
+        launches0 = pkg._lib.get_option("launches")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        drain()  # every step's collective completes inside the timed region
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        region_ms.append(e0.elapsed_time(e1))
+        if launches_region is None:
+            launches_region = (pkg._lib.get_option("launches") - launches0) if graphs is None else 2 * args.steps
+    t_wall1 = time.perf_counter()
+    launches = launches_region
+    if world > 1:  # max over ranks, per region
+        t = torch.tensor(region_ms, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_ms = [float(v) for v in t.tolist()]
+    ms_total = statistics.median(region_ms)
 
     # per-kernel durations (roofline), same loop with an event after every launch
     K2 = min(args.steps, 200)
@@ -585,10 +730,6 @@ def run_ours(args):
     t_region_end = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_region_end) if rank == 0 else None
 
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9
 
@@ -666,6 +807,9 @@ def run_ours(args):
         torch_gpu = {"ms_per_step": ms, "value": (bytes_fwd + bytes_bwd) / (ms * 1e-3) / 1e9, "unit": UNIT,
                      "what": "per-sample F.instance_norm + torch.stack + autograd on the same GPU (PyTorch/ATen)"}
 
+    # ---- model-level legs (every rank takes part: DDP / sharded windows); see baseline/model_bench.py
+    model_legs = run_model_legs(args, pkg, dev, world, rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -694,31 +838,37 @@ def run_ours(args):
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        sec, iters, cores = cpu_port_time(n, c, s, args.dtype, 10.0, 1)
-        cpu_baseline = {"value": 5.0 * E * es / sec / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+        sec, iters, cores, kind = cpu_reference_time(n, c, s, args.dtype, 10.0, 1)
+        cpu_baseline = {"value": 5.0 * E * es / sec / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                         "ms_per_step": sec * 1e3,
-                        "sample": f"{iters} full fwd+bwd passes of the same {n}x{c}x{s}^3 {args.dtype} workload "
-                                  f"(reference call sequence on torch CPU, {cores} threads)"}
+                        "sample": f"{iters} full fwd+bwd passes of the same {n}x{c}x{s}^3 {args.dtype} workload on the host "
+                                  f"CPU, {cores} threads (" + ("the reference's unmodified ConditionalInstanceNorm3d, "
+                                  "oracle/_ref copy" if kind == "reference" else "the oracle's torch-CPU port of the "
+                                  "reference call sequence") + ")"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic",
-        "config": {"workload": f"instance_cond fwd+bwd, {n}x{c}x{s}^3 {args.dtype} per GPU (C-Swin-UNETR f=48 encoder1 "
-                               f"norm; BASELINE.json configs[1] hot path), epilogue={args.epilogue}",
-                   "global_batch": n * world, "parallelism": f"dp{world}",
-                   "l2": f"{R} rotating buffer sets ({R * 4 * E * es / 1e6:.0f} MB) > 126 MB L2; backward reads a "
-                         "different set than the forward before it",
-                   "collective": ("all_reduce(dgamma,dbeta) per step over NCCL, overlapped with the next step's kernels "
-                                  "(double-buffered buckets, waited before reuse and before the clock stops; "
-                                  "147 of 148 SMs run the norm kernels, one is left to NCCL)" if overlap else
-                                  "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none")},
+        "config": workload_config(n, c, s, args.dtype, world, args.epilogue),
+        "notes": {"l2": f"{R} rotating buffer sets ({R * 4 * E * es / 1e6:.0f} MB) > 126 MB L2; backward reads a "
+                        "different set than the forward before it",
+                  "collective": ("all_reduce(dgamma,dbeta) per step over NCCL, overlapped with the next step's kernels "
+                                 "(double-buffered buckets, waited before reuse and before the clock stops; "
+                                 "147 of 148 SMs run the norm kernels, one is left to NCCL)" if overlap else
+                                 "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none"),
+                  "launch": args.launch,
+                  "timing": f"{prewarm} untimed pre-warm steps, then {len(region_ms)} regions of {args.steps} steps "
+                            "(CUDA events, barrier + synchronize on both sides, max over ranks per region); "
+                            "ms_per_step = median region / steps"},
+        "regions_ms": region_ms, "allreduce_check_rel_err": allreduce_check,
         "voxels_per_s": world * n * m / (ms_step * 1e-3),
         "frac_of_peak": value / world / peak,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "torch_gpu_reference": torch_gpu,
         "plan": {k: pkg._lib.get_option(k) for k in ("last_path", "last_cs", "last_slots", "last_grid")},
     }
+    line.update(model_legs)
     if world == 1 and not args.no_model_calls:
         line["swin_unetr_norm_calls"] = run_model_calls(pkg, dev, tdt)
         line["next_rows"] = run_next_rows(pkg, dev, tdt, n, c, s, peak)

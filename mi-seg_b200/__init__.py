@@ -11,10 +11,11 @@ from .functional import instance_cond, reset_workspaces, set_channels_last_nativ
 from .inference import sliding_window_inference, window_slices
 from .integration import convert_module, convert_plain, install, install_plain, uninstall
 from .norms import (FastConditionalInstanceNorm1d, FastConditionalInstanceNorm2d, FastConditionalInstanceNorm3d,
-                    FastInstanceNorm1d, FastInstanceNorm2d, FastInstanceNorm3d, fast_instance_norm, make_dropin_classes)
+                    FastInstanceNorm1d, FastInstanceNorm2d, FastInstanceNorm3d, check_status, fast_instance_norm,
+                    make_dropin_classes, set_sync_free_styles)
 
 __all__ = ["instance_cond", "reset_workspaces", "install", "install_plain", "uninstall", "convert_module",
            "convert_plain", "fuse_blocks", "FastInstanceNorm1d", "FastInstanceNorm2d", "FastInstanceNorm3d",
            "fast_instance_norm", "set_channels_last_native", "sliding_window_inference", "window_slices",
            "FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
-           "make_dropin_classes", "_lib"]
+           "make_dropin_classes", "set_sync_free_styles", "check_status", "_lib"]

@@ -63,6 +63,7 @@ struct Options {
     std::atomic<long long> flat_grid{-1};     // cap on the persistent grid
     std::atomic<long long> flat_ovh_vecs{-1}; // planner: per-piece overhead in vector-equivalents
     std::atomic<long long> flat_coop{-1};     // 0: plain launch instead of a cooperative one (experiments)
+    std::atomic<long long> flat_refuse{-1};   // 1: behave as if the cooperative launch had been refused (tests the fallback chain)
     std::atomic<long long> flat_trace_which{0};  // 0 both, 1 forward only, 2 backward only
     std::atomic<long long> flat_trace{0};     // bring-up: device pointer of a [grid][64][16] int64 trace buffer
     std::atomic<long long> slots{-1};         // force ring slots S
@@ -92,7 +93,7 @@ const OptName kOptNames[] = {
     {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
-    {"flat_coop", &g_opt.flat_coop},       {"flat_trace", &g_opt.flat_trace},
+    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"flat_trace", &g_opt.flat_trace},
     {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
     {"flat_shape_fwd", &g_opt.flat_shape_fwd}, {"flat_shape_bwd", &g_opt.flat_shape_bwd}, {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
@@ -480,11 +481,12 @@ int flat_run(KernelT kernel, int NS, int NSB, const P& p, long long slabs, long 
     fpl.g.ws_slab = ws_flat->slab;
     fpl.g.ws_ctl = ws_flat->ctl;
     record_flat(fpl);
-    const int lrc = launch_flat<TR>(kernel, p, fpl, st);
+    const int lrc = g_opt.flat_refuse.load() == 1 ? (int)cudaErrorCooperativeLaunchTooLarge : launch_flat<TR>(kernel, p, fpl, st);
     // a device that cannot hold the whole persistent grid right now (MPS share, another resident kernel) refuses
     // the cooperative launch: take the cluster / small path instead of failing the call
     if (lrc != (int)cudaErrorCooperativeLaunchTooLarge) return lrc;
     cudaGetLastError();
+    g_opt.launches.fetch_sub(1);  // (record_flat counted a launch that did not happen)
     return kFlatNotTaken;
 }
 
@@ -731,7 +733,7 @@ const char* micn_error_string(int code) {
         case MICN_ERR_BAD_DTYPE: return "micn: unsupported dtype (fp32, bf16, fp16 only)";
         case MICN_ERR_TOO_MANY_STYLES: return "micn: num_styles exceeds MICN_MAX_STYLES";
         case MICN_ERR_WORKSPACE: return "micn: workspace missing or too small";
-        case MICN_ERR_UNALIGNED: return "micn: pointer not aligned to the element size";
+        case MICN_ERR_UNALIGNED: return "micn: pointer not sufficiently aligned (element size; two elements for the channels-last calls; 16 bytes for the workspace)";
         case MICN_ERR_NO_DEVICE: return "micn: no usable CUDA device";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -993,6 +995,8 @@ int micn_fwd_cl(const void* x, void* y, const float* const* gamma, const float* 
     if (!x || !y || (C & 1) || N > 65535) return MICN_ERR_BAD_ARG;
     if (num_styles < 1) return MICN_ERR_BAD_ARG;
     if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    // the kernels load channel PAIRS (32-bit for 16-bit types, 64-bit for fp32)
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & (uintptr_t)(2 * es - 1)) return MICN_ERR_UNALIGNED;
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
     if (rc) return rc;
@@ -1037,8 +1041,9 @@ int micn_bwd_cl(const void* dy, const void* x, const float* const* gamma, const 
         return MICN_OK;
     }
     if (!x || !dy || !dx || !save_mean || !save_rstd || (C & 1) || N > 65535) return MICN_ERR_BAD_ARG;
-    if (num_styles < 1) return MICN_ERR_BAD_ARG;
-    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) &
+        (uintptr_t)(2 * es - 1))
+        return MICN_ERR_UNALIGNED;
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
     if (rc) return rc;

@@ -163,17 +163,22 @@ class _InstanceCondFn(torch.autograd.Function):
         rstd_p = mean_p + 4 * n * c
         res = None
         if epilogue == _lib.EPI_ADD_LRELU:
-            if residual is None or residual.shape != xs.shape or residual.dtype != xs.dtype:
-                raise ValueError("instance_cond: add_lrelu needs a residual of the input's shape and dtype")
-            res = residual.contiguous()
+            if residual is None or residual.shape != xs.shape:
+                raise ValueError("instance_cond: add_lrelu needs a residual of the input's shape")
+            # Under autocast the block input can be fp32 while conv2's output is 16-bit (layer_norm is on autocast's
+            # fp32 list, so C-Swin-UNETR's hidden states reach encoder2/3/4/10 in fp32).  The reference's in-place
+            # `out += residual` (dynunet_block.py:123) rounds the sum to out's dtype; so does this.
+            res = residual.contiguous() if residual.dtype == xs.dtype else residual.to(xs.dtype).contiguous()
         stream = _raw_stream(dev)
         ws = _workspace(dev, stream, n, c, m, _DTYPES[xs.dtype], num_styles)
         with _on_device(dev):
             gp = _ptr_array(weights) if affine else None
             bp = _ptr_array(biases) if affine else None
             slope_t = _slope_tensor(slope, dev)
-            if slope_t is not None and epilogue == _lib.EPI_NONE:
-                raise ValueError("instance_cond: a PReLU slope needs the 'lrelu' or 'add_lrelu' epilogue")
+            if slope_t is not None and epilogue != _lib.EPI_LRELU:
+                # (with a residual the sign of the pre-activation cannot be recovered from the output for a slope <= 0,
+                # and MI-Seg has no prelu(norm(x) + r): C-UNet adds its residual AFTER the activation, convolutions.py:329)
+                raise ValueError("instance_cond: a PReLU slope (tensor) needs the 'lrelu' epilogue")
             if slope_t is None:
                 rc = lib.micn_fwd(xs.data_ptr(), y.data_ptr(), res.data_ptr() if res is not None else None, gp, bp,
                                   num_styles, styles_dev.data_ptr() if styles_dev is not None else None,
@@ -188,14 +193,15 @@ class _InstanceCondFn(torch.autograd.Function):
         keep_y = epilogue == _lib.EPI_ADD_LRELU  # (its LeakyReLU mask, and with a PReLU slope its gradient, come from y)
         ctx.save_for_backward(xs, styles_dev, stats, y if keep_y else None, slope_t, *weights, *biases)
         ctx.meta = (n, c, m, sn, sc, epilogue, None if slope_t is not None else float(slope), num_styles, affine, present,
-                    residual is not None and epilogue == _lib.EPI_ADD_LRELU)
+                    residual.dtype if (residual is not None and epilogue == _lib.EPI_ADD_LRELU) else None)
         ctx.slope_shape = tuple(slope.shape) if slope_t is not None else None
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        n, c, m, sn, sc, epilogue, slope, num_styles, affine, present, has_res = ctx.meta
+        n, c, m, sn, sc, epilogue, slope, num_styles, affine, present, res_dtype = ctx.meta
+        has_res = res_dtype is not None
         xs, styles_dev, stats, act_out, slope_t, *params = ctx.saved_tensors
         weights, biases = params[:num_styles], params[num_styles:]
         lib = _lib.lib()
@@ -235,12 +241,8 @@ class _InstanceCondFn(torch.autograd.Function):
         dslope = None
         if want_ds and ds_part is not None:
             dslope = ds_part.sum().reshape(ctx.slope_shape)
-        elif want_ds:
-            # add_lrelu: d/da prelu(v) = v where v < 0, and there y = a * v:  sum dy * v = sum_{y<0} dy * y / a
-            # (sign(y) = sign(v) needs a > 0, which holds for the 0.25-initialised slopes of MI-Seg's nets)
-            yf, gf = act_out.float(), dy.float()
-            num = torch.where(yf < 0, gf * yf, torch.zeros((), device=dev)).sum()
-            dslope = torch.where(slope_t != 0, num / slope_t, torch.zeros_like(slope_t)).reshape(ctx.slope_shape)
+        if dres is not None and res_dtype != dres.dtype:
+            dres = dres.to(res_dtype)
         grads: List[Optional[torch.Tensor]] = [dx, None, dres, None, None, dslope, None, None]
         if affine:
             if pgrads is None:
@@ -268,6 +270,8 @@ def set_channels_last_native(enabled: bool) -> None:
 def _channels_last_view(x: torch.Tensor) -> Optional[torch.Tensor]:
     """x as a dense [N, *spatial, C] tensor if it is laid out that way (and worth it), else None."""
     if not _cl_native or x.dim() < 3 or x.shape[1] < 2 or (x.shape[1] & 1) or x.stride(1) != 1 or x.shape[0] > 65535:
+        return None
+    if x.data_ptr() % (2 * x.element_size()):  # the kernels load channel pairs: an odd storage offset takes the copy route
         return None
     perm = [0] + list(range(2, x.dim())) + [1]
     v = x.permute(perm)
@@ -373,6 +377,12 @@ def instance_cond(x: torch.Tensor, styles_dev: Optional[torch.Tensor], weights: 
             raise ValueError("instance_cond: styles must be an int64 tensor [N] on the input's device")
         if styles_dev.dim() != 1 or not styles_dev.is_contiguous():
             styles_dev = styles_dev.reshape(-1).contiguous()
+    if present is not None and len(weights):
+        # Parameters of styles absent from the batch stay OUT of the autograd graph, as in the reference (whose loop never
+        # calls their nn.InstanceNorm, conditional_instance_norm.py:60): `.grad` stays None, and DDP's
+        # find_unused_parameters=True (tune.py:103-109) sees them as unused instead of waiting for a hook that never fires.
+        weights = [w if p else w.detach() for w, p in zip(weights, present)]
+        biases = [b if p else b.detach() for b, p in zip(biases, present)]
     if epilogue == "none" and x.is_cuda and x.dtype in _DTYPES:
         x_cl = _channels_last_view(x)
         if x_cl is not None:  # token-major input: reduce the strided columns in place, keep the layout

@@ -88,11 +88,15 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Union[int, Sequence
     mine = list(range(rank, total, world))
 
     mods = None
+    mods_host: Optional[List[int]] = None
     if modalities is not None:
         mods = modalities if isinstance(modalities, torch.Tensor) else torch.as_tensor(list(modalities))
         mods = mods.reshape(-1)
         if mods.numel() != batch:
             raise ValueError("Expected number of styles as batch size.")  # the norm's own message
+        if not (mods.is_cuda and torch.cuda.is_current_stream_capturing()):
+            mods_host = [int(v) for v in mods.tolist()]  # ONE read-back per volume (the fast norms would otherwise read
+                                                         # back every window batch's modality tensor, norms.py)
 
     out_sum: Optional[torch.Tensor] = None
     count = torch.zeros((batch, 1) + size, dtype=torch.float32, device=inputs.device)
@@ -101,7 +105,13 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Union[int, Sequence
         where = [(i // len(slices), slices[i % len(slices)]) for i in idx]
         windows = torch.cat([inputs[(slice(b, b + 1), slice(None)) + sl] for b, sl in where])
         if mods is not None:
-            wmods = mods[torch.as_tensor([b for b, _ in where], device=mods.device)]  # one modality per WINDOW
+            if mods_host is not None:  # one modality per WINDOW; the host copy rides along (norms._cuda_styles_on_host)
+                hv = [mods_host[b] for b, _ in where]
+                wmods = torch.tensor(hv, dtype=mods.dtype, device=mods.device)
+                if wmods.is_cuda:
+                    wmods._micn_host = (wmods._version, hv)
+            else:
+                wmods = mods[torch.as_tensor([b for b, _ in where], device=mods.device)]
             prob = predictor(windows, modalities=wmods)
         else:
             prob = predictor(windows)

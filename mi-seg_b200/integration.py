@@ -50,17 +50,53 @@ def uninstall():
         plain = (nn.InstanceNorm1d, nn.InstanceNorm2d, nn.InstanceNorm3d)
         _installed_plain.Norm.add_factory_callable("instance", lambda dim: plain[dim - 1])
         _installed_plain = None
+    while _patched_functional:
+        mod, real = _patched_functional.pop()
+        mod.F = real
 
 
-def install_plain(factories_module: str = "networks.layers.factories"):
+class _FunctionalProxy:
+    """`torch.nn.functional` as seen by ONE reference module (networks/nets/swin_transformer.py:6 `import
+    torch.nn.functional as F`): everything forwards to torch, except `instance_norm` with batch statistics, which runs
+    on the sm_100a kernels (SwinTransformer.proj_out, swin_transformer.py:135-136: `F.instance_norm(x)` on the five
+    hidden states of every forward)."""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def instance_norm(self, input, running_mean=None, running_var=None, weight=None, bias=None,
+                      use_input_stats=True, momentum=0.1, eps=1e-5):
+        if running_mean is not None or running_var is not None or not use_input_stats or input.dim() < 3:
+            return self._real.instance_norm(input, running_mean, running_var, weight, bias, use_input_stats, momentum, eps)
+        return norms.fast_instance_norm(input, weight, bias, eps)  # (CUDA only: raises for CPU tensors)
+
+
+_patched_functional = []
+
+
+def install_plain(factories_module: str = "networks.layers.factories",
+                  functional_users=("networks.nets.swin_transformer",)):
     """also route the decoders' plain `("instance", {"affine": True})` norms
     (factories.py:221-224 -> nn.InstanceNorm{1,2,3}d) through the same kernels.  The fast classes derive from
-    torch's, so `isinstance(m, nn.InstanceNorm3d)` and every state-dict key stay as they were."""
+    torch's, so `isinstance(m, nn.InstanceNorm3d)` and every state-dict key stay as they were.  The modules named in
+    `functional_users` get their `F` rebound to a proxy whose `instance_norm` is the fast one (`proj_out`)."""
     global _installed_plain
     factories = importlib.import_module(factories_module)
     classes = (norms.FastInstanceNorm1d, norms.FastInstanceNorm2d, norms.FastInstanceNorm3d)
     factories.Norm.add_factory_callable("instance", lambda dim: classes[dim - 1])
     _installed_plain = factories
+    for name in functional_users or ():
+        try:
+            mod = importlib.import_module(name)
+        except Exception:  # noqa: BLE001 - a net that is not importable here simply is not patched
+            continue
+        real = getattr(mod, "F", None)
+        if real is not None and not isinstance(real, _FunctionalProxy):
+            mod.F = _FunctionalProxy(real)
+            _patched_functional.append((mod, real))
     return classes
 
 

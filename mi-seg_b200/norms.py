@@ -24,15 +24,47 @@ from .functional import instance_cond
 
 __all__ = ["FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
            "FastForwardMixin", "make_dropin_classes", "FastInstanceNorm1d", "FastInstanceNorm2d", "FastInstanceNorm3d",
-           "FastPlainForwardMixin", "fast_instance_norm"]
+           "FastPlainForwardMixin", "fast_instance_norm", "set_sync_free_styles", "check_status"]
 
 _STYLE_CACHE = {}
 _STYLE_CACHE_MAX = 256
+_sync_free_styles = False
+
+
+def set_sync_free_styles(enabled: bool) -> None:
+    """How a CUDA `styles` tensor is handled.
+
+    Default (False): its values are read back ONCE per tensor object (one `.tolist()`, cached on the tensor and
+    reused by every norm of the model that receives the same object - MI-Seg hands one `modality.to(device)` tensor
+    to all of them, utils/trainer.py:31,35; the reference itself syncs B times per norm call,
+    conditional_instance_norm.py:60).  With the values on the host the module behaves exactly like the reference:
+    an out-of-range id raises IndexError, and styles absent from the batch keep `.grad is None` (so AdamW neither
+    decays nor moves them).
+
+    True: never sync (needed while capturing a CUDA graph, where it is also selected automatically).  Ids are then
+    read by the kernels; an out-of-range id is clamped and flagged in the workspace status word (`check_status()`
+    raises for it), and absent styles receive ZERO gradients instead of None."""
+    global _sync_free_styles
+    _sync_free_styles = bool(enabled)
+
+
+def _cuda_styles_on_host(styles: Tensor) -> Optional[List[int]]:
+    if _sync_free_styles or torch.cuda.is_current_stream_capturing():
+        return None
+    cached = getattr(styles, "_micn_host", None)
+    if cached is not None and cached[0] == styles._version:
+        return cached[1]
+    vals = [int(v) for v in styles.reshape(-1).tolist()]  # the one device sync per modality tensor
+    try:
+        styles._micn_host = (styles._version, vals)
+    except Exception:  # noqa: BLE001 - a tensor type without a __dict__: just do not cache
+        pass
+    return vals
 
 
 def _host_styles(styles, num_styles: int) -> Optional[List[int]]:
-    """Styles as a list of python ints when they are visible on the host without a device sync
-    (list / int / CPU tensor); None for CUDA tensors.  Mirrors how the reference indexes its
+    """Styles as a list of python ints (list / int / CPU tensor, or a CUDA tensor read back once - see
+    set_sync_free_styles); None for CUDA tensors in sync-free mode.  Mirrors how the reference indexes its
     ModuleList (:57, :60): negative ids wrap, out of range -> IndexError, floats -> TypeError."""
     if isinstance(styles, Tensor):
         if styles.is_floating_point() or styles.is_complex() or styles.dtype == torch.bool:
@@ -40,8 +72,11 @@ def _host_styles(styles, num_styles: int) -> Optional[List[int]]:
             raise TypeError(f"only integer tensors of a single element can be converted to an index "
                             f"(got styles of dtype {styles.dtype})")
         if styles.is_cuda:
-            return None
-        vals = [int(v) for v in styles.reshape(-1).tolist()]
+            vals = _cuda_styles_on_host(styles)
+            if vals is None:
+                return None
+        else:
+            vals = [int(v) for v in styles.reshape(-1).tolist()]
     elif isinstance(styles, int):
         vals = [styles]
     else:
@@ -74,6 +109,26 @@ def _device_styles(host: Sequence[int], device: torch.device) -> Tensor:
         t = torch.tensor(list(host), dtype=torch.int64, device=device)
         _STYLE_CACHE[key] = t
     return t
+
+
+def check_status(device=None) -> None:
+    """Raise IndexError if a kernel met an out-of-range style id since the last check (sync-free mode only: with host-
+    visible styles the id is validated before the launch).  One small device-to-host read per cached workspace;
+    call it at a step / epoch boundary."""
+    import ctypes
+
+    from . import _lib, functional
+
+    lib = _lib.lib()
+    for (dev_index, stream), ws in list(functional._workspaces.items()) + list(functional._cl_workspaces.items()):
+        if device is not None and torch.device(device).index not in (None, dev_index):
+            continue
+        status = ctypes.c_int(0)
+        with torch.cuda.device(dev_index):
+            _lib.check(lib.micn_read_status(ws.data_ptr(), stream, ctypes.byref(status)), "micn_read_status")
+        if status.value & 1:
+            raise IndexError("instance_cond: a style id on the device was out of range "
+                             "(clamped by the kernel; the output of that call used the wrong gamma/beta)")
 
 
 class FastForwardMixin:
@@ -114,7 +169,7 @@ class FastForwardMixin:
             present = [s in host for s in range(self.num_styles)]
         else:
             styles_dev = styles if (styles.dim() == 1 and styles.dtype == torch.int64) else styles.reshape(-1).to(torch.int64)
-            present = None  # unknown without a device sync: absent styles get zero grads instead of None
+            present = None  # sync-free mode: absent styles get zero grads instead of None (set_sync_free_styles)
         if residual is not None and unbatched:
             residual = residual.unsqueeze(0)
         w, b = self._params()

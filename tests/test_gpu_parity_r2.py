@@ -1,0 +1,335 @@
+"""Round-2 GPU parity cases (`pytest -m gpu`): the configurations the sweep TIMES but round 1 never CHECKED (128^3 slabs,
+N = 4 / 8 at 96^3 with the cross-sample d(gamma)/d(beta) fold, N*C = 192 at 48^3, a tensor of more than 2^31 elements),
+the fallback paths the product can take (cluster path, refused cooperative launch, plain launch), and the behaviours
+fixed this round (mixed-dtype residual under autocast, None gradients for absent styles with CUDA style tensors,
+IndexError for an out-of-range CUDA style id).  Everything goes through the C ABI of libmicn.so and is compared with the
+float64 oracle on the same (quantised) inputs; tolerances are BASELINE.json's (1e-5 fp32, 1e-2 bf16/fp16;
+parameter gradients 5x)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import micn_oracle as O
+from test_gpu_parity import SHAPES, TOL, _case, _grads, _make_block, _module, pkg  # noqa: F401  (pkg is a fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def _case_chunked(pkg, shape, styles, num_styles, dtype, seed=0, epilogue="none", chunk=8):
+    """Like test_gpu_parity._case for tensors too large to push through the float64 oracle in one piece: the inputs are
+    generated on the GPU, the CUDA path runs once on the whole tensor, and the oracle checks it channel-chunk by
+    channel-chunk (slabs are independent; d(gamma)/d(beta) of a channel only sum over the samples)."""
+    n, c = shape[0], shape[1]
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    gamma = 1 + 0.3 * torch.randn(num_styles, c, device="cuda", generator=gen)
+    beta = 0.3 * torch.randn(num_styles, c, device="cuda", generator=gen)
+    x = (torch.randn(*shape, device="cuda", generator=gen) * 2 + 1).to(dtype).requires_grad_(True)
+    dy = torch.randn(*shape, device="cuda", generator=gen).to(dtype)
+    w = [gamma[s].clone().requires_grad_(True) for s in range(num_styles)]
+    b = [beta[s].clone().requires_grad_(True) for s in range(num_styles)]
+    st = torch.tensor(styles, dtype=torch.int64, device="cuda")
+    y = pkg.instance_cond(x, st, w, b, epilogue=epilogue)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    tol = TOL[dtype]
+    ptol = 5e-5 if dtype == torch.float32 else 5e-3
+    dg = torch.stack([t.grad for t in w]).cpu().numpy()
+    db = torch.stack([t.grad for t in b]).cpu().numpy()
+    gam, bet = gamma.cpu().numpy(), beta.cpu().numpy()
+    worst = {"y": 0.0, "dx": 0.0, "dgamma": 0.0, "dbeta": 0.0}
+    for c0 in range(0, c, chunk):
+        sl = slice(c0, min(c, c0 + chunk))
+        xn = x.detach()[:, sl].float().cpu().numpy()
+        dyn = dy[:, sl].float().cpu().numpy()
+        if epilogue == "none":
+            yr, m_, r_ = O.fwd_f64(xn, styles, gam[:, sl], bet[:, sl])
+            dxr, dgr, dbr, _ = O.bwd_f64(dyn, xn, styles, gam[:, sl], m_, r_)
+        else:
+            yr, pre, m_, r_ = O.fwd_epilogue_f64(xn, styles, gam[:, sl], bet[:, sl])
+            dxr, _, dgr, dbr, _ = O.bwd_epilogue_f64(dyn, pre, xn, styles, gam[:, sl], m_, r_)
+        worst["y"] = max(worst["y"], rel_err(y.detach()[:, sl].float().cpu().numpy(), yr))
+        worst["dx"] = max(worst["dx"], rel_err(x.grad[:, sl].float().cpu().numpy(), dxr))
+        worst["dgamma"] = max(worst["dgamma"], rel_err(dg[:, sl], dgr))
+        worst["dbeta"] = max(worst["dbeta"], rel_err(db[:, sl], dbr))
+    assert worst["y"] < tol and worst["dx"] < tol, worst
+    assert worst["dgamma"] < ptol and worst["dbeta"] < ptol, worst
+    return worst
+
+
+# ------------------------------------------------------------------------------------------------ shapes the sweep times
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("shape,styles", [((1, 3, 128, 128, 128), [1]), ((2, 2, 128, 128, 128), [0, 1])],
+                         ids=["1x3x128^3", "2x2x128^3"])
+def test_128_cubed_slabs_vs_oracle(pkg, shape, styles, dtype):
+    """BASELINE.json configs[3] times 128^3 volumes (4.2 / 8.4 MB slabs: many pieces per slab, multi-round slabs, the
+    planner's L >= R bound); here they are checked."""
+    _case_chunked(pkg, shape, styles, 2, dtype, seed=128, chunk=1)
+    assert pkg._lib.get_option("last_path") == 2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("n", [4, 8])
+def test_many_samples_at_96_cubed_three_styles(pkg, n, dtype):
+    """N = 4 and 8 on the flat path with three styles (one of them absent when N = 4): the cross-sample fold of the
+    per-slab sums into per-style d(gamma)/d(beta) (micn_flat.cuh, gather warps of the last sample of a channel)."""
+    styles = [(5 * i + 2) % 3 for i in range(n)] if n == 8 else [2, 0, 2, 2]
+    _case_chunked(pkg, (n, 2, 96, 96, 96), styles, 3, dtype, seed=n, chunk=1)
+    assert pkg._lib.get_option("last_path") == 2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_192_slabs_at_48_cubed(pkg, dtype):
+    _case_chunked(pkg, (2, 96, 48, 48, 48), [1, 0], 2, dtype, seed=192, chunk=16)
+
+
+def test_epilogue_at_the_north_star_slab_size_two_samples(pkg):
+    _case_chunked(pkg, (2, 3, 96, 96, 96), [0, 1], 2, torch.bfloat16, seed=3, epilogue="lrelu", chunk=1)
+
+
+def test_more_than_2_pow_31_elements(pkg):
+    """SURVEY.md section 7 "64-bit indexing": 5 x 220 x 128^3 = 2.31 G elements (> 2^31) in bf16, 4.6 GB per tensor.
+    Too large for the float64 oracle, so: (i) size-independent properties on EVERY slab (mean = beta, std = |gamma|,
+    sum dx = 0), (ii) slabs sampled from both ends of the address range - including ones whose element offset exceeds
+    2^31 - against the oracle."""
+    free, _ = torch.cuda.mem_get_info()
+    n, c, s = 5, 220, 128
+    m = s ** 3
+    if free < 40e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    assert n * c * m > 2 ** 31
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    styles = [0, 1, 1, 0, 1]
+    gamma = 1 + 0.3 * torch.randn(2, c, device="cuda", generator=gen)
+    beta = 0.3 * torch.randn(2, c, device="cuda", generator=gen)
+    x = torch.empty(n, c, s, s, s, device="cuda", dtype=torch.bfloat16)
+    dy = torch.empty_like(x)
+    for i in range(n):  # (generated per sample: no 9 GB fp32 temporary)
+        x[i] = (torch.randn(c, s, s, s, device="cuda", generator=gen) * 2 + 1).bfloat16()
+        dy[i] = torch.randn(c, s, s, s, device="cuda", generator=gen).bfloat16()
+    x.requires_grad_(True)
+    w = [gamma[k].clone().requires_grad_(True) for k in range(2)]
+    b = [beta[k].clone().requires_grad_(True) for k in range(2)]
+    st = torch.tensor(styles, device="cuda")
+    y = pkg.instance_cond(x, st, w, b)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    assert pkg._lib.get_option("last_path") == 2
+    # (i) properties, sample by sample
+    for i in range(n):
+        yf = y.detach()[i].float().reshape(c, m)
+        g_, b_ = gamma[styles[i]], beta[styles[i]]
+        assert (yf.mean(1) - b_).abs().max().item() < 1e-2
+        assert (yf.var(1, unbiased=False).sqrt() - g_.abs()).abs().max().item() < 1e-2
+        dxf = x.grad[i].float().reshape(c, m)
+        assert (dxf.sum(1).abs() / dxf.abs().sum(1)).max().item() < 2e-3
+        del yf, dxf
+    # (ii) sampled slabs vs the oracle (element offsets of (4, 219) and (4, 100) are beyond 2^31)
+    for (i, ch) in [(0, 0), (0, 219), (2, 117), (4, 100), (4, 219)]:
+        xn = x.detach()[i:i + 1, ch:ch + 1].float().cpu().numpy()
+        dyn = dy[i:i + 1, ch:ch + 1].float().cpu().numpy()
+        gam = gamma[:, ch:ch + 1].cpu().numpy()
+        bet = beta[:, ch:ch + 1].cpu().numpy()
+        yr, m_, r_ = O.fwd_f64(xn, [styles[i]], gam, bet)
+        dxr, _, _, _ = O.bwd_f64(dyn, xn, [styles[i]], gam, m_, r_)
+        assert rel_err(y.detach()[i:i + 1, ch:ch + 1].float().cpu().numpy(), yr) < 1e-2, (i, ch)
+        assert rel_err(x.grad[i:i + 1, ch:ch + 1].float().cpu().numpy(), dxr) < 1e-2, (i, ch)
+    # parameter gradients of two channels against an fp64 reduction on the GPU
+    for ch in (0, 219):
+        xf = x.detach()[:, ch].double().reshape(n, m)
+        gf = dy[:, ch].double().reshape(n, m)
+        xhat = (xf - xf.mean(1, keepdim=True)) / (xf.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt()
+        for k in range(2):
+            sel = [i for i in range(n) if styles[i] == k]
+            dgr = (gf[sel] * xhat[sel]).sum().item()
+            dbr = gf[sel].sum().item()
+            assert abs(w[k].grad[ch].item() - dgr) < 5e-3 * max(1.0, abs(dgr)) + 2.0
+            assert abs(b[k].grad[ch].item() - dbr) < 5e-3 * max(1.0, abs(dbr)) + 2.0
+
+
+# ------------------------------------------------------------------------------------------------ fallback paths
+@pytest.fixture
+def option(pkg):
+    """Set library options for one test and restore the automatic choice afterwards."""
+    touched = []
+
+    def set_(key, value):
+        pkg._lib.set_option(key, value)
+        touched.append(key)
+    yield set_
+    for key in touched:
+        pkg._lib.set_option(key, -1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape,name", [s for s in SHAPES if s[1] in ("24^3", "48^3", "96^3")], ids=lambda v: v if isinstance(v, str) else None)
+def test_cluster_path_vs_oracle(pkg, option, shape, name, dtype):
+    """micn_cluster.cuh (force_path = 1): the path the dispatcher falls back to when the flat planner declines a slab or
+    the device refuses the cooperative launch."""
+    option("force_path", 1)
+    styles = [(i * 7 + 1) % 2 for i in range(shape[0])]
+    _case(pkg, shape, styles, 2, dtype, seed=41)
+    assert pkg._lib.get_option("last_path") == 1
+    for epi in ("lrelu", "add_lrelu"):
+        _case(pkg, shape, styles, 2, dtype, epilogue=epi, seed=42)
+        assert pkg._lib.get_option("last_path") == 1
+
+
+def test_refused_cooperative_launch_falls_back(pkg, option):
+    """cudaErrorCooperativeLaunchTooLarge (MPS share, another resident kernel) must not fail the call: flat_refuse = 1
+    makes flat_run behave as if the launch had been refused; the call lands on the cluster path and stays correct."""
+    option("flat_refuse", 1)
+    _case(pkg, (2, 5, 48, 48, 48), [1, 0], 2, torch.bfloat16, seed=43)
+    assert pkg._lib.get_option("last_path") == 1
+    _case(pkg, (2, 5, 48, 48, 48), [1, 0], 2, torch.float32, epilogue="add_lrelu", seed=44)
+    assert pkg._lib.get_option("last_path") == 1
+
+
+def test_plain_launch_of_the_flat_kernels(pkg, option):
+    """flat_coop = 0: the persistent grid launched without the cooperative attribute (what a capture under a context
+    that does not support cooperative nodes would use; grid <= resident CTAs is still guaranteed by the planner)."""
+    option("flat_coop", 0)
+    _case(pkg, (2, 5, 48, 48, 48), [1, 0], 2, torch.bfloat16, seed=45)
+    assert pkg._lib.get_option("last_path") == 2
+    _case(pkg, (1, 3, 96, 96, 96), [1], 2, torch.float32, seed=46)
+
+
+def test_flat_declined_slab_goes_to_the_cluster_path(pkg, option):
+    option("flat_min_bytes", 1 << 40)  # the flat planner is never asked
+    _case(pkg, (2, 5, 48, 48, 48), [1, 0], 2, torch.bfloat16, seed=47)
+    assert pkg._lib.get_option("last_path") == 1
+
+
+# ------------------------------------------------------------------------------------------------ behaviours fixed in round 2
+def test_cuda_styles_are_read_back_once_and_absent_styles_keep_none_grads(pkg):
+    """The reference trainer passes `modality.to(device)` (utils/trainer.py:31): with a CUDA tensor the values are read
+    back ONCE per tensor object, so absent styles keep `.grad is None` (AdamW must not decay / move them) and a bad id
+    raises IndexError like the reference's ModuleList indexing."""
+    mod = pkg.FastConditionalInstanceNorm3d(3, 4).cuda()
+    x = torch.randn(2, 4, 8, 8, 8, device="cuda", requires_grad=True)
+    st = torch.tensor([2, 2], device="cuda")
+    mod(x, st).sum().backward()
+    assert getattr(st, "_micn_host", None) == (st._version, [2, 2])
+    assert [n.weight.grad is not None for n in mod.norms] == [False, False, True]
+    assert [n.bias.grad is not None for n in mod.norms] == [False, False, True]
+    with pytest.raises(IndexError):
+        mod(x, torch.tensor([0, 3], device="cuda"))
+    st.fill_(1)  # an in-place change invalidates the cached host copy
+    mod.zero_grad(set_to_none=True)
+    mod(x, st).sum().backward()
+    assert [n.weight.grad is not None for n in mod.norms] == [False, True, False]
+
+
+def test_sync_free_styles_mode_flags_bad_ids_and_gives_zero_grads(pkg):
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4).cuda()
+    x = torch.randn(2, 4, 8, 8, 8, device="cuda", requires_grad=True)
+    pkg.set_sync_free_styles(True)
+    try:
+        mod(x, torch.tensor([1, 1], device="cuda")).sum().backward()
+        assert mod.norms[0].weight.grad is not None and float(mod.norms[0].weight.grad.abs().max()) == 0.0
+        pkg.check_status()  # nothing flagged so far
+        y = mod(x, torch.tensor([0, 5], device="cuda"))  # cannot be validated without a sync: clamped + flagged
+        torch.cuda.synchronize()
+        assert torch.isfinite(y).all()
+        with pytest.raises(IndexError, match="out of range"):
+            pkg.check_status()
+        pkg.check_status()  # the status word was cleared by the read
+    finally:
+        pkg.set_sync_free_styles(False)
+
+
+def test_fused_res_block_under_autocast_with_fp32_input(pkg):
+    """Reference AMP training of C-Swin-UNETR: layer_norm is on autocast's fp32 list, so the hidden states reach
+    encoder2/3/4/10 (identity residual) in fp32 while conv2's output is 16-bit; `out += residual`
+    (dynunet_block.py:123) accepts the mix, and so must the fused add_lrelu (residual rounded to out's dtype, its
+    gradient returned in the residual's dtype)."""
+    torch.manual_seed(5)
+    blk = _make_block(pkg, "res", 6, 6, 1, 2).cuda()
+    ref_blk = _make_block(pkg, "res", 6, 6, 1, 2).cuda()
+    ref_blk.load_state_dict(blk.state_dict())
+    assert pkg.fuse_blocks(blk) == 1
+    x = torch.randn(2, 6, 16, 16, 16, device="cuda", requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    st = [1, 0]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = blk(x, st)
+        # the unfused composition, as dynunet_block.py:100-126 spells it
+        o = ref_blk.lrelu(ref_blk.norm1(ref_blk.conv1(x2), st))
+        o = ref_blk.norm2(ref_blk.conv2(o), st)
+        o += x2
+        ref = ref_blk.lrelu(o)
+    assert out.dtype == torch.bfloat16 and ref.dtype == torch.bfloat16
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    ref.backward(dout)
+    assert x.grad.dtype == torch.float32
+    assert float((out.float() - ref.float()).abs().max() / ref.float().abs().max()) < 2e-2
+    assert float((x.grad - x2.grad).abs().max() / x2.grad.abs().max()) < 3e-2
+
+
+def test_prelu_slope_with_a_residual_is_rejected(pkg):
+    """prelu(norm(x) + r) does not occur in MI-Seg (C-UNet adds its residual after the activation, convolutions.py:329)
+    and its slope gradient cannot be recovered from the output for slopes <= 0: refused, not approximated."""
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4).cuda()
+    x = torch.randn(2, 4, 8, 8, 8, device="cuda")
+    act = torch.nn.PReLU().cuda()
+    with pytest.raises(ValueError, match="'lrelu' epilogue"):
+        mod.forward_fused(x, [0, 1], "add_lrelu", residual=x, slope=act.weight)
+
+
+def test_channels_last_view_with_odd_storage_offset_takes_the_copy_route(pkg):
+    """The channels-last kernels load channel pairs: a view whose storage offset is odd (in elements) is not 2-element
+    aligned and must take the NC* route (and the C ABI must refuse it instead of faulting)."""
+    base = torch.randn(1 + 2 * 50 * 6, device="cuda").bfloat16()
+    x = base[1:].view(2, 50, 6).permute(0, 2, 1)  # [N, C=6, L=50], stride_C = 1, data_ptr % 4 == 2
+    assert x.data_ptr() % 4 == 2 and x.stride(1) == 1
+    mod = pkg.FastConditionalInstanceNorm1d(2, 6).cuda()
+    y = mod(x, [0, 1])
+    assert pkg._lib.get_option("last_path") != 3
+    assert float((y.float() - mod(x.contiguous(), [0, 1]).float()).abs().max()) == 0.0
+    lib = pkg._lib.lib()
+    ws = torch.zeros(lib.micn_cl_workspace_bytes(2, 6, 50), dtype=torch.uint8, device="cuda")
+    xc = base[1:].view(2, 50, 6)
+    out = torch.empty(2 * 50 * 6 + 1, device="cuda", dtype=torch.bfloat16)[1:]
+    rc = lib.micn_fwd_cl(xc.data_ptr(), out.data_ptr(), None, None, 1, None, None, None, 2, 6, 50, 1, 1e-5,
+                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == -5  # MICN_ERR_UNALIGNED
+
+
+# ------------------------------------------------------------------------------------------------ sliding-window driver on the GPU
+def test_sliding_window_driver_with_a_conv_and_fast_norm_predictor(pkg):
+    """SURVEY.md 8(f) row 4 on the device: a small conditional predictor (conv3d -> instance_cond + LeakyReLU fused ->
+    conv3d) run over a volume by `sliding_window_inference` with sw_batch_size 4 (modalities expanded to the window
+    batch) equals (i) the same driver with sw_batch_size 1 and (ii) a by-hand blend of per-window predictions."""
+    torch.manual_seed(9)
+    conv1 = torch.nn.Conv3d(1, 8, 3, padding=1).cuda()
+    norm = pkg.FastConditionalInstanceNorm3d(2, 8).cuda()
+    with torch.no_grad():
+        for k in range(2):
+            norm.norms[k].weight.normal_(1, 0.3)
+            norm.norms[k].bias.normal_(0, 0.3)
+    conv2 = torch.nn.Conv3d(8, 3, 1).cuda()
+
+    def predictor(w, modalities=None):
+        return conv2(norm.forward_fused(conv1(w), modalities, "lrelu"))
+
+    vol = torch.randn(2, 1, 40, 36, 28, device="cuda")
+    mods = torch.tensor([1, 0], device="cuda")
+    roi = (16, 16, 16)
+    with torch.no_grad():
+        a = pkg.sliding_window_inference(vol, roi, 4, predictor, overlap=0.5, modalities=mods)
+        b = pkg.sliding_window_inference(vol, roi, 1, predictor, overlap=0.5, modalities=mods)
+        slices = pkg.window_slices(vol.shape[2:], roi, 0.5)
+        acc = torch.zeros(2, 3, 40, 36, 28, device="cuda")
+        cnt = torch.zeros(2, 1, 40, 36, 28, device="cuda")
+        for bi in range(2):
+            for sl in slices:
+                p = predictor(vol[(slice(bi, bi + 1), slice(None)) + sl], modalities=mods[bi:bi + 1])
+                acc[(slice(bi, bi + 1), slice(None)) + sl] += p
+                cnt[(slice(bi, bi + 1), slice(None)) + sl] += 1
+        ref = acc / cnt
+    assert a.shape == (2, 3, 40, 36, 28)
+    assert float((a - b).abs().max()) < 1e-5
+    assert float((a - ref).abs().max() / ref.abs().max()) < 1e-5
