@@ -312,6 +312,9 @@ def run_next_rows(pkg, dev, tdt, n, c, s, peak):
 
     t_plain = timed(lambda i: plain(xs[i % R]).backward(dy))
     t_prelu = timed(lambda i: cond.forward_fused(xs[i % R], styles, "lrelu", slope=act.weight).backward(dy))
+    # dual-norm epilogue (SURVEY.md 8(d) bytes table, row 3): y = lrelu(norm2(a) + norm3(b)), forward 3*E*s + backward
+    # 5*E*s, raw C-ABI launches back to back on rotating buffers, against the three-call composition it replaces
+    dual = run_dual_leg(pkg, dev, tdt, n, c, s, peak)
     vol = torch.randn(1, 1, 192, 192, 160, device=dev)
     nwin = len(pkg.window_slices((192, 192, 160), (96, 96, 96), 0.5))
     t_sw = timed(lambda i: pkg.sliding_window_inference(vol, 96, 4, lambda w, modalities=None: w, overlap=0.5,
@@ -323,7 +326,85 @@ def run_next_rows(pkg, dev, tdt, n, c, s, peak):
                               "note": "slope gradient accumulated by the backward kernel (one partial per CTA), summed by one small torch op"},
            "sliding_window_driver": {"windows": nwin, "ms_per_volume": t_sw * 1e-3, "windows_per_s": nwin / (t_sw * 1e-6),
                                      "note": "pass-through predictor: the driver's own gather / blend cost, 1 GPU"},
+           "dual_norm_epilogue": dual,
            "what": f"module-level (nn.Module + autograd, host overhead included) on {n}x{c}x{s}^3"}
+    return out
+
+
+def run_dual_leg(pkg, dev, tdt, n, c, s, peak, reps=40):
+    """micn_fwd_dual + micn_bwd_dual on the headline activation (UnetResBlock's downsample branch: C-Swin-UNETR encoder1),
+    and the composition it replaces: micn_fwd(b) + micn_fwd(a, ADD_LRELU) + micn_bwd(ADD_LRELU) + micn_bwd(b)."""
+    import torch
+
+    lib = pkg._lib.lib()
+    es = torch.empty(0, dtype=tdt).element_size()
+    code = {torch.bfloat16: 1, torch.float32: 0, torch.float16: 2}[tdt]
+    m = s ** 3
+    E = n * c * m
+    S = 2
+    R = max(3, int(700e6 // (6 * E * es)) + 1)
+    A = [(torch.randn(n, c, m, device=dev) * 2 + 1).to(tdt) for _ in range(R)]
+    B = [(torch.randn(n, c, m, device=dev) * 0.5).to(tdt) for _ in range(R)]
+    DY = [torch.randn(n, c, m, device=dev).to(tdt) for _ in range(R)]
+    Y, DA, DB, RES = (torch.empty_like(A[0]) for _ in range(4))
+    stats = torch.empty(4, n * c, device=dev)
+    par = [1 + 0.3 * torch.randn(S, c, device=dev), 0.3 * torch.randn(S, c, device=dev),
+           1 + 0.3 * torch.randn(S, c, device=dev), 0.3 * torch.randn(S, c, device=dev)]
+    arr = [(ctypes.c_void_p * S)(*[t[k].data_ptr() for k in range(S)]) for t in par]
+    grads = torch.empty(4, S, c, device=dev)
+    styles = (torch.arange(n, device=dev) % S).to(torch.int64)
+    wsb = lib.micn_workspace_bytes(n, c, m, code, S)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    sp = [stats[k].data_ptr() for k in range(4)]
+    gp = [grads[k].data_ptr() for k in range(4)]
+
+    def fused(i):
+        rc = lib.micn_fwd_dual(A[i].data_ptr(), B[i].data_ptr(), Y.data_ptr(), arr[0], arr[1], arr[2], arr[3], S,
+                               styles.data_ptr(), sp[0], sp[1], sp[2], sp[3], n, c, m, code, 0.01, 1e-5, ws.data_ptr(), wsb,
+                               stream)
+        j = (i + 1) % R
+        rc = rc or lib.micn_bwd_dual(DY[j].data_ptr(), A[j].data_ptr(), B[j].data_ptr(), arr[0], arr[1], arr[2], arr[3], S,
+                                     styles.data_ptr(), sp[0], sp[1], sp[2], sp[3], DA.data_ptr(), DB.data_ptr(), gp[0],
+                                     gp[1], gp[2], gp[3], n, c, m, code, 0.01, ws.data_ptr(), wsb, stream)
+        if rc:
+            raise RuntimeError(f"dual leg: rc={rc}")
+
+    def composed(i):
+        rc = lib.micn_fwd(B[i].data_ptr(), RES.data_ptr(), None, arr[2], arr[3], S, styles.data_ptr(), sp[2], sp[3], n, c, m,
+                          c * m, m, code, 0, 0.01, 1e-5, ws.data_ptr(), wsb, stream)
+        rc = rc or lib.micn_fwd(A[i].data_ptr(), Y.data_ptr(), RES.data_ptr(), arr[0], arr[1], S, styles.data_ptr(), sp[0],
+                                sp[1], n, c, m, c * m, m, code, 2, 0.01, 1e-5, ws.data_ptr(), wsb, stream)
+        j = (i + 1) % R
+        rc = rc or lib.micn_bwd(DY[j].data_ptr(), A[j].data_ptr(), Y.data_ptr(), arr[0], arr[1], S, styles.data_ptr(), sp[0],
+                                sp[1], DA.data_ptr(), RES.data_ptr(), gp[0], gp[1], n, c, m, c * m, m, code, 2, 0.01,
+                                ws.data_ptr(), wsb, stream)
+        rc = rc or lib.micn_bwd(RES.data_ptr(), B[j].data_ptr(), None, arr[2], arr[3], S, styles.data_ptr(), sp[2], sp[3],
+                                DB.data_ptr(), None, gp[2], gp[3], n, c, m, c * m, m, code, 0, 0.01, ws.data_ptr(), wsb,
+                                stream)
+        if rc:
+            raise RuntimeError(f"dual leg (composition): rc={rc}")
+
+    out = {}
+    if not lib.micn_dual_supported(n, c, m, code, 0) or not lib.micn_dual_supported(n, c, m, code, 1):
+        return {"unsupported": True}
+    for key, fn in (("fused", fused), ("composed", composed)):
+        for i in range(3):
+            fn(i % R)
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for i in range(reps):
+            fn(i % R)
+        b_.record()
+        torch.cuda.synchronize()
+        out[key + "_us"] = a_.elapsed_time(b_) / reps * 1e3
+    alg = 8 * E * es
+    out.update({"algorithmic_bytes": alg, "gbps": alg / out["fused_us"] * 1e-3, "frac": alg / out["fused_us"] * 1e-3 / peak,
+                "composed_traffic_bytes": 12 * E * es, "speedup_vs_composed": out["composed_us"] / out["fused_us"],
+                "path": int(pkg._lib.get_option("last_path")),
+                "what": f"lrelu(norm2(a) + norm3(b)) fwd (3*E*s) + bwd (5*E*s) on {n}x{c}x{s}^3, one launch per direction; "
+                        "composed = norm3 fwd, norm2+add+lrelu fwd, its bwd, norm3 bwd (12*E*s of traffic, 4 launches)"})
     return out
 
 

@@ -48,7 +48,9 @@ enum { MICN_F32 = 0, MICN_BF16 = 1, MICN_F16 = 2 };
 enum {
     MICN_EPI_NONE = 0,      /* y = norm(x)                                  */
     MICN_EPI_LRELU = 1,     /* y = lrelu(norm(x))            :107-111       */
-    MICN_EPI_ADD_LRELU = 2  /* y = lrelu(norm(x) + residual) :113-125       */
+    MICN_EPI_ADD_LRELU = 2, /* y = lrelu(norm(x) + residual) :113-125       */
+    MICN_EPI_NORM_ADD_LRELU = 3 /* y = lrelu(norm_a(a) + norm_b(b)): the downsample branch, :113-125 with conv3 /
+                                   norm3 (:82-98); micn_fwd_dual / micn_bwd_dual only */
 };
 
 /* error codes (negative; positive values are cudaError_t) */
@@ -59,13 +61,14 @@ enum {
     MICN_ERR_TOO_MANY_STYLES = -3,
     MICN_ERR_WORKSPACE = -4,
     MICN_ERR_UNALIGNED = -5,
-    MICN_ERR_NO_DEVICE = -6
+    MICN_ERR_NO_DEVICE = -6,
+    MICN_ERR_UNSUPPORTED = -7 /* micn_fwd_dual / micn_bwd_dual: no dual kernel takes this shape */
 };
 
 int micn_version(void);
 const char* micn_error_string(int code);
 
-/* Tuning / experiment knobs ("force_path" 0 small / 1 cluster / 2 flat, "flat_slots", "flat_lag",
+/* Tuning / experiment knobs ("force_path" 0 small / 1 cluster / 2 flat / 4 resident, "flat_slots", "flat_lag",
  * "flat_piece_vecs", "cluster_size", ...) and read-backs ("last_path", "launches").  Returns 0 or
  * MICN_ERR_BAD_ARG for an unknown key.  value < 0 restores the automatic choice. */
 int micn_set_option(const char* key, long long value);
@@ -139,6 +142,33 @@ int micn_bwd_prelu(const void* dy, const void* x, const void* act_out,
                    int dtype, int epilogue, const float* slope_dev,
                    float* dslope_partial,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The downsample branch of UnetResBlock in one pass: y = lrelu(norm_a(a) + norm_b(b)) with a = conv2's output under
+ * norm2 and b = conv3's output under norm3 (networks/blocks/dynunet_block.py:113-125 with :82-98) - C-Swin-UNETR's and
+ * C-UNETR's `encoder1` and every decoder block take it.  Both tensors are dense [N, C, M]; both norms share `styles`
+ * and `num_styles` (pass 1 and NULL styles for plain instance norms).  Forward reads a and b once and writes y once
+ * (3*E*s bytes instead of 2 + 3 for norm3 followed by the add_lrelu call); backward reads a, b, dy once and writes da, db
+ * (5*E*s instead of 4 + 3), recomputing the LeakyReLU mask from the saved statistics, and fills the parameter
+ * gradients of both norms (dbeta_b equals dbeta_a by construction; either pair may be NULL).
+ * micn_dual_supported() says whether these entry points take a problem of that shape (they return
+ * MICN_ERR_UNSUPPORTED otherwise and the caller composes micn_fwd(b) + micn_fwd(a, ADD_LRELU) instead). */
+int micn_dual_supported(int64_t N, int64_t C, int64_t M, int dtype, int backward);
+int micn_fwd_dual(const void* a, const void* b, void* y,
+                  const float* const* gamma_a, const float* const* beta_a,
+                  const float* const* gamma_b, const float* const* beta_b, int num_styles,
+                  const int64_t* styles,
+                  float* save_mean_a, float* save_rstd_a, float* save_mean_b, float* save_rstd_b,
+                  int64_t N, int64_t C, int64_t M, int dtype, float slope, float eps,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int micn_bwd_dual(const void* dy, const void* a, const void* b,
+                  const float* const* gamma_a, const float* const* beta_a,
+                  const float* const* gamma_b, const float* const* beta_b, int num_styles,
+                  const int64_t* styles,
+                  const float* save_mean_a, const float* save_rstd_a, const float* save_mean_b, const float* save_rstd_b,
+                  void* da, void* db,
+                  float* dgamma_a, float* dbeta_a, float* dgamma_b, float* dbeta_b,
+                  int64_t N, int64_t C, int64_t M, int dtype, float slope,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Channels-last (token-major) variant: x, y, dy, dx are dense [N, M, C] tensors (C fastest, C even) - the layout in
  * which PatchMerging's norms (networks/blocks/patch_merging.py:136-141) and the ViT token norms

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmicn.so")
 # dtype / epilogue codes of include/micn.h
 MICN_F32, MICN_BF16, MICN_F16 = 0, 1, 2
 EPI_NONE, EPI_LRELU, EPI_ADD_LRELU, EPI_NORM_ADD_LRELU = 0, 1, 2, 3
+ERR_UNSUPPORTED = -7
 MAX_STYLES = 16
 
 c_void_p, c_int, c_int64, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t,
@@ -40,6 +41,13 @@ SYMBOLS = {
     "micn_bwd_prelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "micn_dual_supported": (c_int, [c_int64, c_int64, c_int64, c_int, c_int]),
+    "micn_fwd_dual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_float,
+                              c_void_p, c_size_t, c_void_p]),
+    "micn_bwd_dual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "micn_cl_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "micn_fwd_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                             c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_size_t, c_void_p]),

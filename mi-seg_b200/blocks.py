@@ -7,6 +7,7 @@ and written once per norm instead of three to five times.
     out = lrelu(norm1(conv1(x)))                norm1.forward_fused(conv1(x), m, "lrelu")
     out = norm2(conv2(out)); out += residual;   norm2.forward_fused(conv2(out), m, "add_lrelu", residual)
     out = lrelu(out)
+    (downsample branch) residual = norm3(conv3(x))  forward_fused_dual(norm2, conv2(out), norm3, conv3(x), m)
 
 C-UNet's `ADN` blocks (acti_norm.py:104-110, "NDA": norm -> dropout(0) -> PReLU) fuse the same way, with the PReLU
 weight read on the device (`adn_forward`).
@@ -21,7 +22,7 @@ import types
 
 import torch.nn as nn
 
-from .norms import FastForwardMixin, FastPlainForwardMixin
+from .norms import FastForwardMixin, FastPlainForwardMixin, forward_fused_dual
 
 _MISSING = "Modalities must be passed to the forward step when encoder_norm_type is 'instance_cond'."
 
@@ -47,7 +48,8 @@ def unet_res_block_forward(self, inp, modalities=None):
     if hasattr(self, "conv3"):
         residual = self.conv3(residual)
     if hasattr(self, "norm3"):
-        residual = self.norm3.forward_fused(residual, modalities, "none")
+        # downsample branch (:82-98, :113-118): lrelu(norm2(out) + norm3(residual)), both norms in ONE kernel per direction
+        return forward_fused_dual(self.norm2, out, self.norm3, residual, modalities, slope=slope)
     return self.norm2.forward_fused(out, modalities, "add_lrelu", residual=residual, slope=slope)
 
 

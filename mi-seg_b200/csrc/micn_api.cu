@@ -43,6 +43,10 @@
 #undef MICN_FLAT_GW
 #undef MICN_FLAT_CPS
 #include "micn_small.cuh"
+#include "micn_res.cuh"
+
+#include <map>
+#include <tuple>
 
 using namespace micn;
 
@@ -51,7 +55,7 @@ namespace {
 // ------------------------------------------------------------------------------------------ options
 struct Options {
     std::atomic<long long> cluster_size{-1};  // force CS (1..16)
-    std::atomic<long long> force_path{-1};    // 0 small, 1 cluster, 2 flat
+    std::atomic<long long> force_path{-1};    // 0 small, 1 cluster, 2 flat, 4 resident (the codes `last_path` reports; 3 = channels-last)
     std::atomic<long long> flat_slots{-1};    // ring A slots (first touch, HBM) of the flat path
     std::atomic<long long> flat_slots_b{-1};  // ring B slots (second touch, L2)
     std::atomic<long long> flat_lag{-1};      // steps P2 trails P1
@@ -63,6 +67,11 @@ struct Options {
     std::atomic<long long> flat_grid{-1};     // cap on the persistent grid
     std::atomic<long long> flat_ovh_vecs{-1}; // planner: per-piece overhead in vector-equivalents
     std::atomic<long long> flat_coop{-1};     // 0: plain launch instead of a cooperative one (experiments)
+    std::atomic<long long> res_cs{-1};        // resident path: force the cluster size (1..8)
+    std::atomic<long long> res_min_bytes{-1}; // smallest slab the resident path takes
+    std::atomic<long long> res_off{-1};       // 1: never the resident path (experiments)
+    std::atomic<long long> res_copies{-1};    // bulk copies per stream of a CTA's share (default 3)
+    std::atomic<long long> res_trace{0};      // bring-up: device pointer of a [grid][8] int64 trace buffer
     std::atomic<long long> flat_refuse{-1};   // 1: behave as if the cooperative launch had been refused (tests the fallback chain)
     std::atomic<long long> flat_trace_which{0};  // 0 both, 1 forward only, 2 backward only
     std::atomic<long long> flat_trace{0};     // bring-up: device pointer of a [grid][64][16] int64 trace buffer
@@ -93,7 +102,7 @@ const OptName kOptNames[] = {
     {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
-    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"flat_trace", &g_opt.flat_trace},
+    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"res_cs", &g_opt.res_cs}, {"res_min_bytes", &g_opt.res_min_bytes}, {"res_off", &g_opt.res_off}, {"res_copies", &g_opt.res_copies}, {"res_trace", &g_opt.res_trace}, {"flat_trace", &g_opt.flat_trace},
     {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
     {"flat_shape_fwd", &g_opt.flat_shape_fwd}, {"flat_shape_bwd", &g_opt.flat_shape_bwd}, {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
@@ -309,9 +318,9 @@ WsLayout ws_layout(long long N, long long C, long long M, int es) {
     WsLayout w;
     const size_t slabs = (size_t)N * (size_t)C;
     w.sums_off = kWsData;
-    w.slab_off = (w.sums_off + slabs * 2 * sizeof(float) + 15) & ~(size_t)15;
-    w.piece_off = w.slab_off + slabs * 16;
-    w.total = w.piece_off + slabs * (size_t)flat_max_pieces(M * es) * 16;
+    w.slab_off = (w.sums_off + slabs * 3 * sizeof(float) + 15) & ~(size_t)15;  // sum g, sum g*xhat, sum g*xhat2 (dual)
+    w.piece_off = w.slab_off + slabs * 16 * 2;  // (two record sets: the dual-norm kernels exchange a second one)
+    w.total = w.piece_off + slabs * (size_t)flat_max_pieces(M * es) * 16 * 2;
     w.total = (w.total + 255) & ~(size_t)255;
     return w;
 }
@@ -342,10 +351,10 @@ int flat_blocks_per_sm(K kernel, int threads, int smem, int smem_optin) {
 // NS = streams of a ring A slot (and, in L2, of a piece between its two touches); NSB = streams of a ring B slot
 template <typename TR, typename KernelT>
 int plan_flat(KernelT kernel, int NS, int NSB, long long slabs, long long C, long long slab_bytes, const DeviceInfo& d,
-              FlatPlan<TR>* fp) {
+              FlatPlan<TR>* fp, int extra_smem = 0) {
     constexpr int kFlatCtasPerSm = TR::kCtasPerSm, kFlatMaxSlots = TR::kMaxSlots, kFlatMinPieceVecs = TR::kMinPieceVecs,
                   kFlatMaxPieces = TR::kMaxPieces, kFlatMaxLag = TR::kMaxLag, kFlatConsumerThreads = TR::kConsumerThreads;
-    auto flat_ctl_bytes = [] { return (long long)TR::kCtlBytes; };
+    auto flat_ctl_bytes = [extra_smem] { return (long long)TR::kCtlBytes + extra_smem; };
     long long G = (long long)d.sm_count * kFlatCtasPerSm;
     const long long gcap = g_opt.flat_grid.load();
     if (gcap > 0 && gcap * kFlatCtasPerSm < G) G = gcap * kFlatCtasPerSm;
@@ -471,9 +480,9 @@ void record_flat(const FlatPlan<TR>& fp) {
 constexpr int kFlatNotTaken = -1000;
 template <typename TR, typename KernelT, typename P>
 int flat_run(KernelT kernel, int NS, int NSB, const P& p, long long slabs, long long slab_bytes, const FlatWs* ws_flat,
-             const DeviceInfo& d, cudaStream_t st, int trace_mute) {
+             const DeviceInfo& d, cudaStream_t st, int trace_mute, int extra_smem = 0) {
     FlatPlan<TR> fpl = {};
-    const int rc = plan_flat<TR>(kernel, NS, NSB, slabs, p.C, slab_bytes, d, &fpl);
+    const int rc = plan_flat<TR>(kernel, NS, NSB, slabs, p.C, slab_bytes, d, &fpl, extra_smem);
     if (rc == 1) return kFlatNotTaken;
     if (rc) return rc;
     if (g_opt.flat_trace_which.load() == trace_mute) fpl.g.trace = nullptr;
@@ -498,6 +507,135 @@ long long flat_min_bytes() {
     return v >= 0 ? v : 32 * 1024;
 }
 
+// ------------------------------------------------------------------------------------------ resident path
+struct ResPlan {
+    res::Geom g;
+    int smem, grid;
+    bool ok;
+};
+std::map<std::tuple<const void*, int, int, long long, long long, long long>, ResPlan> g_res_plans;
+
+// Picks the cluster size for which slabs * CS CTAs fill the SMs in ONE wave with the smallest per-SM share, or declines
+// (ok = false: more bytes than the shared memory of the whole chip holds, slabs too small to split, ...).  Cached.
+template <typename K>
+ResPlan plan_res(K kernel, int NS, long long slabs, long long slab_bytes, const DeviceInfo& d) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    const long long forced = g_opt.res_cs.load();
+    const auto key = std::make_tuple(fn, dev, NS, slabs, slab_bytes, forced * 64 + g_opt.res_copies.load());
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_res_plans.find(key);
+        if (it != g_res_plans.end()) return it->second;
+    }
+    ResPlan best = {};
+    best.ok = false;
+    const long long V = slab_bytes / 16;
+    double best_cost = 1e300;
+    for (int cs = 1; cs <= res::kMaxCluster && V > 0 && V < 0x7fffffffLL; ++cs) {
+        if (forced > 0 && cs != forced) continue;
+        if (slabs * cs > 8LL * d.sm_count) break;
+        const long long nvmax = (V + cs - 1) / cs;
+        if (cs > 1 && nvmax < 256) break;  // 4 KB per CTA: below that the per-CTA fixed cost dominates
+        const long long nch = (nvmax + res::kChunkVecs - 1) / res::kChunkVecs;
+        if (nch * NS > res::kMaxChunks) continue;
+        const int smem = res::smem_bytes(NS, (int)nch);
+        if (smem > d.smem_optin) continue;
+        KernelState* ks = nullptr;
+        if (kernel_prepare(kernel, smem, d.smem_optin, &ks)) continue;
+        int nclusters = 0;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            if (ks->occ[cs_index(cs)] < 0) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(cs * 64));
+                cfg.blockDim = dim3(res::kThreads);
+                cfg.dynamicSmemBytes = smem;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cs;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                int nc = 0;
+                if (cudaOccupancyMaxActiveClusters(&nc, kernel, &cfg) != cudaSuccess) {
+                    cudaGetLastError();
+                    nc = 0;
+                }
+                ks->occ[cs_index(cs)] = nc;
+            }
+            nclusters = ks->occ[cs_index(cs)];
+        }
+        if (nclusters < slabs) continue;  // would need a second wave: the flat path handles that regime better
+        // per-SM bytes in the busiest SM (CTAs are dealt evenly over the SMs) + a small per-CTA charge
+        const long long per_sm = (slabs * cs + d.sm_count - 1) / d.sm_count;
+        const double cost = (double)per_sm * (double)nvmax * NS + 96.0 * cs;
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best.ok = true;
+            best.smem = smem;
+            best.grid = (int)(slabs * cs);
+            best.g.V = (unsigned)V;
+            best.g.CS = (unsigned)cs;
+            best.g.nv_base = (unsigned)(V / cs);
+            best.g.nv_rem = (unsigned)(V % cs);
+            best.g.nch_max = (unsigned)nch;
+            // a share travels as `copies` bulk copies of cv vectors (whole 8 KB granules): few enough that issuing them
+            // (~0.15 us each) does not delay the data, enough that the statistics pass overlaps the arrival
+            long long copies = g_opt.res_copies.load();
+            if (copies <= 0) copies = 3;
+            copies = std::max<long long>(copies, (nch + 3) / 4);  // at most 32 KB per copy (as the flat path's producers)
+            copies = std::min<long long>(std::min<long long>(copies, res::kMaxCopies), nch);
+            best.g.cv = (unsigned)(((nch + copies - 1) / copies) * res::kChunkVecs);
+            best.g.trace = nullptr;
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_res_plans.size() > 4096) g_res_plans.clear();
+    g_res_plans[key] = best;
+    return best;
+}
+
+long long res_min_bytes() {
+    const long long v = g_opt.res_min_bytes.load();
+    return v >= 0 ? v : 32 * 1024;
+}
+
+// plan + launch; kFlatNotTaken when the resident path declines
+constexpr int kNotTaken = -1000;
+template <typename K, typename P>
+int res_run(K kernel, int NS, const P& p, long long slabs, long long slab_bytes, const DeviceInfo& d, cudaStream_t st) {
+    const ResPlan pl = plan_res(kernel, NS, slabs, slab_bytes, d);
+    if (!pl.ok) return kNotTaken;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3(res::kThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.g.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    g_opt.last_path.store(4);  // (3 is the channels-last path)
+    g_opt.last_cs.store(pl.g.CS);
+    g_opt.last_slots.store(pl.g.nch_max);
+    g_opt.last_grid.store(pl.grid);
+    g_opt.launches.fetch_add(1);
+    res::Geom g = pl.g;
+    g.trace = reinterpret_cast<long long*>(g_opt.res_trace.load());
+    return (int)cudaLaunchKernelEx(&cfg, kernel, p, g);
+}
+
+inline bool res_wanted(long long fp, bool can_cluster, long long slab_bytes) {
+    if (!can_cluster || g_opt.res_off.load() == 1) return false;
+    return fp == 4 || (fp < 0 && slab_bytes >= res_min_bytes());
+}
+
 // ------------------------------------------------------------------------------------------ typed dispatch
 template <typename T, int EPI>
 int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const DeviceInfo& d, cudaStream_t st) {
@@ -507,6 +645,10 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     bool use_cluster = can_cluster && slab_bytes >= 32 * 1024;
     if (fp == 0) use_cluster = false;
     if (fp == 1 && can_cluster) use_cluster = true;
+    if (res_wanted(fp, can_cluster, slab_bytes)) {  // everything fits the chip's shared memory in one wave: resident path
+        const int rrc = res_run(res::micn_fwd_res_kernel<T, EPI>, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, p, slabs, slab_bytes, d, st);
+        if (rrc != kNotTaken) return rrc;
+    }
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         // 16-bit I/O: two half-size CTAs per SM hide each other's per-piece latency chains; fp32: one CTA per SM
         const long long shape = g_opt.flat_shape_fwd.load();
@@ -561,7 +703,15 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (fp == 0) use_cluster = false;
     if (fp == 1 && can_cluster) use_cluster = true;
     const bool ds = EPI == MICN_EPI_LRELU && p.dslope != nullptr;
-    if (ds) use_cluster = false;  // the slope-gradient partials are produced by the flat and small kernels only
+    if (ds) use_cluster = false;  // the slope-gradient partials are produced by the resident, flat and small kernels only
+    if (res_wanted(fp, can_cluster, slab_bytes) && !(p.dgamma && p.N > 1 && !p.ws_chan_cnt)) {
+        int rrc;
+        if (ds)
+            rrc = res_run(res::micn_bwd_res_kernel<T, EPI, EPI == MICN_EPI_LRELU>, NS, p, slabs, slab_bytes, d, st);
+        else
+            rrc = res_run(res::micn_bwd_res_kernel<T, EPI, false>, NS, p, slabs, slab_bytes, d, st);
+        if (rrc != kNotTaken) return rrc;
+    }
     if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         int frc;
         if (g_opt.flat_shape_bwd.load() == 2) {
@@ -722,6 +872,60 @@ int cl_fill(ClParams& p, const float* const* gamma, const float* const* beta, in
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------ dual-norm epilogue (typed)
+namespace {
+template <typename T>
+int dual_supported_typed(int64_t N, int64_t C, int64_t M, int backward, const DeviceInfo& d) {
+    const long long slabs = N * C, slab_bytes = M * (long long)sizeof(T);
+    if ((M * (long long)sizeof(T)) % 16 != 0) return 0;
+    const long long fp = g_opt.force_path.load();
+    if (g_opt.res_off.load() != 1 && (fp < 0 || fp == 4)) {
+        if (backward ? plan_res(res::micn_bwd_res_kernel<T, MICN_EPI_NORM_ADD_LRELU, false>, 3, slabs, slab_bytes, d).ok
+                     : plan_res(res::micn_fwd_res_kernel<T, MICN_EPI_NORM_ADD_LRELU>, 2, slabs, slab_bytes, d).ok)
+            return 1;
+    }
+    if ((fp < 0 && slab_bytes >= flat_min_bytes()) || fp == 2) {
+        FlatPlan<flat1::Traits> fpl = {};
+        const int extra = flat1::Traits::kDualExtraBytes;
+        if (backward) return plan_flat<flat1::Traits>(flat1::micn_bwd_flat_kernel<T, MICN_EPI_NORM_ADD_LRELU, false>, 3, 3, slabs, C,
+                                                      slab_bytes, d, &fpl, extra) == 0;
+        return plan_flat<flat1::Traits>(flat1::micn_fwd_flat_kernel<T, MICN_EPI_NORM_ADD_LRELU>, 2, 2, slabs, C, slab_bytes, d,
+                                        &fpl, extra) == 0;
+    }
+    return 0;
+}
+template <typename T>
+int fwd_dual_typed(const FwdParams& p, const FlatWs* wf, const DeviceInfo& d, cudaStream_t st) {
+    const long long slabs = p.N * p.C, slab_bytes = p.M * (long long)sizeof(T);
+    const long long fp = g_opt.force_path.load();
+    if (g_opt.res_off.load() != 1 && (fp < 0 || fp == 4)) {
+        const int rc = res_run(res::micn_fwd_res_kernel<T, MICN_EPI_NORM_ADD_LRELU>, 2, p, slabs, slab_bytes, d, st);
+        if (rc != kNotTaken) return rc;
+    }
+    if (wf && ((fp < 0 && slab_bytes >= flat_min_bytes()) || fp == 2)) {
+        const int rc = flat_run<flat1::Traits>(flat1::micn_fwd_flat_kernel<T, MICN_EPI_NORM_ADD_LRELU>, 2, 2, p, slabs, slab_bytes,
+                                               wf, d, st, 2, flat1::Traits::kDualExtraBytes);
+        if (rc != kFlatNotTaken) return rc;
+    }
+    return MICN_ERR_UNSUPPORTED;
+}
+template <typename T>
+int bwd_dual_typed(const BwdParams& p, const FlatWs* wf, const DeviceInfo& d, cudaStream_t st) {
+    const long long slabs = p.N * p.C, slab_bytes = p.M * (long long)sizeof(T);
+    const long long fp = g_opt.force_path.load();
+    if (g_opt.res_off.load() != 1 && (fp < 0 || fp == 4) && !(p.dgamma && p.N > 1 && !p.ws_chan_cnt)) {
+        const int rc = res_run(res::micn_bwd_res_kernel<T, MICN_EPI_NORM_ADD_LRELU, false>, 3, p, slabs, slab_bytes, d, st);
+        if (rc != kNotTaken) return rc;
+    }
+    if (wf && ((fp < 0 && slab_bytes >= flat_min_bytes()) || fp == 2)) {
+        const int rc = flat_run<flat1::Traits>(flat1::micn_bwd_flat_kernel<T, MICN_EPI_NORM_ADD_LRELU, false>, 3, 3, p, slabs,
+                                               slab_bytes, wf, d, st, 1, flat1::Traits::kDualExtraBytes);
+        if (rc != kFlatNotTaken) return rc;
+    }
+    return MICN_ERR_UNSUPPORTED;
+}
+}  // namespace
+
 extern "C" {
 
 int micn_version(void) { return MICN_VERSION; }
@@ -735,6 +939,7 @@ const char* micn_error_string(int code) {
         case MICN_ERR_WORKSPACE: return "micn: workspace missing or too small";
         case MICN_ERR_UNALIGNED: return "micn: pointer not sufficiently aligned (element size; two elements for the channels-last calls; 16 bytes for the workspace)";
         case MICN_ERR_NO_DEVICE: return "micn: no usable CUDA device";
+        case MICN_ERR_UNSUPPORTED: return "micn: no dual-norm kernel takes this shape (compose micn_fwd calls instead)";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "micn: unknown error";
@@ -976,6 +1181,178 @@ int micn_bwd_prelu(const void* dy, const void* x, const void* act_out, const flo
     return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
                     M, x_stride_n, x_stride_c, dtype, epilogue, 0.f, slope_dev, dslope_partial, workspace, workspace_bytes,
                     stream);
+}
+
+// ------------------------------------------------------------------------------------------ dual-norm epilogue (C ABI)
+int micn_dual_supported(int64_t N, int64_t C, int64_t M, int dtype, int backward) {
+    if (N <= 0 || C <= 0 || M <= 0 || N * C > 0x7fffffffLL) return 0;
+    DeviceInfo* d = nullptr;
+    if (device_info(&d)) return 0;
+    if (d->cc_major < 9) return 0;
+    switch (dtype) {
+        case MICN_F32: return dual_supported_typed<float>(N, C, M, backward, *d);
+        case MICN_BF16: return dual_supported_typed<__nv_bfloat16>(N, C, M, backward, *d);
+        case MICN_F16: return dual_supported_typed<__half>(N, C, M, backward, *d);
+    }
+    return 0;
+}
+
+int micn_fwd_dual(const void* a, const void* b, void* y, const float* const* gamma_a, const float* const* beta_a,
+                  const float* const* gamma_b, const float* const* beta_b, int num_styles, const int64_t* styles,
+                  float* save_mean_a, float* save_rstd_a, float* save_mean_b, float* save_rstd_b, int64_t N, int64_t C,
+                  int64_t M, int dtype, float slope, float eps, void* workspace, size_t workspace_bytes, void* stream) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if (N == 0 || C == 0 || M == 0) return MICN_OK;
+    if (!a || !b || !y) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if ((gamma_a == nullptr) != (beta_a == nullptr) || (gamma_b == nullptr) != (beta_b == nullptr) ||
+        (gamma_a == nullptr) != (gamma_b == nullptr))
+        return MICN_ERR_BAD_ARG;
+    if ((save_mean_a == nullptr) != (save_rstd_a == nullptr) || (save_mean_b == nullptr) != (save_rstd_b == nullptr))
+        return MICN_ERR_BAD_ARG;
+    if (N * C > 0x7fffffffLL) return MICN_ERR_BAD_ARG;
+    if (workspace && workspace_bytes < kWsHeader) return MICN_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MICN_ERR_UNALIGNED;
+    if (!aligned16(a) || !aligned16(b) || !aligned16(y) || (M * es) % 16 != 0) return MICN_ERR_UNSUPPORTED;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc) return rc;
+    if (d->cc_major < 9) return MICN_ERR_UNSUPPORTED;
+    FwdParams p = {};
+    p.x = a;
+    p.x2 = b;
+    p.y = y;
+    p.affine = gamma_a != nullptr;
+    for (int s = 0; s < num_styles && gamma_a; ++s) {
+        if (!gamma_a[s] || !beta_a[s] || !gamma_b[s] || !beta_b[s]) return MICN_ERR_BAD_ARG;
+        p.gamma[s] = gamma_a[s];
+        p.beta[s] = beta_a[s];
+        p.gamma2[s] = gamma_b[s];
+        p.beta2[s] = beta_b[s];
+    }
+    p.styles = reinterpret_cast<const long long*>(styles);
+    p.save_mean = save_mean_a;
+    p.save_rstd = save_rstd_a;
+    p.save_mean2 = save_mean_b;
+    p.save_rstd2 = save_rstd_b;
+    p.status = workspace ? reinterpret_cast<int*>(workspace) + 1 : nullptr;
+    p.N = N;
+    p.C = C;
+    p.M = M;
+    p.x_sN = C * M;
+    p.x_sC = M;
+    p.num_styles = num_styles;
+    p.eps = eps;
+    p.slope = slope;
+    cudaStream_t st = (cudaStream_t)stream;
+    FlatWs wf = {nullptr, nullptr, nullptr};
+    const WsLayout wl = ws_layout(N, C, M, es);
+    const bool have_flat_ws = workspace && workspace_bytes >= wl.total;
+    if (have_flat_ws) {
+        wf.slab = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.slab_off);
+        wf.piece = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.piece_off);
+        wf.ctl = reinterpret_cast<unsigned*>(workspace) + 2;
+    }
+    const FlatWs* wfp = have_flat_ws ? &wf : nullptr;
+    switch (dtype) {
+        case MICN_F32: return fwd_dual_typed<float>(p, wfp, *d, st);
+        case MICN_BF16: return fwd_dual_typed<__nv_bfloat16>(p, wfp, *d, st);
+        case MICN_F16: return fwd_dual_typed<__half>(p, wfp, *d, st);
+    }
+    return MICN_ERR_BAD_DTYPE;
+}
+
+int micn_bwd_dual(const void* dy, const void* a, const void* b, const float* const* gamma_a, const float* const* beta_a,
+                  const float* const* gamma_b, const float* const* beta_b, int num_styles, const int64_t* styles,
+                  const float* save_mean_a, const float* save_rstd_a, const float* save_mean_b, const float* save_rstd_b,
+                  void* da, void* db, float* dgamma_a, float* dbeta_a, float* dgamma_b, float* dbeta_b, int64_t N,
+                  int64_t C, int64_t M, int dtype, float slope, void* workspace, size_t workspace_bytes, void* stream) {
+    const int es = elem_size(dtype);
+    if (!es) return MICN_ERR_BAD_DTYPE;
+    if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
+    if (num_styles < 1) return MICN_ERR_BAD_ARG;
+    if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
+    if ((dgamma_a == nullptr) != (dbeta_a == nullptr) || (dgamma_b == nullptr) != (dbeta_b == nullptr)) return MICN_ERR_BAD_ARG;
+    if (N == 0 || C == 0 || M == 0) {
+        cudaStream_t st0 = (cudaStream_t)stream;
+        for (float* g : {dgamma_a, dbeta_a, dgamma_b, dbeta_b})
+            if (g && C > 0) cudaMemsetAsync(g, 0, sizeof(float) * num_styles * C, st0);
+        return MICN_OK;
+    }
+    if (!dy || !a || !b || !da || !db || !save_mean_a || !save_rstd_a || !save_mean_b || !save_rstd_b) return MICN_ERR_BAD_ARG;
+    if ((gamma_a == nullptr) != (beta_a == nullptr) || (gamma_b == nullptr) != (beta_b == nullptr) ||
+        (gamma_a == nullptr) != (gamma_b == nullptr))
+        return MICN_ERR_BAD_ARG;
+    if (N * C > 0x7fffffffLL) return MICN_ERR_BAD_ARG;
+    if (dgamma_b && !dgamma_a) return MICN_ERR_BAD_ARG;  // (the second norm's gradients ride on the first's fold)
+    if (dgamma_a && (!workspace || workspace_bytes < ws_layout(N, C, 0, es).slab_off)) return MICN_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MICN_ERR_UNALIGNED;
+    if (!aligned16(a) || !aligned16(b) || !aligned16(dy) || !aligned16(da) || !aligned16(db) || (M * es) % 16 != 0)
+        return MICN_ERR_UNSUPPORTED;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc) return rc;
+    if (d->cc_major < 9) return MICN_ERR_UNSUPPORTED;
+    BwdParams p = {};
+    p.dy = dy;
+    p.x = a;
+    p.x2 = b;
+    p.affine = gamma_a != nullptr;
+    for (int s = 0; s < num_styles && gamma_a; ++s) {
+        if (!gamma_a[s] || !beta_a[s] || !gamma_b[s] || !beta_b[s]) return MICN_ERR_BAD_ARG;
+        p.gamma[s] = gamma_a[s];
+        p.beta[s] = beta_a[s];
+        p.gamma2[s] = gamma_b[s];
+        p.beta2[s] = beta_b[s];
+    }
+    p.styles = reinterpret_cast<const long long*>(styles);
+    p.save_mean = save_mean_a;
+    p.save_rstd = save_rstd_a;
+    p.save_mean2 = save_mean_b;
+    p.save_rstd2 = save_rstd_b;
+    p.dx = da;
+    p.dx2 = db;
+    p.dgamma = dgamma_a;
+    p.dbeta = dbeta_a;
+    p.dgamma2 = dgamma_b;
+    p.dbeta2 = dbeta_b;
+    if (workspace) {
+        unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+        p.ws_counter = reinterpret_cast<unsigned int*>(w);
+        p.status = reinterpret_cast<int*>(w) + 1;
+        if (dgamma_a) {
+            p.ws_sum_dy = reinterpret_cast<float*>(w + kWsData);
+            p.ws_sum_dyxh = p.ws_sum_dy + N * C;
+            p.ws_sum_dyxh2 = p.ws_sum_dyxh + N * C;
+            p.ws_chan_cnt = (size_t)C <= kWsChanCounters ? reinterpret_cast<unsigned int*>(w + kWsHeader) : nullptr;
+        }
+    }
+    p.N = N;
+    p.C = C;
+    p.M = M;
+    p.x_sN = C * M;
+    p.x_sC = M;
+    p.num_styles = num_styles;
+    p.slope = slope;
+    cudaStream_t st = (cudaStream_t)stream;
+    FlatWs wf = {nullptr, nullptr, nullptr};
+    const WsLayout wl = ws_layout(N, C, M, es);
+    const bool have_flat_ws = workspace && workspace_bytes >= wl.total;
+    if (have_flat_ws) {
+        wf.slab = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.slab_off);
+        wf.piece = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + wl.piece_off);
+        wf.ctl = reinterpret_cast<unsigned*>(workspace) + 2;
+    }
+    const FlatWs* wfp = have_flat_ws ? &wf : nullptr;
+    switch (dtype) {
+        case MICN_F32: return bwd_dual_typed<float>(p, wfp, *d, st);
+        case MICN_BF16: return bwd_dual_typed<__nv_bfloat16>(p, wfp, *d, st);
+        case MICN_F16: return bwd_dual_typed<__half>(p, wfp, *d, st);
+    }
+    return MICN_ERR_BAD_DTYPE;
 }
 
 // ------------------------------------------------------------------------------------------ channels-last path (C ABI)

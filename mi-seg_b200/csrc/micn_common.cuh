@@ -37,6 +37,12 @@ struct FwdParams {
     int affine;  // 0 -> gamma = 1, beta = 0
     float eps, slope;
     const float* slope_dev;  // non-null: the activation slope lives in device memory (nn.PReLU weight, one element)
+    // MICN_EPI_NORM_ADD_LRELU: the second normalised tensor (dense [N,C,M]) and its norm's parameters / statistics
+    const void* x2;
+    const float* gamma2[kMaxStyles];
+    const float* beta2[kMaxStyles];
+    float* save_mean2;
+    float* save_rstd2;
 };
 
 struct BwdParams {
@@ -65,6 +71,16 @@ struct BwdParams {
     const float* slope_dev;
     float* dslope;  // PReLU (EPI_LRELU with slope_dev): partial sums of dy * pre over pre <= 0, one entry per CTA
                     // (flat path) or per slab (small path); the caller zero-fills the buffer and adds it up
+    // MICN_EPI_NORM_ADD_LRELU: the second normalised tensor, its parameters / statistics and its gradients
+    const void* x2;
+    const float* gamma2[kMaxStyles];
+    const float* beta2[kMaxStyles];
+    const float* save_mean2;
+    const float* save_rstd2;
+    void* dx2;
+    float* dgamma2;  // [S*C] or null (dbeta2 goes with it)
+    float* dbeta2;
+    float* ws_sum_dyxh2;  // [N*C] per-slab sum(g*xhat2)
 };
 
 // ---------------------------------------------------------------------------------------------

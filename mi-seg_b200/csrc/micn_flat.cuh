@@ -142,15 +142,19 @@ __device__ __forceinline__ unsigned flat_epoch_tag(const FlatGeom& g) {
 
 // control block: slot barriers of both rings + the per-piece ring
 __host__ __device__ constexpr int flat_ctl_bytes() {
-    return kFlatMaxSlots * (4 * 8 + 16) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 32) + 16;
+    return kFlatMaxSlots * (4 * 8 + 32) + kFlatNB * (2 * 8 + kFlatConsumerWarps * 16 + 64) + 16;
 }
+// the dual-norm kernels (MICN_EPI_NORM_ADD_LRELU) carry a second set of per-warp partials behind the control block
+__host__ __device__ constexpr int flat_dual_extra_bytes() { return kFlatNB * kFlatConsumerWarps * 16; }
+constexpr int kFlatCoefStride = 16;  // floats per entry of the coefficient ring
 
 struct FlatCtx {
     uint32_t dataA, dataB, fullA, emptyA, fullB, emptyB, p1d0, coef0, tagbar;  // shared::cta addresses
     volatile unsigned* tagw;                     // this launch's record tag (written once by the publish warp)
-    float* slot_prec;                            // [KA][4]  slab constants of the piece in the A slot (backward)
+    float* slot_prec;                            // [KA][8]  slab constants of the piece in the A slot (backward)
     float* warp_part;                            // [NB][16][4]
-    float* coefv;                                // [NB][8]
+    float* warp_part2;                           // [NB][16][4]  second tensor of the dual-norm kernels (else unused)
+    float* coefv;                                // [NB][kFlatCoefStride]
     uint32_t stream_bytes, slot_bytes, slot_bytes_b;  // one stream of a slot; a ring A slot; a ring B slot
 };
 
@@ -171,9 +175,10 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
     c.coef0 = c.p1d0 + kFlatNB * 8;
     float* f = reinterpret_cast<float*>(ctl + kFlatMaxSlots * 32 + kFlatNB * 16);
     c.slot_prec = f;
-    c.warp_part = c.slot_prec + kFlatMaxSlots * 4;
+    c.warp_part = c.slot_prec + kFlatMaxSlots * 8;
     c.coefv = c.warp_part + kFlatNB * kFlatConsumerWarps * 4;
-    c.tagw = reinterpret_cast<volatile unsigned*>(c.coefv + kFlatNB * 8);
+    c.tagw = reinterpret_cast<volatile unsigned*>(c.coefv + kFlatNB * kFlatCoefStride);
+    c.warp_part2 = reinterpret_cast<float*>(ctl + flat_ctl_bytes());  // (only the dual kernels reserve it)
     c.tagbar = smem_u32(const_cast<unsigned*>(c.tagw) + 2);
     // one barrier per thread (73 of them): a single thread doing all the inits costs ~0.4 us before the first TMA
     {
@@ -340,8 +345,10 @@ template <typename T, int EPI>
 __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_kernel(const FwdParams p, const FlatGeom g) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VN = VecT<T>::N;
-    constexpr int NSB = EPI == MICN_EPI_ADD_LRELU ? 2 : 1;  // ring B: x [, residual]
-    const FlatCtx c = flat_setup<1, NSB>(smem, g);
+    constexpr bool DUAL = EPI == MICN_EPI_NORM_ADD_LRELU;   // y = lrelu(norm_a(x) + norm_b(x2)): statistics of TWO tensors
+    constexpr int NSA = DUAL ? 2 : 1;                       // ring A: x [, x2]
+    constexpr int NSB = (EPI == MICN_EPI_ADD_LRELU || DUAL) ? 2 : 1;  // ring B: x [, residual | x2]
+    const FlatCtx c = flat_setup<NSA, NSB>(smem, g);
     const unsigned cta = blockIdx.x, G = gridDim.x;
     const unsigned nj = cta < g.T ? (g.T - cta + G - 1) / G : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -371,12 +378,13 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
                 flat_trace(g, j, isA ? TR_LOAD : TR_LOAD2);
                 const uint32_t dst = data0 + r.i * (isA ? c.slot_bytes : c.slot_bytes_b);
                 flat_issue(dst, src, bytes, bar, pol);
-                if (NSB == 2 && !isA) {  // the residual rides in the same slot (read once, from HBM)
-                    const char* rsrc = reinterpret_cast<const char*>(p.res) + ((size_t)pc.slab * (size_t)p.M) * sizeof(T) +
-                                       (size_t)pc.k * g.PV * 16;
+                const bool second = isA ? DUAL : NSB == 2;
+                if (second) {  // the residual rides in the same slot (read once, from HBM); dual: the second tensor, both touches
+                    const char* rsrc = reinterpret_cast<const char*>(DUAL ? p.x2 : p.res) +
+                                       ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
                     flat_issue(dst + c.stream_bytes, rsrc, bytes, bar, pol);
                 }
-                mbar_arrive_expect_tx(bar, (NSB == 2 && !isA) ? 2 * bytes : bytes);
+                mbar_arrive_expect_tx(bar, second ? 2 * bytes : bytes);
                 r.next(K);
             }
         }
@@ -396,18 +404,22 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
             const float nw = lane < kFlatConsumerWarps ? (float)(warp_vecs(pv, lane) * VN) : 0.f;
             mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
-            Stat st{0.f, 0.f, 0.f};
-            if (lane < kFlatConsumerWarps) {
-                const float4 w = *reinterpret_cast<const float4*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
-                st = stat_from_shifted(w.z, w.x, w.y, nw);
+#pragma unroll
+            for (int t = 0; t < NSA; ++t) {  // one record per normalised tensor (dual: the second set sits T records further)
+                Stat st{0.f, 0.f, 0.f};
+                if (lane < kFlatConsumerWarps) {
+                    const float4 w = *reinterpret_cast<const float4*>((t ? c.warp_part2 : c.warp_part) +
+                                                                     (e.i * kFlatConsumerWarps + lane) * 4);
+                    st = stat_from_shifted(w.z, w.x, w.y, nw);
+                }
+                // fold about the first warp's mean (see the file header)
+                const float ref = __shfl_sync(0xffffffffu, st.mean, 0);
+                const float d = st.n > 0.f ? st.mean - ref : 0.f;
+                const float A = warp_sum(st.n * d), B = warp_sum(fmaf(st.n * d, d, st.m2));
+                const float N = (float)(pv * VN);
+                const float m = A / N;
+                if (lane == 0) ll_store(g.ws_piece + (size_t)t * g.T + gidx, ref + m, fmaxf(B - A * m, 0.f), tag);
             }
-            // fold about the first warp's mean (see the file header)
-            const float ref = __shfl_sync(0xffffffffu, st.mean, 0);
-            const float d = st.n > 0.f ? st.mean - ref : 0.f;
-            const float A = warp_sum(st.n * d), B = warp_sum(fmaf(st.n * d, d, st.m2));
-            const float N = (float)(pv * VN);
-            const float m = A / N;
-            if (lane == 0) ll_store(g.ws_piece + gidx, ref + m, fmaxf(B - A * m, 0.f), tag);
             if (lane == 0) flat_trace(g, j, TR_PUB_END);
         }
     } else if (warp >= kFlatGatherWarp0) {
@@ -420,8 +432,20 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
             const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
             // parameter loads first: their latency hides behind everything below
             const int style = load_style(p.styles, n, p.num_styles, p.status);
-            float gamma, beta;
+            float gamma, beta, gammaB = 1.f, betaB = 0.f;
             load_affine(p, style, ch, gamma, beta);
+            if (DUAL && p.affine) {
+                const float* gp = p.gamma2[0];
+                const float* bp = p.beta2[0];
+#pragma unroll
+                for (int i = 1; i < kMaxStyles; ++i)
+                    if (i == style) {
+                        gp = p.gamma2[i];
+                        bp = p.beta2[i];
+                    }
+                gammaB = __ldg(gp + ch);
+                betaB = __ldg(bp + ch);
+            }
             // no polling before this CTA's own piece is through P1: the other CTAs are at the same point
             mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
             // ... and let their record stores land; the last L pieces of the CTA are the kernel's tail, where
@@ -439,6 +463,18 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
             if (lane == 0) flat_trace(g, j, TR_GA_POLLED);
             A = warp_sum(A);
             B = warp_sum(B);
+            float refB = 0.f, AB = 0.f, BB = 0.f;
+            if (DUAL) {  // the second tensor's records of the same slab
+                ll_gather(g.ws_piece + (size_t)g.T + (size_t)pc.slab * g.P, g.P, tag, g.poll_backoff_ns, lane,
+                          [&](float a0, float) { refB = a0; },
+                          [&](unsigned q, float a, float b) {
+                              const float nq = (float)(piece_vecs(g, q) * VN), d = a - refB;
+                              AB = fmaf(nq, d, AB);
+                              BB += fmaf(nq * d, d, b);
+                          });
+                AB = warp_sum(AB);
+                BB = warp_sum(BB);
+            }
             if (lane == 0) {
                 const float invM = 1.f / (float)p.M;
                 const float m = A * invM;
@@ -446,11 +482,24 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
                 const float rstd = 1.f / sqrtf(fmaxf(B - A * m, 0.f) * invM + p.eps);  // biased variance, eps inside the sqrt
                 const float a = rstd * gamma;
                 // fp32: (x - mean) * a + beta.  16-bit: x * a + (beta - mean * a): one FMA per element.
-                *reinterpret_cast<float4*>(c.coefv + e.i * 8) =
+                float* cf = c.coefv + e.i * kFlatCoefStride;
+                *reinterpret_cast<float4*>(cf) =
                     make_float4(sizeof(T) == 4 ? mean : 0.f, a, sizeof(T) == 4 ? beta : fmaf(-mean, a, beta), 0.f);
                 if (pc.k == 0 && p.save_mean) {
                     p.save_mean[pc.slab] = mean;
                     p.save_rstd[pc.slab] = rstd;
+                }
+                if (DUAL) {
+                    const float mB = AB * invM;
+                    const float meanB = refB + mB;
+                    const float rstdB = 1.f / sqrtf(fmaxf(BB - AB * mB, 0.f) * invM + p.eps);
+                    const float aB = rstdB * gammaB;
+                    *reinterpret_cast<float4*>(cf + 4) =
+                        make_float4(sizeof(T) == 4 ? meanB : 0.f, aB, sizeof(T) == 4 ? betaB : fmaf(-meanB, aB, betaB), 0.f);
+                    if (pc.k == 0 && p.save_mean2) {
+                        p.save_mean2[pc.slab] = meanB;
+                        p.save_rstd2[pc.slab] = rstdB;
+                    }
                 }
                 mbar_arrive(c.coef0 + 8 * e.i);
                 flat_trace(g, j, TR_GA_END);
@@ -469,36 +518,41 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
                 const unsigned pv = piece_vecs(g, gidx - fastdiv(gidx, g.divP) * g.P);
                 mbar_wait_park(c.fullA + 8 * ra.i, ra.ph);
                 if (tid == 0) flat_trace(g, s, TR_P1_BEGIN);
-                const uint32_t base = c.dataA + ra.i * c.slot_bytes;
-                float Kw = 0.f;
-                f32x2 sacc = f2_splat(0.f), qacc = f2_splat(0.f), sacc2 = sacc, qacc2 = sacc;
-                if ((unsigned)warp * 32u < pv) {
-                    Kw = first_elem<T>(base + warp * 512);  // shift = the warp's first element of the piece
-                    const f32x2 K2 = f2_splat(Kw);
-                    uint4 q[4];
-                    piece_sweep<4>(
-                        pv, tid, [&](int i, unsigned v) { q[i] = lds128(base + v * 16); },
-                        [&](int i, unsigned) {
-                            f32x2 f[VN / 2];
-                            VecT<T>::unpack2(q[i], f);
+                const uint32_t base0 = c.dataA + ra.i * c.slot_bytes;
 #pragma unroll
-                            for (int k = 0; k < VN / 2; k += 2) {  // two independent accumulator pairs
-                                const f32x2 d0 = f2_sub(f[k], K2), d1 = f2_sub(f[k + 1], K2);
-                                sacc = f2_add(sacc, d0);
-                                sacc2 = f2_add(sacc2, d1);
-                                qacc = f2_fma(d0, d0, qacc);
-                                qacc2 = f2_fma(d1, d1, qacc2);
-                            }
-                        });
+                for (int t = 0; t < NSA; ++t) {  // the same sweep per normalised tensor of the slot
+                    const uint32_t base = base0 + t * c.stream_bytes;
+                    float Kw = 0.f;
+                    f32x2 sacc = f2_splat(0.f), qacc = f2_splat(0.f), sacc2 = sacc, qacc2 = sacc;
+                    if ((unsigned)warp * 32u < pv) {
+                        Kw = first_elem<T>(base + warp * 512);  // shift = the warp's first element of the piece
+                        const f32x2 K2 = f2_splat(Kw);
+                        uint4 q[4];
+                        piece_sweep<4>(
+                            pv, tid, [&](int i, unsigned v) { q[i] = lds128(base + v * 16); },
+                            [&](int i, unsigned) {
+                                f32x2 f[VN / 2];
+                                VecT<T>::unpack2(q[i], f);
+#pragma unroll
+                                for (int k = 0; k < VN / 2; k += 2) {  // two independent accumulator pairs
+                                    const f32x2 d0 = f2_sub(f[k], K2), d1 = f2_sub(f[k + 1], K2);
+                                    sacc = f2_add(sacc, d0);
+                                    sacc2 = f2_add(sacc2, d1);
+                                    qacc = f2_fma(d0, d0, qacc);
+                                    qacc2 = f2_fma(d1, d1, qacc2);
+                                }
+                            });
+                    }
+                    if (t == NSA - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
+                    }
+                    const float s1 = warp_sum(f2_hsum(f2_add(sacc, sacc2))), s2 = warp_sum(f2_hsum(f2_add(qacc, qacc2)));
+                    if (lane == 0)
+                        *reinterpret_cast<float4*>((t ? c.warp_part2 : c.warp_part) + (e.i * kFlatConsumerWarps + warp) * 4) =
+                            make_float4(s1, s2, Kw, 0.f);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
-                const float s1 = warp_sum(f2_hsum(f2_add(sacc, sacc2))), s2 = warp_sum(f2_hsum(f2_add(qacc, qacc2)));
-                if (lane == 0) {
-                    *reinterpret_cast<float4*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) =
-                        make_float4(s1, s2, Kw, 0.f);
-                    mbar_arrive(c.p1d0 + 8 * e.i);
-                }
+                if (lane == 0) mbar_arrive(c.p1d0 + 8 * e.i);
                 if (tid == 0) flat_trace(g, s, TR_P1_END);
                 ra.next(g.KA);
             }
@@ -512,8 +566,11 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
                 const uint32_t base = c.dataB + rb.i * c.slot_bytes_b;
                 if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
                 mbar_wait_park(c.coef0 + 8 * e.i, e.ph);
-                const float4 cf = *reinterpret_cast<const float4*>(c.coefv + e.i * 8);
+                const float4 cf = *reinterpret_cast<const float4*>(c.coefv + e.i * kFlatCoefStride);
                 const f32x2 sub2 = f2_splat(cf.x), ca2 = f2_splat(cf.y), cb2 = f2_splat(cf.z);
+                float4 cfB = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (DUAL) cfB = *reinterpret_cast<const float4*>(c.coefv + e.i * kFlatCoefStride + 4);
+                const f32x2 subB = f2_splat(cfB.x), caB = f2_splat(cfB.y), cbB = f2_splat(cfB.z);
                 mbar_wait_park(c.fullB + 8 * rb.i, rb.ph);
                 if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
                 uint4 q[2], rq[2];
@@ -530,7 +587,8 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_fwd_flat_ke
 #pragma unroll
                         for (int k = 0; k < VN / 2; ++k) {
                             f32x2 o = sizeof(T) == 4 ? f2_fma(f2_sub(f[k], sub2), ca2, cb2) : f2_fma(f[k], ca2, cb2);
-                            if (NSB == 2) o = f2_add(o, rr[k]);
+                            if (DUAL) o = f2_add(o, sizeof(T) == 4 ? f2_fma(f2_sub(rr[k], subB), caB, cbB) : f2_fma(rr[k], caB, cbB));
+                            else if (NSB == 2) o = f2_add(o, rr[k]);
                             if (EPI != MICN_EPI_NONE) {
                                 float lo, hi;
                                 f2_split(o, lo, hi);
@@ -580,6 +638,40 @@ __device__ __forceinline__ f32x2 bwd_masked2(f32x2 x, f32x2 gy, f32x2 o, f32x2 m
     return f2_make(p0 > zero ? g0 : g0 * slope, p1 > zero ? g1 : g1 * slope);
 }
 
+// dual-norm epilogue: the mask is the sign of norm_a(x) + norm_b(x2), the SAME expression the forward evaluated
+template <typename T>
+__device__ __forceinline__ f32x2 bwd_masked_dual(f32x2 x, f32x2 x2, f32x2 gy, f32x2 mean2, f32x2 a2, f32x2 bq2, f32x2 meanB2,
+                                                 f32x2 aB2, f32x2 bqB2, float slope) {
+    const f32x2 pa = sizeof(T) == 4 ? f2_fma(f2_sub(x, mean2), a2, bq2) : f2_fma(x, a2, bq2);
+    const f32x2 pb = sizeof(T) == 4 ? f2_fma(f2_sub(x2, meanB2), aB2, bqB2) : f2_fma(x2, aB2, bqB2);
+    const f32x2 pre = f2_add(pa, pb);
+    const float zero = (sizeof(T) == 2 && !VecT<T>::kWideExponent) ? 2.98023224e-8f : 0.f;  // (see bwd_masked2)
+    float p0, p1, g0, g1;
+    f2_split(pre, p0, p1);
+    f2_split(gy, g0, g1);
+    return f2_make(p0 > zero ? g0 : g0 * slope, p1 > zero ? g1 : g1 * slope);
+}
+
+// (mean, rstd, gamma, beta) of a slab's SECOND norm (dual-norm epilogue)
+template <typename P>
+__device__ __forceinline__ float4 slab_consts2(const P& p, unsigned slab, unsigned n, unsigned ch) {
+    const int style = load_style(p.styles, n, p.num_styles, nullptr);
+    float gamma = 1.f, beta = 0.f;
+    if (p.affine) {
+        const float* gp = p.gamma2[0];
+        const float* bp = p.beta2[0];
+#pragma unroll
+        for (int i = 1; i < kMaxStyles; ++i)
+            if (i == style) {
+                gp = p.gamma2[i];
+                bp = p.beta2[i];
+            }
+        gamma = __ldg(gp + ch);
+        beta = __ldg(bp + ch);
+    }
+    return make_float4(__ldg(p.save_mean2 + slab), __ldg(p.save_rstd2 + slab), gamma, beta);
+}
+
 // (mean, rstd, gamma, beta) of a slab
 template <typename P>
 __device__ __forceinline__ float4 slab_consts(const P& p, unsigned slab, unsigned n, unsigned ch) {
@@ -593,7 +685,8 @@ __device__ __forceinline__ float4 slab_consts(const P& p, unsigned slab, unsigne
 // consumer thread carries its share across ALL of the CTA's pieces and the CTA writes one partial at the end
 template <typename T, int EPI, bool DS = false>
 __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_kernel(const BwdParams p, const FlatGeom g) {
-    constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
+    constexpr bool DUAL = EPI == MICN_EPI_NORM_ADD_LRELU;  // two normalised inputs: x, x2 (stream 2), one dy
+    constexpr int NS = (EPI == MICN_EPI_ADD_LRELU || DUAL) ? 3 : 2;  // x, dy [, act_out | x2]
     constexpr int VN = VecT<T>::N;
     constexpr int U = NS == 3 ? 1 : 2;  // vectors per thread in flight per stream (register budget: 72)
     extern __shared__ __align__(128) unsigned char smem[];
@@ -615,8 +708,9 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             for (unsigned j = 0; j < nj; ++j) {
                 const PieceId pc = piece_of(g, j * G + cta);
                 const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
-                float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 pr = make_float4(0.f, 0.f, 0.f, 0.f), prB = pr;
                 if (isA) pr = slab_consts(p, pc.slab, n, ch);  // for P1: loads issued before the waits
+                if (isA && DUAL) prB = slab_consts2(p, pc.slab, n, ch);
                 const size_t poff = (size_t)pc.k * g.PV * 16;
                 const size_t doff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + poff;
                 const char* xsrc = reinterpret_cast<const char*>(p.x) +
@@ -632,8 +726,10 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                 flat_issue(dst, xsrc, bytes, bar, pol);
                 flat_issue(dst + c.stream_bytes, reinterpret_cast<const char*>(p.dy) + doff, bytes, bar, pol);
                 if (NS == 3)
-                    flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(p.act_out) + doff, bytes, bar, pol);
-                if (isA) *reinterpret_cast<float4*>(c.slot_prec + r.i * 4) = pr;  // visible through the barrier
+                    flat_issue(dst + 2 * c.stream_bytes, reinterpret_cast<const char*>(DUAL ? p.x2 : p.act_out) + doff, bytes,
+                               bar, pol);
+                if (isA) *reinterpret_cast<float4*>(c.slot_prec + r.i * 8) = pr;  // visible through the barrier
+                if (isA && DUAL) *reinterpret_cast<float4*>(c.slot_prec + r.i * 8 + 4) = prB;
                 mbar_arrive_expect_tx(bar, bytes * NS);
                 r.next(K);
             }
@@ -650,15 +746,18 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             const Ring e = entry_of(j);
             mbar_wait_park(c.p1d0 + 8 * e.i, e.ph);
             if (lane == 0) flat_trace(g, j, TR_PUB_BEGIN);
-            float s1 = 0.f, s2 = 0.f;
+            float s1 = 0.f, s2 = 0.f, s3 = 0.f;
             if (lane < kFlatConsumerWarps) {
-                const float2 w = *reinterpret_cast<const float2*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
+                const float4 w = *reinterpret_cast<const float4*>(c.warp_part + (e.i * kFlatConsumerWarps + lane) * 4);
                 s1 = w.x;
                 s2 = w.y;
+                s3 = w.z;
             }
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
+            if (DUAL) s3 = warp_sum(s3);
             if (lane == 0) ll_store(g.ws_piece + (j * G + cta), s1, s2, tag);
+            if (DUAL && lane == 0) ll_store(g.ws_piece + (size_t)g.T + (j * G + cta), s3, 0.f, tag);
             if (lane == 0) flat_trace(g, j, TR_PUB_END);
         }
     } else if (warp >= kFlatGatherWarp0) {
@@ -672,6 +771,8 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             const unsigned n = fastdiv(pc.slab, g.divC), ch = pc.slab - n * C;
             const float4 pr = slab_consts(p, pc.slab, n, ch);  // latency hides behind the wait below
             const float mean = pr.x, rstd = pr.y, gamma = pr.z, beta = pr.w;
+            float4 prB = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (DUAL) prB = slab_consts2(p, pc.slab, n, ch);
             // no polling before this CTA's own piece is through P1 (the others are at the same point)
             mbar_wait_idle(c.p1d0 + 8 * e.i, e.ph);
             __nanosleep(j + g.L >= nj ? g.poll_delay_tail_ns : g.poll_delay_ns);  // let the record stores land (tail: eager)
@@ -685,44 +786,72 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             if (lane == 0) flat_trace(g, j, TR_GA_POLLED);
             S1 = warp_sum(S1);
             S2 = warp_sum(S2);
+            float S2B = 0.f;
+            if (DUAL) {  // sum g * (x2 - mean2): the second record set of the same slab
+                ll_gather(g.ws_piece + (size_t)g.T + (size_t)pc.slab * g.P, g.P, tag, g.poll_backoff_ns, lane, [](float, float) {},
+                          [&](unsigned, float a, float) { S2B += a; });
+                S2B = warp_sum(S2B);
+            }
             const float a = rstd * gamma;
             const float S2r = S2 * rstd;  // sum g * xhat
+            const float aB = prB.y * prB.z, S2Br = S2B * prB.y;
             if (lane == 0) {
                 // dx = a*g - a*S1/M - a*rstd*(S2r/M)*(x - mean)
                 const float B1 = -a * S2r * invM * rstd, B0c = -a * S1 * invM;
-                float* cf = c.coefv + e.i * 8;
+                float* cf = c.coefv + e.i * kFlatCoefStride;
                 *reinterpret_cast<float4*>(cf) = make_float4(a, B1, sizeof(T) == 4 ? B0c : fmaf(-B1, mean, B0c), mean);
                 cf[4] = sizeof(T) == 4 ? beta : fmaf(-mean, a, beta);
+                if (DUAL) {
+                    const float meanB = prB.x, rstdB = prB.y;
+                    const float B1b = -aB * S2Br * invM * rstdB, B0cb = -aB * S1 * invM;
+                    *reinterpret_cast<float4*>(cf + 8) =
+                        make_float4(aB, B1b, sizeof(T) == 4 ? B0cb : fmaf(-B1b, meanB, B0cb), meanB);
+                    cf[12] = sizeof(T) == 4 ? prB.w : fmaf(-meanB, aB, prB.w);
+                }
                 mbar_arrive(c.coef0 + 8 * e.i);
                 flat_trace(g, j, TR_GA_END);
             }
             if (pc.k == 0 && p.dgamma) {
+                const bool two = DUAL && p.dgamma2 != nullptr;
                 if (p.N == 1) {
                     // one sample: this slab's sums ARE the gradients of its style's row
                     const int style = load_style(p.styles, 0, p.num_styles, nullptr);
                     for (int s = lane; s < p.num_styles; s += 32) {
                         p.dbeta[(size_t)s * C + ch] = s == style ? S1 : 0.f;
                         p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
+                        if (two) {
+                            p.dbeta2[(size_t)s * C + ch] = s == style ? S1 : 0.f;
+                            p.dgamma2[(size_t)s * C + ch] = s == style ? S2Br : 0.f;
+                        }
                     }
                 } else {
+                    const size_t slabs = (size_t)p.N * C;
                     if (lane == 0) ll_store(g.ws_slab + pc.slab, S1, S2r, tag);
+                    if (two && lane == 0) ll_store(g.ws_slab + slabs + pc.slab, S2Br, 0.f, tag);
                     if (n == (unsigned)p.N - 1) {
                         // last sample of this channel: fold every sample's record per style, fixed order
                         for (int s = 0; s < p.num_styles; ++s) {
-                            float ab = 0.f, ag = 0.f;
+                            float ab = 0.f, ag = 0.f, ag2 = 0.f;
                             for (unsigned nn = lane; nn < (unsigned)p.N; nn += 32) {
-                                float ra, rb;
+                                float ra, rb, rc = 0.f, rd;
                                 ll_wait1(g.ws_slab + (size_t)nn * C + ch, tag, g.poll_backoff_ns, ra, rb);
+                                if (two) ll_wait1(g.ws_slab + slabs + (size_t)nn * C + ch, tag, g.poll_backoff_ns, rc, rd);
                                 if (load_style(p.styles, nn, p.num_styles, nullptr) == s) {
                                     ab += ra;
                                     ag += rb;
+                                    ag2 += rc;
                                 }
                             }
                             ab = warp_sum(ab);
                             ag = warp_sum(ag);
+                            if (two) ag2 = warp_sum(ag2);
                             if (lane == 0) {
                                 p.dbeta[(size_t)s * C + ch] = ab;
                                 p.dgamma[(size_t)s * C + ch] = ag;
+                                if (two) {
+                                    p.dbeta2[(size_t)s * C + ch] = ab;
+                                    p.dgamma2[(size_t)s * C + ch] = ag2;
+                                }
                             }
                         }
                     }
@@ -745,10 +874,18 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                 mbar_wait_park(c.fullA + 8 * ra.i, ra.ph);
                 if (tid == 0) flat_trace(g, s, TR_P1_BEGIN);
                 const uint32_t base = c.dataA + ra.i * c.slot_bytes;
-                const float4 pr = *reinterpret_cast<const float4*>(c.slot_prec + ra.i * 4);
+                const float4 pr = *reinterpret_cast<const float4*>(c.slot_prec + ra.i * 8);
                 const float mean = pr.x, ca = pr.y * pr.z;
                 const float bq = sizeof(T) == 4 ? pr.w : fmaf(-mean, ca, pr.w);
                 const f32x2 mean2 = f2_splat(mean), ca2 = f2_splat(ca), bq2 = f2_splat(bq);
+                f32x2 meanB2 = 0ull, caB2 = 0ull, bqB2 = 0ull, s3a = f2_splat(0.f), s3b = s3a;
+                if (DUAL) {
+                    const float4 prB = *reinterpret_cast<const float4*>(c.slot_prec + ra.i * 8 + 4);
+                    const float caB = prB.y * prB.z;
+                    meanB2 = f2_splat(prB.x);
+                    caB2 = f2_splat(caB);
+                    bqB2 = f2_splat(sizeof(T) == 4 ? prB.w : fmaf(-prB.x, caB, prB.w));
+                }
                 f32x2 s1a = f2_splat(0.f), s1b = s1a, s2a = s1a, s2b = s1a;
                 uint4 qx[U], qg[U], qo[U];
                 piece_sweep<U>(
@@ -775,8 +912,16 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                                     ds2 = f2_fma(gf[k + h], f2_make(p0 > 0.f ? 0.f : p0, p1 > 0.f ? 0.f : p1), ds2);
                                 }
                             }
-                            const f32x2 g0 = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, ca2, bq2, slope);
-                            const f32x2 g1 = bwd_masked2<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0ull, mean2, ca2, bq2, slope);
+                            f32x2 g0, g1;
+                            if (DUAL) {
+                                g0 = bwd_masked_dual<T>(xf[k], of[k], gf[k], mean2, ca2, bq2, meanB2, caB2, bqB2, slope);
+                                g1 = bwd_masked_dual<T>(xf[k + 1], of[k + 1], gf[k + 1], mean2, ca2, bq2, meanB2, caB2, bqB2, slope);
+                                s3a = f2_fma(g0, f2_sub(of[k], meanB2), s3a);
+                                s3b = f2_fma(g1, f2_sub(of[k + 1], meanB2), s3b);
+                            } else {
+                                g0 = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, ca2, bq2, slope);
+                                g1 = bwd_masked2<T, EPI>(xf[k + 1], gf[k + 1], NS == 3 ? of[k + 1] : 0ull, mean2, ca2, bq2, slope);
+                            }
                             s1a = f2_add(s1a, g0);
                             s1b = f2_add(s1b, g1);
                             s2a = f2_fma(g0, f2_sub(xf[k], mean2), s2a);
@@ -786,8 +931,9 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                 __syncwarp();
                 if (lane == 0) mbar_arrive(c.emptyA + 8 * ra.i);
                 const float s1 = warp_sum(f2_hsum(f2_add(s1a, s1b))), s2 = warp_sum(f2_hsum(f2_add(s2a, s2b)));
+                const float s3 = DUAL ? warp_sum(f2_hsum(f2_add(s3a, s3b))) : 0.f;
                 if (lane == 0) {
-                    *reinterpret_cast<float2*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) = make_float2(s1, s2);
+                    *reinterpret_cast<float4*>(c.warp_part + (e.i * kFlatConsumerWarps + warp) * 4) = make_float4(s1, s2, s3, 0.f);
                     mbar_arrive(c.p1d0 + 8 * e.i);
                 }
                 if (tid == 0) flat_trace(g, s, TR_P1_END);
@@ -800,14 +946,23 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                 const PieceId pc = piece_of(g, j * G + cta);
                 const size_t goff = ((size_t)pc.slab * (size_t)p.M) * sizeof(T) + (size_t)pc.k * g.PV * 16;
                 char* dxdst = reinterpret_cast<char*>(p.dx) + goff;
-                char* drdst = NS == 3 ? reinterpret_cast<char*>(p.dres) + goff : nullptr;
+                char* drdst = NS == 3 ? reinterpret_cast<char*>(DUAL ? p.dx2 : p.dres) + goff : nullptr;
                 const uint32_t base = c.dataB + rb.i * c.slot_bytes;
                 if (tid == 0) flat_trace(g, j, TR_P2_WAIT);
                 mbar_wait_park(c.coef0 + 8 * e.i, e.ph);
-                const float* cf = c.coefv + e.i * 8;
+                const float* cf = c.coefv + e.i * kFlatCoefStride;
                 const float4 cq = *reinterpret_cast<const float4*>(cf);
                 const f32x2 A2 = f2_splat(cq.x), B12 = f2_splat(cq.y), B02 = f2_splat(cq.z), mean2 = f2_splat(cq.w),
                             bq2 = f2_splat(cf[4]);
+                f32x2 AB2 = 0ull, B1B2 = 0ull, B0B2 = 0ull, meanB2 = 0ull, bqB2 = 0ull;
+                if (DUAL) {
+                    const float4 cb = *reinterpret_cast<const float4*>(cf + 8);
+                    AB2 = f2_splat(cb.x);
+                    B1B2 = f2_splat(cb.y);
+                    B0B2 = f2_splat(cb.z);
+                    meanB2 = f2_splat(cb.w);
+                    bqB2 = f2_splat(cf[12]);
+                }
                 mbar_wait_park(c.fullB + 8 * rb.i, rb.ph);
                 if (tid == 0) flat_trace(g, j, TR_P2_BEGIN);
                 uint4 qx[U], qg[U], qo[U];
@@ -825,8 +980,10 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                         if (NS == 3) VecT<T>::unpack2(qo[i], of);
 #pragma unroll
                         for (int k = 0; k < VN / 2; ++k) {
-                            const f32x2 gg = bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, A2, bq2, slope);
-                            gf[k] = gg;
+                            const f32x2 gg = DUAL ? bwd_masked_dual<T>(xf[k], of[k], gf[k], mean2, A2, bq2, meanB2, AB2, bqB2, slope)
+                                                  : bwd_masked2<T, EPI>(xf[k], gf[k], NS == 3 ? of[k] : 0ull, mean2, A2, bq2, slope);
+                            // (dual: the second store carries d(x2) instead of d(residual))
+                            gf[k] = DUAL ? f2_fma(AB2, gg, f2_fma(B1B2, sizeof(T) == 4 ? f2_sub(of[k], meanB2) : of[k], B0B2)) : gg;
                             xf[k] = f2_fma(A2, gg, f2_fma(B12, sizeof(T) == 4 ? f2_sub(xf[k], mean2) : xf[k], B02));
                         }
                         stg_stream(dxdst + (size_t)v * 16, VecT<T>::pack2v(xf));
@@ -856,7 +1013,8 @@ struct Traits {
     using Geom = FlatGeom;
     static constexpr int kThreads = kFlatThreads, kCtasPerSm = kFlatCtasPerSm, kConsumerThreads = kFlatConsumerThreads,
                          kMaxSlots = kFlatMaxSlots, kMaxLag = kFlatMaxLag, kMaxPieces = kFlatMaxPieces,
-                         kMinPieceVecs = kFlatMinPieceVecs, kCtlBytes = flat_ctl_bytes();
+                         kMinPieceVecs = kFlatMinPieceVecs, kCtlBytes = flat_ctl_bytes(),
+                         kDualExtraBytes = flat_dual_extra_bytes();
 };
 
 }  // namespace MICN_FLAT_NS

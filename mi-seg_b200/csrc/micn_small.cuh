@@ -259,6 +259,13 @@ __device__ __forceinline__ void small_fold_channel(const BwdParams& p, long long
         }
         p.dbeta[(long long)s * p.C + ch] = acc_b;
         p.dgamma[(long long)s * p.C + ch] = acc_g;
+        if (p.dgamma2) {  // second norm of the dual epilogue: same sum(g), its own sum(g * xhat2)
+            float acc_g2 = 0.f;
+            for (long long kk = 0; kk < p.N; ++kk)
+                if (load_style(p.styles, kk, p.num_styles, nullptr) == s) acc_g2 += __ldcg(p.ws_sum_dyxh2 + kk * p.C + ch);
+            p.dbeta2[(long long)s * p.C + ch] = acc_b;
+            p.dgamma2[(long long)s * p.C + ch] = acc_g2;
+        }
     }
 }
 

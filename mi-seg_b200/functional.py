@@ -254,6 +254,122 @@ class _InstanceCondFn(torch.autograd.Function):
         return tuple(grads)
 
 
+# ------------------------------------------------------------------------------------------------ dual-norm epilogue
+_dual_ok = {}
+
+
+def dual_supported(n: int, c: int, m: int, dtype: torch.dtype, backward: bool) -> bool:
+    """Whether micn_fwd_dual / micn_bwd_dual take a problem of this shape (cached per shape)."""
+    key = (n, c, m, dtype, backward, torch.cuda.current_device())
+    ok = _dual_ok.get(key)
+    if ok is None:
+        ok = bool(_lib.lib().micn_dual_supported(n, c, m, _DTYPES[dtype], 1 if backward else 0))
+        if len(_dual_ok) > 4096:
+            _dual_ok.clear()
+        _dual_ok[key] = ok
+    return ok
+
+
+class _DualNormFn(torch.autograd.Function):
+    """forward(a, b, styles_dev, eps, slope, present, S, *wa, *ba, *wb, *bb) = lrelu(norm_a(a) + norm_b(b)): the
+    downsample branch of UnetResBlock (dynunet_block.py:113-125 with conv3 / norm3) in one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, a, b, styles_dev, eps, slope, present, num_styles, *params):
+        lib = _lib.lib()
+        dev = a.device
+        affine = len(params) > 0
+        S = num_styles
+        ps = _f32_params(params, dev) if affine else []
+        n, c = a.shape[0], a.shape[1]
+        m = a.numel() // max(n * c, 1)
+        if affine and any(w.numel() != c for w in ps):
+            raise ValueError("instance_cond: parameter length does not match the channel count")
+        y = torch.empty_like(a)
+        stats = torch.empty(4, n * c, dtype=torch.float32, device=dev)  # mean_a, rstd_a, mean_b, rstd_b
+        sp = stats.data_ptr()
+        q = 4 * n * c
+        stream = _raw_stream(dev)
+        ws = _workspace(dev, stream, n, c, m, _DTYPES[a.dtype], S)
+        with _on_device(dev):
+            arrs = [_ptr_array(ps[i * S:(i + 1) * S]) for i in range(4)] if affine else [None] * 4
+            rc = lib.micn_fwd_dual(a.data_ptr(), b.data_ptr(), y.data_ptr(), arrs[0], arrs[1], arrs[2], arrs[3], S,
+                                   styles_dev.data_ptr() if styles_dev is not None else None, sp, sp + q, sp + 2 * q,
+                                   sp + 3 * q, n, c, m, _DTYPES[a.dtype], float(slope), float(eps), ws.data_ptr(),
+                                   ws.numel(), stream)
+        _lib.check(rc, "micn_fwd_dual")
+        ctx.save_for_backward(a, b, styles_dev, stats, *ps)
+        ctx.meta = (n, c, m, float(slope), S, affine, present)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        n, c, m, slope, S, affine, present = ctx.meta
+        a, b, styles_dev, stats, *ps = ctx.saved_tensors
+        lib = _lib.lib()
+        dev = a.device
+        dy = dy.contiguous()
+        if dy.dtype != a.dtype:
+            dy = dy.to(a.dtype)
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        need_pg = affine and any(ctx.needs_input_grad[7:])
+        # rows: dgamma_a[S], dbeta_a[S], dgamma_b[S], dbeta_b[S]
+        pg = torch.empty((4 * S, c), dtype=torch.float32, device=dev) if need_pg else None
+        gp = pg.data_ptr() if need_pg else None
+        q = 4 * S * c
+        sp = stats.data_ptr()
+        sq = 4 * n * c
+        stream = _raw_stream(dev)
+        ws = _workspace(dev, stream, n, c, m, _DTYPES[a.dtype], S)
+        with _on_device(dev):
+            arrs = [_ptr_array(ps[i * S:(i + 1) * S]) for i in range(4)] if affine else [None] * 4
+            rc = lib.micn_bwd_dual(dy.data_ptr(), a.data_ptr(), b.data_ptr(), arrs[0], arrs[1], arrs[2], arrs[3], S,
+                                   styles_dev.data_ptr() if styles_dev is not None else None, sp, sp + sq, sp + 2 * sq,
+                                   sp + 3 * sq, da.data_ptr(), db.data_ptr(), gp, gp + q if need_pg else None,
+                                   gp + 2 * q if need_pg else None, gp + 3 * q if need_pg else None, n, c, m,
+                                   _DTYPES[a.dtype], slope, ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "micn_bwd_dual")
+        grads: List[Optional[torch.Tensor]] = [da, db, None, None, None, None, None]
+        if affine:
+            if pg is None:
+                grads.extend([None] * (4 * S))
+            elif present is None:
+                grads.extend(pg.unbind(0))
+            else:
+                grads.extend(g if present[i % S] else None for i, g in enumerate(pg.unbind(0)))
+        return tuple(grads)
+
+
+def instance_cond_dual(a: torch.Tensor, b: torch.Tensor, styles_dev: Optional[torch.Tensor],
+                       weights_a: Sequence[torch.Tensor], biases_a: Sequence[torch.Tensor],
+                       weights_b: Sequence[torch.Tensor], biases_b: Sequence[torch.Tensor], eps: float = 1e-5,
+                       slope: float = 0.01, present: Optional[Sequence[bool]] = None,
+                       num_styles: Optional[int] = None) -> Optional[torch.Tensor]:
+    """lrelu(norm_a(a) + norm_b(b)) in one pass, or None when the dual kernels do not take this problem (the caller
+    then composes `instance_cond(b)` and `instance_cond(a, epilogue="add_lrelu", residual=...)`)."""
+    if not (a.is_cuda and b.is_cuda) or a.dtype not in _DTYPES or a.dtype != b.dtype or a.shape != b.shape or a.dim() < 3:
+        return None
+    if not (len(weights_a) == len(biases_a) == len(weights_b) == len(biases_b)):
+        return None
+    s = len(weights_a) if len(weights_a) else (num_styles or 1)
+    n, c = a.shape[0], a.shape[1]
+    m = a.numel() // max(n * c, 1)
+    if a.numel() == 0 or not a.is_contiguous() or not b.is_contiguous() or a.data_ptr() % 16 or b.data_ptr() % 16:
+        return None
+    need_bwd = torch.is_grad_enabled() and (a.requires_grad or b.requires_grad or any(
+        t.requires_grad for t in list(weights_a) + list(biases_a) + list(weights_b) + list(biases_b)))
+    with _on_device(a.device):
+        if not dual_supported(n, c, m, a.dtype, False) or (need_bwd and not dual_supported(n, c, m, a.dtype, True)):
+            return None
+    if styles_dev is not None and (styles_dev.dim() != 1 or not styles_dev.is_contiguous()):
+        styles_dev = styles_dev.reshape(-1).contiguous()
+    params = list(weights_a) + list(biases_a) + list(weights_b) + list(biases_b)
+    if present is not None and params:
+        params = [t if present[i % s] else t.detach() for i, t in enumerate(params)]
+    return _DualNormFn.apply(a, b, styles_dev, eps, slope, tuple(present) if present is not None else None, s, *params)
+
+
 # ------------------------------------------------------------------------------------------------ channels-last
 _cl_native = True
 _cl_workspaces = {}

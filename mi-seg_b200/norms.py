@@ -20,11 +20,11 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .functional import instance_cond
+from .functional import instance_cond, instance_cond_dual
 
 __all__ = ["FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
            "FastForwardMixin", "make_dropin_classes", "FastInstanceNorm1d", "FastInstanceNorm2d", "FastInstanceNorm3d",
-           "FastPlainForwardMixin", "fast_instance_norm", "set_sync_free_styles", "check_status"]
+           "FastPlainForwardMixin", "fast_instance_norm", "set_sync_free_styles", "check_status", "forward_fused_dual"]
 
 _STYLE_CACHE = {}
 _STYLE_CACHE_MAX = 256
@@ -176,6 +176,46 @@ class FastForwardMixin:
         y = instance_cond(x, styles_dev, w, b, eps=first.eps, epilogue=epilogue, residual=residual,
                           slope=slope, present=present)
         return y.squeeze(0) if unbatched else y
+
+
+def forward_fused_dual(norm_a, a: Tensor, norm_b, b: Tensor, styles, slope: float = 0.01) -> Tensor:
+    """lrelu(norm_a(a, styles) + norm_b(b, styles)): the downsample branch of UnetResBlock
+    (dynunet_block.py:113-125, residual = norm3(conv3(inp)), :82-98).  One kernel per direction when both norms are fast
+    norms of the same family (both conditional with the same number of styles, or both plain) and the dual kernels take
+    the shape; otherwise the two-call composition (norm_b, then norm_a with the add_lrelu epilogue)."""
+    fam_a = isinstance(norm_a, FastForwardMixin), isinstance(norm_a, FastPlainForwardMixin)
+    fam_b = isinstance(norm_b, FastForwardMixin), isinstance(norm_b, FastPlainForwardMixin)
+    y = None
+    if fam_a == fam_b and a.dim() == b.dim() and a.dim() == norm_a._get_no_batch_dim() + 1 and a.shape == b.shape:
+        if fam_a[0] and norm_a.num_styles == norm_b.num_styles:
+            for nm, x in ((norm_a, a), (norm_b, b)):
+                nm._check_input_dim(x)
+                nm._check_input_styles(x, styles)
+            host = _host_styles(styles, norm_a.num_styles)
+            first_a = norm_a._modules["norms"]._modules["0"]
+            first_b = norm_b._modules["norms"]._modules["0"]
+            if a.shape[1] == first_a.num_features == first_b.num_features and first_a.eps == first_b.eps:
+                if host is not None:
+                    styles_dev = _device_styles(host, a.device)
+                    present = [s in host for s in range(norm_a.num_styles)]
+                else:
+                    styles_dev = styles if (styles.dim() == 1 and styles.dtype == torch.int64) else styles.reshape(-1).to(torch.int64)
+                    present = None
+                wa, ba = norm_a._params()
+                wb, bb = norm_b._params()
+                y = instance_cond_dual(a, b, styles_dev, wa, ba, wb, bb, eps=first_a.eps, slope=slope, present=present)
+        elif fam_a[1] and norm_a.affine == norm_b.affine and norm_a.eps == norm_b.eps \
+                and not norm_a.track_running_stats and not norm_b.track_running_stats \
+                and a.shape[1] == norm_a.num_features == norm_b.num_features:
+            wa = [norm_a.weight] if norm_a.affine else []
+            ba = [norm_a.bias] if norm_a.affine else []
+            wb = [norm_b.weight] if norm_b.affine else []
+            bb = [norm_b.bias] if norm_b.affine else []
+            y = instance_cond_dual(a, b, None, wa, ba, wb, bb, eps=norm_a.eps, slope=slope, present=None, num_styles=1)
+    if y is None:
+        residual = norm_b.forward_fused(b, styles, "none")
+        y = norm_a.forward_fused(a, styles, "add_lrelu", residual=residual, slope=slope)
+    return y
 
 
 def _init_checks(track_running_stats: bool) -> None:

@@ -136,6 +136,24 @@ def bwd_epilogue_f64(dout, pre, x, styles, gamma, mean, rstd, slope: float = LRE
     return dx, (g if has_residual else None), dgamma, dbeta, present
 
 
+def fwd_dual_f64(a, b, styles, gamma_a, beta_a, gamma_b, beta_b, slope: float = LRELU_SLOPE, eps: float = EPS_DEFAULT):
+    """out = lrelu(norm_a(a) + norm_b(b)): the downsample branch of UnetResBlock (dynunet_block.py:113-125 with the
+    conv3 / norm3 residual of :82-98, :115-118).  Returns (out, pre, (mean_a, rstd_a), (mean_b, rstd_b))."""
+    ya, ma, ra = fwd_f64(a, styles, gamma_a, beta_a, eps)
+    yb, mb, rb = fwd_f64(b, styles, gamma_b, beta_b, eps)
+    pre = ya + yb
+    return lrelu(pre, slope), pre, (ma, ra), (mb, rb)
+
+
+def bwd_dual_f64(dout, pre, a, b, styles, gamma_a, gamma_b, stats_a, stats_b, slope: float = LRELU_SLOPE):
+    """Backward of fwd_dual_f64: g = dout * lrelu'(pre) flows into both norms.
+    Returns (da, db, dgamma_a, dbeta_a, dgamma_b, dbeta_b, present)."""
+    g = np.asarray(dout, dtype=np.float64) * lrelu_grad(pre, slope)
+    da, dga, dba, present = bwd_f64(g, a, styles, gamma_a, stats_a[0], stats_a[1])
+    db, dgb, dbb, _ = bwd_f64(g, b, styles, gamma_b, stats_b[0], stats_b[1])
+    return da, db, dga, dba, dgb, dbb, present
+
+
 def prelu(v, a):
     return np.where(v > 0, v, v * a)
 

@@ -628,7 +628,7 @@ def test_plain_instance_norm_matches_torch_module_and_functional(pkg):
     assert float((got - want).abs().max() / want.abs().max()) < 1e-5
 
 
-def test_cuda_graph_replay_is_safe(pkg):
+def test_cuda_graph_replay_is_safe(pkg, request):
     """A captured graph replays the same kernel parameters; the flat path's record tags come from the workspace
     (device-side epoch), so records of the previous replay can never be mistaken for current ones."""
     torch.manual_seed(3)
@@ -640,6 +640,8 @@ def test_cuda_graph_replay_is_safe(pkg):
             mod.norms[k].bias.normal_(0, 0.3)
     styles = torch.tensor([1, 0], device="cuda")
     x_static = torch.randn(n, c, s, s, s, device="cuda").bfloat16()
+    pkg._lib.set_option("force_path", 2)  # (this shape would take the resident path, which keeps no cross-launch state)
+    request.addfinalizer(lambda: pkg._lib.set_option("force_path", -1))
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side), torch.no_grad():

@@ -73,6 +73,25 @@ def test_block_epilogue_oracle_matches_reference_golden(path):
     assert o1.shape == g["conv1_out"].shape
 
 
+@pytest.mark.parametrize("path", [p for p in golden_files("block") if "down" in p or "stride2" in p], ids=os.path.basename)
+def test_dual_norm_oracle_matches_reference_golden(path):
+    """lrelu(norm2(conv2_out) + norm3(conv3_out)) - the downsample branch of the real UnetResBlock
+    (dynunet_block.py:113-125 with :82-98) - restated in one function, against the tensors recorded inside the block."""
+    g = load_golden(path)
+    st = g["styles"]
+    tol = 3e-6
+    out, pre, sa, sb = O.fwd_dual_f64(g["conv2_out"], g["conv3_out"], st, g["norm2_gamma"], g["norm2_beta"],
+                                      g["norm3_gamma"], g["norm3_beta"])
+    assert rel_err(out, g["out"]) < tol
+    da, db, dga, dba, dgb, dbb, present = O.bwd_dual_f64(g["dout"], pre, g["conv2_out"], g["conv3_out"], st,
+                                                         g["norm2_gamma"], g["norm3_gamma"], sa, sb)
+    assert rel_err(da, g["conv2_out_grad"]) < tol
+    assert rel_err(db, g["conv3_out_grad"]) < tol
+    assert rel_err(dga, g["norm2_dgamma"]) < 5 * tol and rel_err(dba, g["norm2_dbeta"]) < 5 * tol
+    assert rel_err(dgb, g["norm3_dgamma"]) < 5 * tol and rel_err(dbb, g["norm3_dbeta"]) < 5 * tol
+    assert list(present) == list(g["norm2_present"])
+
+
 def test_styles_validation_messages():
     with pytest.raises(ValueError, match="Expected number of styles as batch size."):
         O.normalize_styles([0], 2, 2)
