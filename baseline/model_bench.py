@@ -128,7 +128,17 @@ def train_step_bench(kind: str, variant: str, pkg, dev, world: int, rank: int, s
     model = net
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        model = DDP(net, device_ids=[dev.index], output_device=dev.index, find_unused_parameters=True)
+        kw = dict(find_unused_parameters=True)  # tune.py:103-109 for instance_cond norms
+        for opt in os.environ.get("MICN_DDP_OPTS", "").split(","):  # experiments: bucket_view, bucket_cap=MB, no_find_unused
+            if opt == "bucket_view":
+                kw["gradient_as_bucket_view"] = True
+            elif opt.startswith("bucket_cap="):
+                kw["bucket_cap_mb"] = int(opt.split("=")[1])
+            elif opt == "no_find_unused":
+                kw["find_unused_parameters"] = False
+                if pkg is not None:
+                    pkg.set_sync_free_styles(True)  # zero gradients instead of None for absent styles: every parameter is used
+        model = DDP(net, device_ids=[dev.index], output_device=dev.index, **kw)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     R = 2  # two synthetic patches per rank (the CT / MR "patch pair"), alternated
@@ -169,8 +179,12 @@ def train_step_bench(kind: str, variant: str, pkg, dev, world: int, rank: int, s
     out = {"ms_per_step": ms_step, "voxels_per_s": batch * ROI ** 3 * world / (ms_step * 1e-3),
            "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "blocks_fused": fused,
            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
-    if profile_share and rank == 0 and world == 1:
-        out["norm_share"] = _norm_kernel_share(step)
+    if profile_share and (world == 1 or os.environ.get("MICN_PROFILE_DDP")):
+        share = _norm_kernel_share(step)  # (every rank runs the profiled steps: they contain collectives)
+        if rank == 0:
+            out["norm_share"] = share
+    if pkg is not None:
+        pkg.set_sync_free_styles(False)
     del model, net, opt
     torch.cuda.empty_cache()
     return out

@@ -60,8 +60,10 @@ def parse_args():
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
     ap.add_argument("--no-model-calls", action="store_true", help="skip the C-Swin-UNETR norm-call-list leg")
     ap.add_argument("--regions", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
-    ap.add_argument("--launch", default="stream", choices=["stream", "graph"],
-                    help="stream: the C-ABI calls are issued every step; graph: one step per buffer set captured once and replayed")
+    ap.add_argument("--launch", default="graph", choices=["stream", "graph"],
+                    help="graph (default): the micn_fwd + micn_bwd pair of every buffer set is captured once into a CUDA graph and "
+                         "replayed, as a captured training step would be (the calls keep no per-launch state on the host); "
+                         "stream: the two C-ABI calls are issued from Python every step")
     ap.add_argument("--model-steps", default="auto", help="comma list of swin_unetr,unetr,unet_cpu,sliding_window; auto = "
                     "swin_unetr + sliding_window at every N, plus unetr and unet_cpu at N=1; none = skip")
     ap.add_argument("--model-step-iters", type=int, default=8)
@@ -640,7 +642,7 @@ def run_ours(args):
     bytes_fwd, bytes_bwd = 2 * E * es, 3 * E * es
 
     # rotating buffer sets, footprint >> L2 (126 MB): every launch reads HBM-cold inputs
-    R = max(3, int(600e6 // (4 * E * es)) + 1)
+    R = max(4, int(600e6 // (4 * E * es)) + 1)
     torch.manual_seed(rank)
     xs = [(torch.randn(n, c, m, device=dev) * 2 + 1).to(tdt) for _ in range(R)]
     dys = [torch.randn(n, c, m, device=dev).to(tdt) for _ in range(R)]
@@ -654,8 +656,9 @@ def run_ours(args):
     # dgamma, dbeta: one bucket per step for the all-reduce, double-buffered so that the collective of step i (a few
     # microseconds of NCCL on one SM) runs while step i+1 computes - the way DDP overlaps its buckets with the
     # rest of backward; a bucket is waited for before it is written again and before the clock stops
-    grads2 = [torch.empty(2, S, c, device=dev) for _ in range(2)]
-    pending = [None, None]
+    # (one bucket per buffer set, so that a captured step always writes the same bucket)
+    grads2 = [torch.empty(2, S, c, device=dev) for _ in range(R)]
+    pending = [None] * R
     overlap = world > 1 and not os.environ.get("MICN_BENCH_SYNC_ALLREDUCE")
     if overlap:  # leave one SM to NCCL (the flat kernels are persistent, one CTA per SM)
         pkg._lib.set_option("flat_grid", torch.cuda.get_device_properties(dev).multi_processor_count - 1)
@@ -681,20 +684,23 @@ def run_ours(args):
     def step(i):
         # forward on set i, backward on the NEXT set (its statistics come from an earlier forward of the
         # same data): neither kernel finds its inputs in L2 from the launch before it
-        b = i & 1
-        fwd(i % R)
+        b = i % R
         if pending[b] is not None:  # the bucket's previous all-reduce must be through before it is overwritten
             pending[b].wait()
             pending[b] = None
-        bwd((i + 1) % R, grads2[b])
+        launch_pair(b)
         if world > 1 and not os.environ.get("MICN_BENCH_NO_ALLREDUCE"):  # (debug knob: isolate the collective)
             if overlap:
                 pending[b] = dist.all_reduce(grads2[b], async_op=True)
             else:
                 dist.all_reduce(grads2[b])
 
+    def launch_pair(b):  # replaced by a graph replay under --launch graph
+        fwd(b)
+        bwd((b + 1) % R, grads2[b])
+
     def drain():
-        for b in range(2):
+        for b in range(R):
             if pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
@@ -720,8 +726,6 @@ def run_ours(args):
     graphs = None
     bwd(0, grads2[0])  # (first launch of every kernel outside any capture: function attributes are set once)
     if args.launch == "graph":
-        if world > 1:
-            raise SystemExit("bench.py: --launch graph is a single-GPU option (the collective is issued from the host)")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         graphs = []
@@ -730,14 +734,14 @@ def run_ours(args):
             for i in range(R):
                 g_ = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_, stream=side):
-                    fwd(i % R)
-                    bwd((i + 1) % R, grads2[i & 1])
+                    fwd(i)
+                    bwd((i + 1) % R, grads2[i])
                 graphs.append(g_)
         torch.cuda.current_stream().wait_stream(side)
         stream = torch.cuda.current_stream().cuda_stream
 
-        def step(i):  # noqa: F811 - replaces the stream-launch step
-            graphs[i % R].replay()
+        def launch_pair(b):  # noqa: F811 - the collective (N > 1) is still issued from the host after every replay
+            graphs[b].replay()
 
     sampler = ClockSampler(local)
     if rank == 0:  # BEFORE the pre-warm: nvidia-smi takes ~0.2 s to produce its first sample

@@ -7,7 +7,7 @@ interface that calls them.  The directory name carries a hyphen, so import it wi
 """
 from . import _lib
 from .blocks import fuse_blocks
-from .functional import instance_cond, reset_workspaces, set_channels_last_native
+from .functional import binding_in_use, instance_cond, reset_workspaces, set_binding, set_channels_last_native
 from .inference import sliding_window_inference, window_slices
 from .integration import convert_module, convert_plain, install, install_plain, uninstall
 from .norms import (FastConditionalInstanceNorm1d, FastConditionalInstanceNorm2d, FastConditionalInstanceNorm3d,
@@ -18,4 +18,4 @@ __all__ = ["instance_cond", "reset_workspaces", "install", "install_plain", "uni
            "convert_plain", "fuse_blocks", "FastInstanceNorm1d", "FastInstanceNorm2d", "FastInstanceNorm3d",
            "fast_instance_norm", "set_channels_last_native", "sliding_window_inference", "window_slices",
            "FastConditionalInstanceNorm1d", "FastConditionalInstanceNorm2d", "FastConditionalInstanceNorm3d",
-           "make_dropin_classes", "set_sync_free_styles", "check_status", "_lib"]
+           "make_dropin_classes", "set_sync_free_styles", "check_status", "set_binding", "binding_in_use", "_lib"]

@@ -94,8 +94,13 @@ def check(rc: int, what: str) -> None:
         raise MicnError(f"{what} failed: rc={rc} ({msg.decode() if msg else '?'})")
 
 
+option_generation = 0  # bumped by every set_option: plans cached on the Python side (dual_supported) key on it
+
+
 def set_option(key: str, value: int) -> None:
+    global option_generation
     check(lib().micn_set_option(key.encode(), int(value)), f"micn_set_option({key})")
+    option_generation += 1
 
 
 def get_option(key: str) -> int:

@@ -14,6 +14,8 @@ No CPU path: CPU tensors raise.  All statistics / parameter math is fp32; I/O dt
 from __future__ import annotations
 
 import ctypes
+import importlib.util
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -25,6 +27,54 @@ _EPILOGUES = {"none": _lib.EPI_NONE, "lrelu": _lib.EPI_LRELU, "add_lrelu": _lib.
 
 _workspaces = {}
 _ptr_arrays = {}
+
+# ---- host-side binding: the C++ autograd functions of csrc/micn_torch.cpp when _micn_torch.so was built, else the
+#      torch.autograd.Function / ctypes classes below.  Both issue the same C-ABI calls into libmicn.so.
+_binding_choice = os.environ.get("MICN_BINDING", "auto")  # auto | cpp | ctypes
+_ext_module = None
+_ext_tried = False
+
+
+def set_binding(which: str) -> None:
+    """"auto" (C++ binding when built), "cpp" (require it) or "ctypes" (the Python path)."""
+    global _binding_choice
+    if which not in ("auto", "cpp", "ctypes"):
+        raise ValueError("binding must be 'auto', 'cpp' or 'ctypes'")
+    _binding_choice = which
+
+
+def _ext():
+    global _ext_module, _ext_tried
+    if _binding_choice == "ctypes":
+        return None
+    if not _ext_tried:
+        _ext_tried = True
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_micn_torch.so")
+        if os.path.exists(path):
+            _lib.lib()  # libmicn.so first (the binding links against it)
+            spec = importlib.util.spec_from_file_location("_micn_torch", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            if mod.micn_version() != _lib.lib().micn_version():
+                raise _lib.MicnError("_micn_torch.so and libmicn.so were built from different sources: rebuild both")
+            _ext_module = mod
+    if _ext_module is None and _binding_choice == "cpp":
+        raise _lib.MicnError("the C++ binding mi-seg_b200/_micn_torch.so is not built (make -C mi-seg_b200/csrc)")
+    return _ext_module
+
+
+def binding_in_use() -> str:
+    return "cpp" if _ext() is not None else "ctypes"
+
+
+def _present_mask(present) -> int:
+    if present is None:
+        return -1
+    mask = 0
+    for i, p in enumerate(present):
+        if p:
+            mask |= 1 << i
+    return mask
 
 
 _ws_need = {}
@@ -260,7 +310,7 @@ _dual_ok = {}
 
 def dual_supported(n: int, c: int, m: int, dtype: torch.dtype, backward: bool) -> bool:
     """Whether micn_fwd_dual / micn_bwd_dual take a problem of this shape (cached per shape)."""
-    key = (n, c, m, dtype, backward, torch.cuda.current_device())
+    key = (n, c, m, dtype, backward, torch.cuda.current_device(), _lib.option_generation)
     ok = _dual_ok.get(key)
     if ok is None:
         ok = bool(_lib.lib().micn_dual_supported(n, c, m, _DTYPES[dtype], 1 if backward else 0))
@@ -367,6 +417,10 @@ def instance_cond_dual(a: torch.Tensor, b: torch.Tensor, styles_dev: Optional[to
     params = list(weights_a) + list(biases_a) + list(weights_b) + list(biases_b)
     if present is not None and params:
         params = [t if present[i % s] else t.detach() for i, t in enumerate(params)]
+    ext = _ext()
+    if ext is not None:
+        ws = _workspace(a.device, _raw_stream(a.device), n, c, m, _DTYPES[a.dtype], s)
+        return ext.instance_cond_dual(a, b, styles_dev, ws, float(eps), float(slope), _present_mask(present), s, params)
     return _DualNormFn.apply(a, b, styles_dev, eps, slope, tuple(present) if present is not None else None, s, *params)
 
 
@@ -499,11 +553,29 @@ def instance_cond(x: torch.Tensor, styles_dev: Optional[torch.Tensor], weights: 
         # find_unused_parameters=True (tune.py:103-109) sees them as unused instead of waiting for a hook that never fires.
         weights = [w if p else w.detach() for w, p in zip(weights, present)]
         biases = [b if p else b.detach() for b, p in zip(biases, present)]
+    ext = _ext() if (x.is_cuda and x.dtype in _DTYPES) else None
     if epilogue == "none" and x.is_cuda and x.dtype in _DTYPES:
         x_cl = _channels_last_view(x)
         if x_cl is not None:  # token-major input: reduce the strided columns in place, keep the layout
-            y_cl = _InstanceCondClFn.apply(x_cl, styles_dev, eps, tuple(present) if present is not None else None, s,
-                                           *weights, *biases)
+            if ext is not None:
+                n, c = x_cl.shape[0], x_cl.shape[-1]
+                ws = _cl_workspace(x.device, _raw_stream(x.device), n, c, x_cl.numel() // max(n * c, 1))
+                y_cl = ext.instance_cond_cl(x_cl, styles_dev, ws, float(eps), _present_mask(present), s,
+                                            list(weights) + list(biases))
+            else:
+                y_cl = _InstanceCondClFn.apply(x_cl, styles_dev, eps, tuple(present) if present is not None else None, s,
+                                               *weights, *biases)
             return y_cl.permute([0, x.dim() - 1] + list(range(1, x.dim() - 1)))
+    if ext is not None:
+        n, c = x.shape[0], x.shape[1]
+        m = x.numel() // max(n * c, 1)
+        ws = _workspace(x.device, _raw_stream(x.device), n, c, m, _DTYPES[x.dtype], s)
+        slope_t = None
+        if isinstance(slope, torch.Tensor):  # nn.PReLU weight: stays in the autograd graph (its gradient comes back)
+            _slope_tensor(slope, x.device)  # (validation only)
+            slope_t = slope.reshape(1) if slope.dtype == torch.float32 else slope.float().reshape(1)
+        return ext.instance_cond(x, styles_dev, residual, slope_t, ws, float(eps), _EPILOGUES[epilogue],
+                                 0.0 if slope_t is not None else float(slope), _present_mask(present), s,
+                                 list(weights) + list(biases))
     return _InstanceCondFn.apply(x, styles_dev, residual, eps, _EPILOGUES[epilogue], slope,
                                  tuple(present) if present is not None else None, s, *weights, *biases)
