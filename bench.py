@@ -64,6 +64,10 @@ def parse_args():
                     help="graph (default): the micn_fwd + micn_bwd pair of every buffer set is captured once into a CUDA graph and "
                          "replayed, as a captured training step would be (the calls keep no per-launch state on the host); "
                          "stream: the two C-ABI calls are issued from Python every step")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: how d(gamma)/d(beta) are all-reduced every step.  fused (default): inside the backward kernel, "
+                         "records stored straight into every peer's memory over NVLink (micn_bwd_allreduce); nccl: an "
+                         "asynchronous ncclAllReduce per step overlapped with the next step (round 1's scheme)")
     ap.add_argument("--model-steps", default="auto", help="comma list of swin_unetr,unetr,unet_cpu,sliding_window; auto = "
                     "swin_unetr + sliding_window at every N, plus unetr and unet_cpu at N=1; none = skip")
     ap.add_argument("--model-step-iters", type=int, default=8)
@@ -659,7 +663,15 @@ def run_ours(args):
     # (one bucket per buffer set, so that a captured step always writes the same bucket)
     grads2 = [torch.empty(2, S, c, device=dev) for _ in range(R)]
     pending = [None] * R
-    overlap = world > 1 and not os.environ.get("MICN_BENCH_SYNC_ALLREDUCE")
+    # N > 1, default: the exchange is fused into the backward kernel over NVLink peer memory (no NCCL call in the step)
+    px, px_note = None, None
+    if world > 1 and args.collective == "fused":
+        try:
+            px = pkg.PeerExchange(c, S, dev)
+            px_note = f"peer buffers mapped with {px.how}"
+        except Exception as e:  # noqa: BLE001 - no peer access on this box: NCCL it is
+            px_note = "fused exchange unavailable (" + repr(e)[:200] + "): NCCL all-reduce instead"
+    overlap = world > 1 and px is None and not os.environ.get("MICN_BENCH_SYNC_ALLREDUCE")
     if overlap:  # leave one SM to NCCL (the flat kernels are persistent, one CTA per SM)
         pkg._lib.set_option("flat_grid", torch.cuda.get_device_properties(dev).multi_processor_count - 1)
     wsb = lib.micn_workspace_bytes(n, c, m, code, S)
@@ -681,6 +693,15 @@ def run_ours(args):
         if rc:
             raise RuntimeError(f"micn_bwd rc={rc}")
 
+    def bwd_fused(i, grads, mode=2):
+        # mode 2 (MICN_FOLD_PREVIOUS): `grads` receives the all-reduced gradients of the PREVIOUS step - the bucket completes
+        # one step behind, as with the asynchronous NCCL scheme; drain() folds the last step's with micn_allreduce_fold
+        rc = lib.micn_bwd_allreduce(dys[i].data_ptr(), xs[i].data_ptr(), None, gp, bp, S, styles.data_ptr(), means[i].data_ptr(),
+                                    rstds[i].data_ptr(), dxs[i].data_ptr(), None, grads[0].data_ptr(), grads[1].data_ptr(),
+                                    n, c, m, c * m, m, code, epi, 0.01, ws.data_ptr(), wsb, px.ptrs, rank, world, mode, stream)
+        if rc:
+            raise RuntimeError(f"micn_bwd_allreduce rc={rc}")
+
     def step(i):
         # forward on set i, backward on the NEXT set (its statistics come from an earlier forward of the
         # same data): neither kernel finds its inputs in L2 from the launch before it
@@ -689,7 +710,7 @@ def run_ours(args):
             pending[b].wait()
             pending[b] = None
         launch_pair(b)
-        if world > 1 and not os.environ.get("MICN_BENCH_NO_ALLREDUCE"):  # (debug knob: isolate the collective)
+        if world > 1 and px is None and not os.environ.get("MICN_BENCH_NO_ALLREDUCE"):  # (debug knob: isolate the collective)
             if overlap:
                 pending[b] = dist.all_reduce(grads2[b], async_op=True)
             else:
@@ -697,9 +718,13 @@ def run_ours(args):
 
     def launch_pair(b):  # replaced by a graph replay under --launch graph
         fwd(b)
-        bwd((b + 1) % R, grads2[b])
+        (bwd_fused if px is not None else bwd)((b + 1) % R, grads2[b])
 
     def drain():
+        if px is not None:  # the last step's exchange (every earlier one was folded by the step after it)
+            rc = lib.micn_allreduce_fold(px.ptrs, rank, world, c, S, grads2[0][0].data_ptr(), grads2[0][1].data_ptr(), stream)
+            if rc:
+                raise RuntimeError(f"micn_allreduce_fold rc={rc}")
         for b in range(R):
             if pending[b] is not None:
                 pending[b].wait()
@@ -711,10 +736,13 @@ def run_ours(args):
 
     # ---- N > 1: prove once that the collective delivers the right numbers (sum over ranks of the rank-local dgamma/dbeta)
     allreduce_check = None
-    if world > 1:
+    if world > 1 and not os.environ.get("MICN_BENCH_SKIP_CHECK"):  # (debug knob for timing-only experiments)
         bwd(0, grads2[0])
         local = grads2[0].clone()
-        dist.all_reduce(grads2[0])
+        if px is not None:
+            bwd_fused(0, grads2[0], 1)  # synchronous fold (every rank makes this call: the exchange is a collective)
+        else:
+            dist.all_reduce(grads2[0])
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local)
         expect = torch.stack(parts).double().sum(0)
@@ -735,7 +763,7 @@ def run_ours(args):
                 g_ = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_, stream=side):
                     fwd(i)
-                    bwd((i + 1) % R, grads2[i])
+                    (bwd_fused if px is not None else bwd)((i + 1) % R, grads2[i])
                 graphs.append(g_)
         torch.cuda.current_stream().wait_stream(side)
         stream = torch.cuda.current_stream().cuda_stream
@@ -777,7 +805,12 @@ def run_ours(args):
             launches_region = (pkg._lib.get_option("launches") - launches0) if graphs is None else 2 * args.steps
     t_wall1 = time.perf_counter()
     launches = launches_region
-    if world > 1:  # max over ranks, per region
+    per_rank_us = None
+    if world > 1:  # max over ranks, per region (the spread between the GPUs of the box is reported beside it)
+        mine = torch.tensor([statistics.median(region_ms) / args.steps * 1e3], device=dev, dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_us = [round(float(v.item()), 2) for v in allr]
         t = torch.tensor(region_ms, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         region_ms = [float(v) for v in t.tolist()]
@@ -938,7 +971,13 @@ def run_ours(args):
         "config": workload_config(n, c, s, args.dtype, world, args.epilogue),
         "notes": {"l2": f"{R} rotating buffer sets ({R * 4 * E * es / 1e6:.0f} MB) > 126 MB L2; backward reads a "
                         "different set than the forward before it",
-                  "collective": ("all_reduce(dgamma,dbeta) per step over NCCL, overlapped with the next step's kernels "
+                  "collective": ("d(gamma)/d(beta) all-reduced INSIDE the backward kernel: every rank stores its per-channel sums "
+                                 "into every peer's memory over NVLink (micn_bwd_allreduce, MICN_FOLD_PREVIOUS; " + str(px_note) +
+                                 "); the records of step i are folded in rank order at the start of step i+1's kernel "
+                                 "(one-step lag, like an asynchronous bucket), the last step's by micn_allreduce_fold inside "
+                                 "the timed region; no NCCL call in the step"
+                                 if px is not None else
+                                 "all_reduce(dgamma,dbeta) per step over NCCL, overlapped with the next step's kernels "
                                  "(double-buffered buckets, waited before reuse and before the clock stops; "
                                  "147 of 148 SMs run the norm kernels, one is left to NCCL)" if overlap else
                                  "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none"),
@@ -946,7 +985,8 @@ def run_ours(args):
                   "timing": f"{prewarm} untimed pre-warm steps, then {len(region_ms)} regions of {args.steps} steps "
                             "(CUDA events, barrier + synchronize on both sides, max over ranks per region); "
                             "ms_per_step = median region / steps"},
-        "regions_ms": region_ms, "allreduce_check_rel_err": allreduce_check,
+        "regions_ms": region_ms, "allreduce_check_rel_err": allreduce_check, "collective_note": px_note,
+        "per_rank_us_per_step": per_rank_us,
         "voxels_per_s": world * n * m / (ms_step * 1e-3),
         "frac_of_peak": value / world / peak,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),

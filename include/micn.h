@@ -40,6 +40,7 @@ extern "C" {
 
 #define MICN_VERSION 100 /* 0.1.0 */
 #define MICN_MAX_STYLES 16
+#define MICN_MAX_PEERS 16 /* GPUs of one NVLink box taking part in micn_bwd_allreduce */
 
 /* I/O element types */
 enum { MICN_F32 = 0, MICN_BF16 = 1, MICN_F16 = 2 };
@@ -115,6 +116,40 @@ int micn_bwd(const void* dy, const void* x, const void* act_out,
              int64_t x_stride_n, int64_t x_stride_c,
              int dtype, int epilogue, float slope,
              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward with the data-parallel exchange of the per-style parameter gradients FUSED into the kernel (the
+ * one collective of the path; tune.py:103-109 does it with DDP's NCCL all-reduce).  One process per GPU of an NVLink box;
+ * `peer_bufs` is a HOST array of `world` DEVICE pointers: entry r is rank r's exchange buffer as mapped into THIS process
+ * (CUDA IPC / symmetric memory; entry `rank` is the local one), each micn_peer_buffer_bytes() large, 16-byte aligned and
+ * zero-filled once.  As soon as the sums of a channel are final, the kernel stores them as self-validating 16-byte records
+ * straight into every peer's buffer (st.relaxed.sys over NVLink); at its end it folds the `world` records of every channel
+ * straight into every peer's buffer (st.relaxed.sys over NVLink); the `world` records of every channel are then folded from
+ * the rank's OWN buffer in rank order into dgamma / dbeta = the SUM over all ranks (bit-identical on every rank):
+ *   MICN_FOLD_THIS      at the end of this kernel (synchronous all-reduce: exposes one NVLink latency + the skew between
+ *                       the GPUs, a few microseconds, instead of a ~17 us NCCL launch);
+ *   MICN_FOLD_PREVIOUS  at the START of this kernel, the PREVIOUS call's exchange (its records arrived a whole kernel ago:
+ *                       nothing to wait for) - dgamma / dbeta then lag one call behind, the way an asynchronous bucketed
+ *                       all-reduce completes behind the backward pass; micn_allreduce_fold() delivers the last call's;
+ *   MICN_FOLD_NONE      only store the records (fold later with micn_allreduce_fold()).
+ * Requirements: every rank makes the same sequence of micn_bwd_allreduce calls on its buffer (the record tag is a launch
+ * counter kept in the buffer, CUDA-graph safe); the problem must take the flat path (MICN_ERR_UNSUPPORTED otherwise: fall
+ * back to micn_bwd + NCCL). */
+enum { MICN_FOLD_NONE = 0, MICN_FOLD_THIS = 1, MICN_FOLD_PREVIOUS = 2 };
+size_t micn_peer_buffer_bytes(int64_t C, int num_styles, int world);
+/* Folds the exchange of the most recent micn_bwd_allreduce call on this buffer (a small kernel on `stream`). */
+int micn_allreduce_fold(void* const* peer_bufs, int rank, int world, int64_t C, int num_styles, float* dgamma, float* dbeta,
+                        void* stream);
+int micn_bwd_allreduce(const void* dy, const void* x, const void* act_out,
+                       const float* const* gamma, const float* const* beta, int num_styles,
+                       const int64_t* styles,
+                       const float* save_mean, const float* save_rstd,
+                       void* dx, void* dresidual,
+                       float* dgamma, float* dbeta,
+                       int64_t N, int64_t C, int64_t M,
+                       int64_t x_stride_n, int64_t x_stride_c,
+                       int dtype, int epilogue, float slope,
+                       void* workspace, size_t workspace_bytes,
+                       void* const* peer_bufs, int rank, int world, int fold_mode, void* stream);
 
 /* The same two calls with the activation slope read from DEVICE memory: `slope_dev` points at the single weight of
  * the nn.PReLU that follows the norm in C-UNet's ADN block ("NDA": norm -> dropout(0) -> PReLU,

@@ -17,6 +17,8 @@ MICN_F32, MICN_BF16, MICN_F16 = 0, 1, 2
 EPI_NONE, EPI_LRELU, EPI_ADD_LRELU, EPI_NORM_ADD_LRELU = 0, 1, 2, 3
 ERR_UNSUPPORTED = -7
 MAX_STYLES = 16
+MAX_PEERS = 16
+FOLD_NONE, FOLD_THIS, FOLD_PREVIOUS = 0, 1, 2
 
 c_void_p, c_int, c_int64, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t,
                                                ctypes.c_float)
@@ -35,6 +37,11 @@ SYMBOLS = {
     "micn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                          c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "micn_peer_buffer_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "micn_bwd_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                   c_int, c_int, c_float, c_void_p, c_size_t, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "micn_allreduce_fold": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "micn_fwd_prelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_float,
                                c_void_p, c_size_t, c_void_p]),

@@ -70,6 +70,7 @@ struct Options {
     std::atomic<long long> res_cs{-1};        // resident path: force the cluster size (1..8)
     std::atomic<long long> res_min_bytes{-1}; // smallest slab the resident path takes
     std::atomic<long long> res_off{-1};       // 1: never the resident path (experiments)
+    std::atomic<long long> xchg_dbg{-1};      // bring-up bits of the fused peer exchange: 1 no start fold, 2 no header atomic, 4 no peer stores
     std::atomic<long long> res_copies{-1};    // bulk copies per stream of a CTA's share (default 3)
     std::atomic<long long> res_trace{0};      // bring-up: device pointer of a [grid][8] int64 trace buffer
     std::atomic<long long> flat_refuse{-1};   // 1: behave as if the cooperative launch had been refused (tests the fallback chain)
@@ -102,7 +103,7 @@ const OptName kOptNames[] = {
     {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
-    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"res_cs", &g_opt.res_cs}, {"res_min_bytes", &g_opt.res_min_bytes}, {"res_off", &g_opt.res_off}, {"res_copies", &g_opt.res_copies}, {"res_trace", &g_opt.res_trace}, {"flat_trace", &g_opt.flat_trace},
+    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"res_cs", &g_opt.res_cs}, {"res_min_bytes", &g_opt.res_min_bytes}, {"res_off", &g_opt.res_off}, {"xchg_dbg", &g_opt.xchg_dbg}, {"res_copies", &g_opt.res_copies}, {"res_trace", &g_opt.res_trace}, {"flat_trace", &g_opt.flat_trace},
     {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
     {"flat_shape_fwd", &g_opt.flat_shape_fwd}, {"flat_shape_bwd", &g_opt.flat_shape_bwd}, {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
@@ -704,7 +705,8 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
     if (fp == 1 && can_cluster) use_cluster = true;
     const bool ds = EPI == MICN_EPI_LRELU && p.dslope != nullptr;
     if (ds) use_cluster = false;  // the slope-gradient partials are produced by the resident, flat and small kernels only
-    if (res_wanted(fp, can_cluster, slab_bytes) && !(p.dgamma && p.N > 1 && !p.ws_chan_cnt)) {
+    const bool xchg = p.xchg_world > 1;  // fused peer exchange of the parameter gradients: flat kernels only
+    if (!xchg && res_wanted(fp, can_cluster, slab_bytes) && !(p.dgamma && p.N > 1 && !p.ws_chan_cnt)) {
         int rrc;
         if (ds)
             rrc = res_run(res::micn_bwd_res_kernel<T, EPI, EPI == MICN_EPI_LRELU>, NS, p, slabs, slab_bytes, d, st);
@@ -712,7 +714,7 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
             rrc = res_run(res::micn_bwd_res_kernel<T, EPI, false>, NS, p, slabs, slab_bytes, d, st);
         if (rrc != kNotTaken) return rrc;
     }
-    if (can_cluster && ws_flat && (fp == 2 || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
+    if (can_cluster && ws_flat && (fp == 2 || xchg || (fp < 0 && slab_bytes >= flat_min_bytes()))) {
         int frc;
         if (g_opt.flat_shape_bwd.load() == 2) {
             auto kernel = ds ? flat2::micn_bwd_flat_kernel<T, EPI, EPI == MICN_EPI_LRELU> : flat2::micn_bwd_flat_kernel<T, EPI, false>;
@@ -723,6 +725,7 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
         }
         if (frc != kFlatNotTaken) return frc;
     }
+    if (xchg) return MICN_ERR_UNSUPPORTED;
     if (use_cluster) {
         auto kernel = micn_bwd_cluster_kernel<T, EPI>;
         int rc = plan_cluster(kernel, NS, EPI == MICN_EPI_ADD_LRELU ? 2 : 1, slabs, slab_bytes, d, &pl);
@@ -1070,13 +1073,20 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
                     const float* const* beta, int num_styles, const int64_t* styles, const float* save_mean,
                     const float* save_rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C,
                     int64_t M, int64_t x_stride_n, int64_t x_stride_c, int dtype, int epilogue, float slope,
-                    const float* slope_dev, float* dslope_partial, void* workspace, size_t workspace_bytes, void* stream) {
+                    const float* slope_dev, float* dslope_partial, void* workspace, size_t workspace_bytes, void* stream,
+                    void* const* peer_bufs = nullptr, int peer_rank = 0, int peer_world = 1, int peer_mode = 1) {
     const int es = elem_size(dtype);
     if (!es) return MICN_ERR_BAD_DTYPE;
     if (N < 0 || C < 0 || M < 0) return MICN_ERR_BAD_ARG;
     if (num_styles < 1) return MICN_ERR_BAD_ARG;
     if (num_styles > MICN_MAX_STYLES) return MICN_ERR_TOO_MANY_STYLES;
     if ((dgamma == nullptr) != (dbeta == nullptr)) return MICN_ERR_BAD_ARG;
+    if (peer_world > 1) {
+        if (!peer_bufs || peer_world > MICN_MAX_PEERS || peer_rank < 0 || peer_rank >= peer_world || !dgamma) return MICN_ERR_BAD_ARG;
+        if (N == 0 || C == 0 || M == 0) return MICN_ERR_UNSUPPORTED;  // (every rank must take part: no empty shards)
+        for (int r = 0; r < peer_world; ++r)
+            if (!peer_bufs[r] || (reinterpret_cast<uintptr_t>(peer_bufs[r]) & 15u)) return MICN_ERR_BAD_ARG;
+    }
     if (N == 0 || C == 0 || M == 0) {
         if (dgamma && C > 0) {
             cudaStream_t st = (cudaStream_t)stream;
@@ -1140,6 +1150,10 @@ static int bwd_impl(const void* dy, const void* x, const void* act_out, const fl
     p.slope = slope;
     p.slope_dev = slope_dev;
     p.dslope = dslope_partial;
+    p.xchg_rank = peer_rank;
+    p.xchg_world = peer_world > 1 ? peer_world : 1;
+    p.xchg_mode = peer_mode | ((int)std::max<long long>(0, g_opt.xchg_dbg.load()) << 4);  // (bring-up bits, see micn_flat.cuh)
+    for (int r = 0; r < peer_world && peer_world > 1; ++r) p.xchg_peers[r] = peer_bufs[r];
 
     const bool can_cluster = d->cc_major >= 9 && aligned16(x) && aligned16(dy) && aligned16(dx) &&
                              (!p.act_out || aligned16(p.act_out)) && (!p.dres || aligned16(p.dres)) &&
@@ -1169,6 +1183,46 @@ int micn_bwd(const void* dy, const void* x, const void* act_out, const float* co
              void* stream) {
     return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
                     M, x_stride_n, x_stride_c, dtype, epilogue, slope, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+size_t micn_peer_buffer_bytes(int64_t C, int num_styles, int world) {
+    if (C <= 0 || num_styles < 1 || world < 1) return 0;
+    // header, then [4 slots][world source ranks][S*C] 16-byte records
+    return (size_t)64 + (size_t)4 * world * num_styles * (size_t)C * 16;
+}
+
+int micn_allreduce_fold(void* const* peer_bufs, int rank, int world, int64_t C, int num_styles, float* dgamma, float* dbeta,
+                        void* stream) {
+    if (!peer_bufs || world < 2 || world > MICN_MAX_PEERS || rank < 0 || rank >= world || C <= 0 || num_styles < 1 ||
+        num_styles > MICN_MAX_STYLES || !dgamma || !dbeta)
+        return MICN_ERR_BAD_ARG;
+    BwdParams p = {};
+    for (int r = 0; r < world; ++r) {
+        if (!peer_bufs[r]) return MICN_ERR_BAD_ARG;
+        p.xchg_peers[r] = peer_bufs[r];
+    }
+    p.xchg_rank = rank;
+    p.xchg_world = world;
+    p.C = C;
+    p.num_styles = num_styles;
+    p.dgamma = dgamma;
+    p.dbeta = dbeta;
+    const long long entries = (long long)num_styles * C;
+    const unsigned blocks = (unsigned)std::min<long long>(64, (entries + 7) / 8);
+    g_opt.launches.fetch_add(1);
+    flat1::micn_xchg_fold_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int micn_bwd_allreduce(const void* dy, const void* x, const void* act_out, const float* const* gamma, const float* const* beta,
+                       int num_styles, const int64_t* styles, const float* save_mean, const float* save_rstd, void* dx,
+                       void* dresidual, float* dgamma, float* dbeta, int64_t N, int64_t C, int64_t M, int64_t x_stride_n,
+                       int64_t x_stride_c, int dtype, int epilogue, float slope, void* workspace, size_t workspace_bytes,
+                       void* const* peer_bufs, int rank, int world, int fold_mode, void* stream) {
+    if (world < 1 || fold_mode < MICN_FOLD_NONE || fold_mode > MICN_FOLD_PREVIOUS) return MICN_ERR_BAD_ARG;
+    return bwd_impl(dy, x, act_out, gamma, beta, num_styles, styles, save_mean, save_rstd, dx, dresidual, dgamma, dbeta, N, C,
+                    M, x_stride_n, x_stride_c, dtype, epilogue, slope, nullptr, nullptr, workspace, workspace_bytes, stream,
+                    peer_bufs, rank, world, fold_mode);
 }
 
 int micn_bwd_prelu(const void* dy, const void* x, const void* act_out, const float* const* gamma,

@@ -17,6 +17,7 @@
 namespace micn {
 
 constexpr int kMaxStyles = MICN_MAX_STYLES;
+constexpr int kMaxPeers = MICN_MAX_PEERS;
 
 // ---------------------------------------------------------------------------------------------
 // kernel parameter blocks (passed by value; < 1 KB)
@@ -81,6 +82,11 @@ struct BwdParams {
     float* dgamma2;  // [S*C] or null (dbeta2 goes with it)
     float* dbeta2;
     float* ws_sum_dyxh2;  // [N*C] per-slab sum(g*xhat2)
+    // micn_bwd_allreduce: exchange of d(gamma)/d(beta) with the other GPUs of the box, fused into the backward kernel.
+    // xchg_peers[r] = rank r's exchange buffer as mapped in this process (NVLink peer memory; [xchg_rank] is local)
+    void* xchg_peers[kMaxPeers];
+    int xchg_rank, xchg_world;  // world <= 1: no exchange
+    int xchg_mode;              // 1: fold this call's exchange at the kernel's end; 2: fold the PREVIOUS call's at its start
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -289,6 +289,96 @@ __device__ __forceinline__ void ll_wait1(const uint4* p, unsigned tag, unsigned 
     } while (!ll_try(p, tag, a, b));
 }
 
+// ---- the same records at SYSTEM scope: written into another GPU's memory over NVLink, polled by that GPU (micn_bwd_allreduce)
+__device__ __forceinline__ void ll_store_sys(uint4* p, float a, float b, unsigned tag) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag),
+                 "r"(__float_as_uint(b)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_try_sys(const uint4* p, unsigned tag, float& a, float& b) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    a = __uint_as_float(v.x);
+    b = __uint_as_float(v.z);
+    return v.y == tag && v.w == tag;
+}
+// Exchange buffer of one rank: 64-byte header (64-bit word {launch count : CTAs arrived}, as the workspace's), then
+// [4 slots][world source ranks][S*C] records, slot = launch count mod 4.  The tag of a launch is its count on this buffer:
+// every rank makes the same sequence of calls, so all ranks derive the same tag without talking to each other.  Four
+// slots: a peer can run at most two launches ahead of the slowest CTA of this GPU (its launch k+1 needs this GPU's records
+// of launch k), so the slot a fold reads is never the one a peer is writing.
+constexpr unsigned kXchgHeader = 64;
+constexpr unsigned kXchgSlots = 4;
+__device__ __forceinline__ unsigned xchg_epoch_tag(void* local_buf) {
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(local_buf);
+    const unsigned long long old = atomicAdd(w, 1ull);
+    const unsigned e0 = (unsigned)(old >> 32);
+    if ((unsigned)old == gridDim.x - 1) atomicAdd(w, (1ull << 32) - (unsigned long long)gridDim.x);
+    return (e0 + 1u) | 0x80000000u;
+}
+__device__ __forceinline__ uint4* xchg_rec(void* buf, unsigned tag, unsigned src_rank, unsigned world, unsigned SC, unsigned idx) {
+    return reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(buf) + kXchgHeader) +
+           ((size_t)(tag & (kXchgSlots - 1u)) * world + src_rank) * SC + idx;
+}
+// one final (style, channel) entry of this rank -> every rank's buffer (own included)
+__device__ __forceinline__ void xchg_emit(const BwdParams& p, unsigned xtag, unsigned idx, float dbeta, float dgamma) {
+    const unsigned SC = (unsigned)p.num_styles * (unsigned)p.C;
+    if ((p.xchg_mode >> 4) & 4) return;  // (bring-up: time the kernel without the peer stores)
+    for (int r = 0; r < p.xchg_world; ++r)
+        ll_store_sys(xchg_rec(p.xchg_peers[r], xtag, (unsigned)p.xchg_rank, (unsigned)p.xchg_world, SC, idx), dbeta, dgamma, xtag);
+}
+// the same for the S entries of one channel at once, called by a whole warp: lane (s * world + r) stores entry s into
+// rank r's buffer, so all S * world peer stores leave in one instruction
+__device__ __forceinline__ void xchg_emit_channel(const BwdParams& p, unsigned xtag, unsigned ch, int style, float dbeta,
+                                                  float dgamma, int lane) {
+    const unsigned world = (unsigned)p.xchg_world, S = (unsigned)p.num_styles, C = (unsigned)p.C;
+    if ((p.xchg_mode >> 4) & 4) return;
+    for (unsigned q = lane; q < S * world; q += 32) {
+        const unsigned s = q / world, r = q - s * world;
+        const bool hit = (int)s == style;
+        uint4* dst = xchg_rec(p.xchg_peers[r], xtag, (unsigned)p.xchg_rank, world, S * C, s * C + ch);
+        if ((p.xchg_mode >> 4) & 8) {  // (bring-up: plain store instead of st.relaxed.sys)
+            *dst = make_uint4(__float_as_uint(hit ? dbeta : 0.f), xtag, __float_as_uint(hit ? dgamma : 0.f), xtag);
+            continue;
+        }
+        ll_store_sys(dst, hit ? dbeta : 0.f, hit ? dgamma : 0.f, xtag);
+    }
+}
+
+// Fold the exchange of launch `tag`: entry idx of every rank sits in THIS rank's buffer (or arrives within the skew between
+// the GPUs); the (CTA, warp) pairs share the S*C entries, lane r polls rank r's record, the sum runs in rank order on every
+// GPU alike (bit-identical results everywhere).  Called by whole warps; `slot` in [0, nslots) enumerates them.
+__device__ __forceinline__ void xchg_fold(const BwdParams& p, unsigned tag, unsigned slot, unsigned nslots, int lane) {
+    const unsigned SC = (unsigned)p.num_styles * (unsigned)p.C, world = (unsigned)p.xchg_world;
+    void* mine = p.xchg_peers[p.xchg_rank];
+    for (unsigned idx = slot; idx < SC; idx += nslots) {
+        float a = 0.f, b = 0.f;
+        if ((unsigned)lane < world) {
+            const uint4* rec = xchg_rec(mine, tag, (unsigned)lane, world, SC, idx);
+            if (!ll_try_sys(rec, tag, a, b)) {
+                const uint64_t t0 = globaltimer_ns();
+                uint32_t spins = 0;
+                do {
+                    __nanosleep(100);
+                    if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+                } while (!ll_try_sys(rec, tag, a, b));
+            }
+        }
+        float sa = 0.f, sb = 0.f;
+        for (unsigned r = 0; r < world; ++r) {
+            sa += __shfl_sync(0xffffffffu, a, r);
+            sb += __shfl_sync(0xffffffffu, b, r);
+        }
+        if (lane == 0) {
+            p.dbeta[idx] = sa;
+            p.dgamma[idx] = sb;
+        }
+    }
+}
+
 // vectors of a piece (pv vectors, strided over the 512 consumer threads) that land in consumer warp w
 __device__ __forceinline__ unsigned warp_vecs(unsigned pv, unsigned w) {
     const unsigned full = pv / kFlatConsumerThreads, rem = pv % kFlatConsumerThreads;
@@ -765,6 +855,18 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
         const float invM = 1.f / (float)p.M;
         mbar_wait_idle(c.tagbar, 0u);
         const unsigned tag = *c.tagw;
+        // peer exchange: its launch tag is fetched HERE, by the first gather warp (idle until the first piece is through P1),
+        // not by the publish warp, whose first record is on the critical path of every CTA of the slab
+        const bool xchg = p.xchg_world > 1;
+        if (xchg) {
+            if (warp == kFlatGatherWarp0 && lane == 0) c.tagw[1] = xchg_epoch_tag(p.xchg_peers[p.xchg_rank]);
+            bar_sync(2, kFlatGatherWarps * 32);
+        }
+        const unsigned xtag = xchg ? c.tagw[1] : 0u;
+        if (xchg && p.dgamma && (p.xchg_mode & 15) == 2 && (xtag & 0x7fffffffu) > 1u && !((p.xchg_mode >> 4) & 1))
+            // lagged mode: dgamma / dbeta receive the all-reduced gradients of the PREVIOUS call - its records arrived a
+            // whole kernel ago, nothing to wait for - while this call's records travel during this kernel
+            xchg_fold(p, xtag - 1u, cta * kFlatGatherWarps + (warp - kFlatGatherWarp0), G * kFlatGatherWarps, lane);
         for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
             const Ring e = entry_of(j);
             const PieceId pc = piece_of(g, j * G + cta);
@@ -816,7 +918,9 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                 if (p.N == 1) {
                     // one sample: this slab's sums ARE the gradients of its style's row
                     const int style = load_style(p.styles, 0, p.num_styles, nullptr);
-                    for (int s = lane; s < p.num_styles; s += 32) {
+                    if (xchg)  // final for this rank: straight into every rank's exchange buffer (folded later)
+                        xchg_emit_channel(p, xtag, ch, style, S1, S2r, lane);
+                    for (int s = lane; s < p.num_styles && !xchg; s += 32) {
                         p.dbeta[(size_t)s * C + ch] = s == style ? S1 : 0.f;
                         p.dgamma[(size_t)s * C + ch] = s == style ? S2r : 0.f;
                         if (two) {
@@ -845,7 +949,9 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
                             ab = warp_sum(ab);
                             ag = warp_sum(ag);
                             if (two) ag2 = warp_sum(ag2);
-                            if (lane == 0) {
+                            if (lane == 0 && xchg) {
+                                xchg_emit(p, xtag, (unsigned)s * C + ch, ab, ag);
+                            } else if (lane == 0) {
                                 p.dbeta[(size_t)s * C + ch] = ab;
                                 p.dgamma[(size_t)s * C + ch] = ag;
                                 if (two) {
@@ -859,6 +965,8 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             }
             __syncwarp();
         }
+        if (xchg && p.dgamma && (p.xchg_mode & 15) == 1)  // synchronous mode: this call's own exchange, folded at the kernel's end
+            xchg_fold(p, xtag, cta * kFlatGatherWarps + (warp - kFlatGatherWarp0), G * kFlatGatherWarps, lane);
     } else {
         // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
         Ring ra{0u, 0u}, rb{0u, 0u};
@@ -1006,6 +1114,15 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             }
         }
     }
+}
+
+// stand-alone fold of the LATEST call's exchange (micn_allreduce_fold): the tag is the buffer's launch count
+__global__ void micn_xchg_fold_kernel(const BwdParams p) {
+    const unsigned long long hdr = *reinterpret_cast<volatile unsigned long long*>(p.xchg_peers[p.xchg_rank]);
+    const unsigned e = (unsigned)(hdr >> 32);
+    if (e == 0u) return;  // no call has been made on this buffer yet
+    xchg_fold(p, e | 0x80000000u, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5),
+              (int)(threadIdx.x & 31));
 }
 
 // what the host-side planner needs to know about this shape

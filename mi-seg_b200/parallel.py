@@ -7,6 +7,7 @@ the same code runs on `gloo` for the CPU tests.
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Tuple
 
 import torch
@@ -73,3 +74,78 @@ def allreduce_style_grads(params: Iterable[torch.nn.Parameter], group=None, aver
             p.grad = None
         off += n
     return bucket
+
+
+class PeerExchange:
+    """Exchange buffers for `micn_bwd_allreduce` (include/micn.h): the all-reduce of d(gamma) / d(beta) fused into the
+    backward kernel over NVLink peer memory, one process per GPU of one box.
+
+    Every rank allocates one zero-filled buffer, shares it through CUDA IPC (the handle travels with
+    `dist.all_gather_object`), and maps every peer's buffer into its own address space.  `ptrs` is the ctypes array of
+    `world` device pointers the C ABI takes (entry `rank` = the local buffer).  All ranks must then make the same sequence
+    of `micn_bwd_allreduce` calls with this exchange (the record tag is a launch counter kept in the buffer)."""
+
+    def __init__(self, channels: int, num_styles: int, device: torch.device, group=None):
+        import ctypes
+
+        from . import _lib
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group (one process per GPU)")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError(f"at most {_lib.MAX_PEERS} GPUs can take part in the fused exchange")
+        nbytes = int(_lib.lib().micn_peer_buffer_bytes(channels, num_styles, self.world))
+        self.channels, self.num_styles = channels, num_styles
+        self._peers = []  # keeps mapped peer storages alive (CUDA IPC route)
+        self.how = None
+        how = os.environ.get("MICN_PEER_ALLOC", "auto")
+        ptrs = None
+        if how in ("auto", "symm"):
+            try:  # symmetric memory: one allocation mapped into every rank with access for all peers (cuMemSetAccess)
+                import torch.distributed._symmetric_memory as symm_mem
+
+                with torch.cuda.device(device):
+                    self.local = symm_mem.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+                    self._hdl = symm_mem.rendezvous(self.local, dist.group.WORLD if group is None else group)
+                self.local.zero_()
+                torch.cuda.synchronize(device)
+                ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+                self.how = "symmetric_memory"
+            except Exception as e:  # noqa: BLE001
+                if how == "symm":
+                    raise
+                self._symm_error = repr(e)[:300]
+        if ptrs is None:
+            ptrs = self._map_with_cuda_ipc(nbytes, device, group)
+            self.how = "cuda_ipc"
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.local.data_ptr()
+        self.ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        dist.barrier(group=group)  # nobody writes into a buffer that is not mapped (and zeroed) everywhere yet
+
+    def _map_with_cuda_ipc(self, nbytes, device, group):
+        """Every rank exports its buffer with cudaIpcGetMemHandle (torch's storage sharing), the handles travel with
+        all_gather_object, and every peer buffer is opened in this process; a first peer-to-peer copy makes PyTorch
+        enable peer access device -> peer for the kernels."""
+        self.local = torch.zeros(max(nbytes, 2 << 20), dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)
+        handle = self.local.untyped_storage()._share_cuda_()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self.local.data_ptr())
+                continue
+            if not torch.cuda.can_device_access_peer(device.index, int(h[0])):
+                raise RuntimeError(f"PeerExchange: GPU {device.index} cannot access the memory of rank {r}'s GPU")
+            with torch.cuda.device(device):
+                st = torch.UntypedStorage._new_shared_cuda(*h)
+            t = torch.empty(0, dtype=torch.uint8, device=st.device).set_(st)
+            scratch = torch.empty(16, dtype=torch.uint8, device=device)
+            scratch.copy_(t[:16])
+            self._peers.append(t)
+            ptrs.append(t.data_ptr())
+        torch.cuda.synchronize(device)
+        return ptrs
+

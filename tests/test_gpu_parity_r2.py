@@ -555,3 +555,63 @@ def test_dual_norm_at_the_north_star_shape_takes_the_flat_path(pkg):
     assert float((wa - na.norms[1].weight.grad).abs().max() / na.norms[1].weight.grad.abs().max()) < 5e-2
     assert float((wb - nb.norms[1].weight.grad).abs().max() / nb.norms[1].weight.grad.abs().max()) < 5e-2
     assert na.norms[0].weight.grad is None and nb.norms[0].weight.grad is None
+
+
+# ------------------------------------------------------------------------------------------------ fused peer exchange
+def test_fused_peer_exchange_two_ranks_emulated_on_one_gpu(pkg, option):
+    """micn_bwd_allreduce (the NVLink exchange of d(gamma)/d(beta) fused into the flat backward kernel) with BOTH ranks on
+    this GPU: two persistent half-grids (flat_grid = 70 SMs each) run concurrently on two streams, each storing its records
+    into both exchange buffers and folding its own - against the sum of two plain micn_bwd calls.  (The real thing, one
+    process per GPU over NVLink, is tools/peer_xchg_test.py under torchrun.)"""
+    import ctypes
+    lib = pkg._lib.lib()
+    option("flat_grid", 70)
+    n, c, sp, S, world = 2, 6, 48, 3, 2
+    m = sp ** 3
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    gam = 1 + 0.3 * torch.randn(S, c, device="cuda", generator=gen)
+    bet = 0.3 * torch.randn(S, c, device="cuda", generator=gen)
+    gp = (ctypes.c_void_p * S)(*[gam[k].data_ptr() for k in range(S)])
+    bp = (ctypes.c_void_p * S)(*[bet[k].data_ptr() for k in range(S)])
+    nbytes = lib.micn_peer_buffer_bytes(c, S, world)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ptrs = (ctypes.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    wsb = lib.micn_workspace_bytes(n, c, m, 1, S)
+    ranks = []
+    for r in range(world):
+        x = (torch.randn(n, c, m, device="cuda", generator=gen) * 2 + 1).bfloat16()
+        dy = torch.randn(n, c, m, device="cuda", generator=gen).bfloat16()
+        st = torch.tensor([(r + i) % S for i in range(n)], device="cuda")
+        ranks.append(dict(x=x, dy=dy, st=st, y=torch.empty_like(x), dx=torch.empty_like(x), stats=torch.empty(2, n * c, device="cuda"),
+                          ws=torch.zeros(wsb, dtype=torch.uint8, device="cuda"), g=torch.empty(2, S, c, device="cuda"),
+                          gf=torch.empty(2, S, c, device="cuda"), stream=torch.cuda.Stream()))
+    cur = torch.cuda.current_stream().cuda_stream
+    for d in ranks:  # statistics + the reference gradients of each rank
+        assert lib.micn_fwd(d["x"].data_ptr(), d["y"].data_ptr(), None, gp, bp, S, d["st"].data_ptr(), d["stats"][0].data_ptr(),
+                            d["stats"][1].data_ptr(), n, c, m, c * m, m, 1, 0, 0.01, 1e-5, d["ws"].data_ptr(), wsb, cur) == 0
+        assert lib.micn_bwd(d["dy"].data_ptr(), d["x"].data_ptr(), None, gp, bp, S, d["st"].data_ptr(), d["stats"][0].data_ptr(),
+                            d["stats"][1].data_ptr(), d["dx"].data_ptr(), None, d["g"][0].data_ptr(), d["g"][1].data_ptr(), n, c, m,
+                            c * m, m, 1, 0, 0.01, d["ws"].data_ptr(), wsb, cur) == 0
+    torch.cuda.synchronize()
+    expect = ranks[0]["g"] + ranks[1]["g"]
+    for rep in range(3):  # both parities of the record buffers
+        for r, d in enumerate(ranks):
+            d["gf"].fill_(float("nan"))
+        torch.cuda.synchronize()
+        for r, d in enumerate(ranks):
+            rc = lib.micn_bwd_allreduce(d["dy"].data_ptr(), d["x"].data_ptr(), None, gp, bp, S, d["st"].data_ptr(),
+                                        d["stats"][0].data_ptr(), d["stats"][1].data_ptr(), d["dx"].data_ptr(), None,
+                                        d["gf"][0].data_ptr(), d["gf"][1].data_ptr(), n, c, m, c * m, m, 1, 0, 0.01,
+                                        d["ws"].data_ptr(), wsb, ptrs, r, world, 1, d["stream"].cuda_stream)
+            assert rc == 0, rc
+        torch.cuda.synchronize()
+        for d in ranks:
+            assert float((d["gf"] - expect).abs().max() / expect.abs().max()) < 1e-6, rep
+        assert torch.equal(ranks[0]["gf"], ranks[1]["gf"])  # same fold order on every rank: same bits
+    # a shape that cannot take the flat path is refused, not mis-served
+    small = torch.randn(1, 4, 64, device="cuda")
+    rc = lib.micn_bwd_allreduce(small.data_ptr(), small.data_ptr(), None, None, None, 1, None, ranks[0]["stats"][0].data_ptr(),
+                                ranks[0]["stats"][1].data_ptr(), small.data_ptr(), None, ranks[0]["gf"][0].data_ptr(),
+                                ranks[0]["gf"][1].data_ptr(), 1, 4, 64, 256, 64, 0, 0, 0.01, ranks[0]["ws"].data_ptr(), wsb, ptrs, 0,
+                                world, 1, cur)
+    assert rc == -7  # MICN_ERR_UNSUPPORTED

@@ -12,3 +12,4 @@ print("e2e", json.dumps(d.get("e2e"))[:300])
 for k in ("model_step","sliding_window","model_legs_error"):
     print(k, json.dumps(d.get(k))[:1600])
 PY
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tools/peer_xchg_test.py 2>&1 | grep "PEER EXCHANGE\|FAIL\|peer buffers" | sort | uniq -c | head
