@@ -415,18 +415,14 @@ def run_dual_leg(pkg, dev, tdt, n, c, s, peak, reps=40):
 
 
 def ncu_traffic(args, n, c, s):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the backward kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/); None for any other workload."""
-    if (n, c, s, args.dtype, args.epilogue) != (1, 48, 96, "bf16", "none"):
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the backward kernel of this workload, from the committed
+    `ncu --set full` captures (profiles/traffic.json, written from profiles/r02_*.txt); None when this workload has none."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_flat_bwd_bf16_1x48x96.txt")) as f:
-            for line in f:
-                if line.strip().startswith("traffic ="):
-                    return float(line.split()[-1])
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            v = json.load(f).get(f"bwd_{args.dtype}_{n}x{c}x{s}")
+        return float(v) if v is not None else None
     except Exception:
-        pass
-    return None
+        return None
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -947,12 +943,6 @@ def run_ours(args):
                         "bytes_per_launch": bytes_fwd},
                 "fwd_plus_bwd": {"achieved": (bytes_fwd + bytes_bwd) / ((fwd_avg + bwd_avg) * 1e-6) / 1e9,
                                  "frac": (bytes_fwd + bytes_bwd) / ((fwd_avg + bwd_avg) * 1e-6) / 1e9 / peak}}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get(f"bwd_{args.dtype}_{n}x{c}x{s}")
-        except Exception:
-            pass
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

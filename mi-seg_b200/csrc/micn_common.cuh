@@ -497,8 +497,14 @@ __device__ __forceinline__ void mbar_wait_park_t(uint32_t bar, uint32_t parity) 
     }
 }
 // consumers (on the critical path: short naps) / helper warps (producers, publish, gather: longer naps)
-__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) { mbar_wait_park_t<32>(bar, parity); }
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) { mbar_wait_park_t<200>(bar, parity); }
+#ifndef MICN_PARK_NS
+#define MICN_PARK_NS 32
+#endif
+#ifndef MICN_IDLE_NS
+#define MICN_IDLE_NS 200
+#endif
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) { mbar_wait_park_t<MICN_PARK_NS>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) { mbar_wait_park_t<MICN_IDLE_NS>(bar, parity); }
 
 // x / d for x < 2^31 with a precomputed multiplier (host: fastdiv_make)
 struct FastDiv {
