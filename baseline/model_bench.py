@@ -190,6 +190,72 @@ def train_step_bench(kind: str, variant: str, pkg, dev, world: int, rank: int, s
     return out
 
 
+def graphed_step_bench(kind: str, pkg, dev, steps: int, warmup: int, batch: int, dtype=torch.bfloat16) -> dict:
+    """The "ours" training step captured ONCE into a CUDA graph and replayed (single GPU): forward, loss, backward and
+    AdamW(capturable) in one graph, the modality fed through a static device tensor.  Possible because the drop-in reads
+    the style ids ON THE DEVICE (sync-free mode, selected automatically during capture); the reference's norm indexes its
+    ModuleList with `styles[i]` - one host sync per sample per norm call - and cannot be captured.  In this mode styles
+    absent from the batch receive zero gradients instead of None (set_sync_free_styles docstring)."""
+    net, fused = build_model(kind, "ours", pkg)
+    net = net.to(dev).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5, capturable=True)
+    g = torch.Generator(device="cpu").manual_seed(100)
+    R = 2
+    datas = [torch.randn(batch, 1, ROI, ROI, ROI, generator=g).to(dev) for _ in range(R)]
+    targets = [torch.randint(0, OUT_CHANNELS, (batch, 1, ROI, ROI, ROI), generator=g).to(dev) for _ in range(R)]
+    mods = [((torch.arange(batch) + r) % 2).to(dev) for r in range(R)]
+    s_data, s_target, s_mod = datas[0].clone(), targets[0].clone(), mods[0].clone()
+    s_loss = torch.zeros((), device=dev)
+    pkg.set_sync_free_styles(True)
+    try:
+        def body():
+            with torch.autocast("cuda", dtype=dtype):
+                loss = dice_ce_loss(net(s_data, s_mod), s_target)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=False)
+            s_loss.copy_(loss.detach())
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+
+        def step(i):
+            s_data.copy_(datas[i % R], non_blocking=True)
+            s_target.copy_(targets[i % R], non_blocking=True)
+            s_mod.copy_(mods[i % R], non_blocking=True)
+            graph.replay()
+
+        for i in range(max(warmup, 2)):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        first = None
+        e0.record()
+        for i in range(steps):
+            step(i)
+            if first is None:
+                first = s_loss.clone()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / steps
+        return {"ms_per_step": ms_step, "voxels_per_s": batch * ROI ** 3 / (ms_step * 1e-3), "loss_first": float(first),
+                "loss_last": float(s_loss), "blocks_fused": fused,
+                "note": "whole step (forward, loss, backward, AdamW capturable) replayed from ONE CUDA graph; style ids read on "
+                        "the device; absent styles get zero gradients in this mode"}
+    finally:
+        pkg.set_sync_free_styles(False)
+        del net, opt
+        torch.cuda.empty_cache()
+
+
 def model_step_leg(kind: str, pkg, dev, world: int, rank: int, steps: int, warmup: int, batch: int) -> dict:
     """Both variants back to back on the same GPU(s); voxels/s = B * 96^3 * world / step time."""
     res = {"what": f"{kind} training step (reference nets from its own networks/ package; bf16 autocast, AdamW, "
@@ -201,6 +267,15 @@ def model_step_leg(kind: str, pkg, dev, world: int, rank: int, steps: int, warmu
             res[variant] = train_step_bench(kind, variant, pkg, dev, world, rank, steps, warmup, batch)
         except Exception as e:  # noqa: BLE001 - a failing leg must not take the headline line down
             res[variant] = {"error": repr(e)[:400]}
+    if world == 1 and not os.environ.get("MICN_NO_GRAPHED_STEP"):
+        try:
+            res["ours_cuda_graph"] = graphed_step_bench(kind, pkg, dev, steps, warmup, batch)
+        except Exception as e:  # noqa: BLE001
+            res["ours_cuda_graph"] = {"error": repr(e)[:400]}
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
     if "ms_per_step" in res.get("reference", {}) and "ms_per_step" in res.get("ours", {}):
         res["speedup"] = res["reference"]["ms_per_step"] / res["ours"]["ms_per_step"]
         res["voxels_per_s"] = res["ours"]["voxels_per_s"]

@@ -60,10 +60,10 @@ def parse_args():
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
     ap.add_argument("--no-model-calls", action="store_true", help="skip the C-Swin-UNETR norm-call-list leg")
     ap.add_argument("--regions", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
-    ap.add_argument("--launch", default="graph", choices=["stream", "graph"],
-                    help="graph (default): the micn_fwd + micn_bwd pair of every buffer set is captured once into a CUDA graph and "
-                         "replayed, as a captured training step would be (the calls keep no per-launch state on the host); "
-                         "stream: the two C-ABI calls are issued from Python every step")
+    ap.add_argument("--launch", default="stream", choices=["stream", "graph"],
+                    help="stream (default): the two C-ABI calls are issued from Python every step; graph: the micn_fwd + micn_bwd "
+                         "pair of every buffer set is captured once into a CUDA graph and replayed (the calls keep no per-launch "
+                         "state on the host)")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
                     help="N > 1: how d(gamma)/d(beta) are all-reduced every step.  fused (default): inside the backward kernel, "
                          "records stored straight into every peer's memory over NVLink (micn_bwd_allreduce); nccl: an "
@@ -631,6 +631,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n, c, s, m = workload(args)
     S = 2
+    # One stream carries every kernel of this process, so the persistent flat kernels can be launched as programmatic
+    # dependents (griddepcontrol: their launch latency and barrier set-up overlap the tail of the kernel before them) instead
+    # of cooperatively; the library's default stays the cooperative launch, which is also safe when two streams launch
+    # flat kernels at the same time (include/micn.h, "flat_pdl").
+    pdl = not os.environ.get("MICN_BENCH_NO_PDL")
+    if pdl:
+        pkg._lib.set_option("flat_pdl", 1)
+        pkg._lib.set_option("flat_coop", 0)
     for kv in os.environ.get("MICN_BENCH_OPTS", "").split(","):  # (debug knob: library options, name=value)
         if "=" in kv:
             pkg._lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
@@ -971,7 +979,8 @@ def run_ours(args):
                                  "(double-buffered buckets, waited before reuse and before the clock stops; "
                                  "147 of 148 SMs run the norm kernels, one is left to NCCL)" if overlap else
                                  "all_reduce(dgamma,dbeta) per step over NCCL" if world > 1 else "none"),
-                  "launch": args.launch,
+                  "launch": args.launch + (", flat kernels launched as programmatic dependents (flat_pdl=1, flat_coop=0: one stream "
+                                           "carries every kernel of this process)" if pdl else ", cooperative launches"),
                   "timing": f"{prewarm} untimed pre-warm steps, then {len(region_ms)} regions of {args.steps} steps "
                             "(CUDA events, barrier + synchronize on both sides, max over ranks per region); "
                             "ms_per_step = median region / steps"},

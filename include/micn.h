@@ -71,7 +71,15 @@ const char* micn_error_string(int code);
 
 /* Tuning / experiment knobs ("force_path" 0 small / 1 cluster / 2 flat / 4 resident, "flat_slots", "flat_lag",
  * "flat_piece_vecs", "cluster_size", ...) and read-backs ("last_path", "launches").  Returns 0 or
- * MICN_ERR_BAD_ARG for an unknown key.  value < 0 restores the automatic choice. */
+ * MICN_ERR_BAD_ARG for an unknown key.  value < 0 restores the automatic choice.
+ *
+ * Launch modes.  Every kernel starts with griddepcontrol.wait; the small, resident and fused channels-last kernels are
+ * launched as programmatic dependents (their launch latency overlaps the tail of the kernel before them in the stream;
+ * "pdl" = 0 switches that off).  The persistent flat kernels - whose CTAs wait for each other's records across the grid -
+ * are launched COOPERATIVELY by default, which also keeps two such kernels launched from different streams from
+ * dead-locking each other on half a GPU each.  A process that issues all its kernels on ONE stream (the usual training
+ * loop) can set "flat_pdl" = 1 and "flat_coop" = 0: the flat kernels then queue as programmatic dependents too, which
+ * saves about 2 us per launch (1 x 48 x 96^3 bf16 forward + backward: 80.1 -> 76.6 us). */
 int micn_set_option(const char* key, long long value);
 long long micn_get_option(const char* key);
 

@@ -73,6 +73,8 @@ struct Options {
     std::atomic<long long> xchg_dbg{-1};      // bring-up bits of the fused peer exchange: 1 no start fold, 2 no header atomic, 4 no peer stores
     std::atomic<long long> res_copies{-1};    // bulk copies per stream of a CTA's share (default 3)
     std::atomic<long long> res_trace{0};      // bring-up: device pointer of a [grid][8] int64 trace buffer
+    std::atomic<long long> pdl{-1};           // 0: no programmatic dependent launch for the small / resident / channels-last kernels
+    std::atomic<long long> flat_pdl{-1};      // 1: launch the flat kernels with programmatic stream serialization (PDL)
     std::atomic<long long> flat_refuse{-1};   // 1: behave as if the cooperative launch had been refused (tests the fallback chain)
     std::atomic<long long> flat_trace_which{0};  // 0 both, 1 forward only, 2 backward only
     std::atomic<long long> flat_trace{0};     // bring-up: device pointer of a [grid][64][16] int64 trace buffer
@@ -103,7 +105,7 @@ const OptName kOptNames[] = {
     {"launches", &g_opt.launches}, {"host_groups", &g_opt.host_groups}, {"host_copy_2d", &g_opt.host_copy_2d}, {"host_taper", &g_opt.host_taper}, {"host_trace", &g_opt.host_trace},        {"sm_bw_mbps", &g_opt.sm_bw_mbps}, {"hbm_bw_mbps", &g_opt.hbm_bw_mbps},
     {"flat_slots", &g_opt.flat_slots},     {"flat_lag", &g_opt.flat_lag},     {"flat_piece_vecs", &g_opt.flat_piece_vecs},
     {"flat_min_bytes", &g_opt.flat_min_bytes}, {"flat_grid", &g_opt.flat_grid}, {"flat_ovh_vecs", &g_opt.flat_ovh_vecs},
-    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"res_cs", &g_opt.res_cs}, {"res_min_bytes", &g_opt.res_min_bytes}, {"res_off", &g_opt.res_off}, {"xchg_dbg", &g_opt.xchg_dbg}, {"res_copies", &g_opt.res_copies}, {"res_trace", &g_opt.res_trace}, {"flat_trace", &g_opt.flat_trace},
+    {"flat_coop", &g_opt.flat_coop},       {"flat_refuse", &g_opt.flat_refuse}, {"flat_pdl", &g_opt.flat_pdl}, {"pdl", &g_opt.pdl}, {"res_cs", &g_opt.res_cs}, {"res_min_bytes", &g_opt.res_min_bytes}, {"res_off", &g_opt.res_off}, {"xchg_dbg", &g_opt.xchg_dbg}, {"res_copies", &g_opt.res_copies}, {"res_trace", &g_opt.res_trace}, {"flat_trace", &g_opt.flat_trace},
     {"flat_trace_which", &g_opt.flat_trace_which}, {"flat_slots_b", &g_opt.flat_slots_b}, {"flat_l2_mb", &g_opt.flat_l2_mb},
     {"flat_shape_fwd", &g_opt.flat_shape_fwd}, {"flat_shape_bwd", &g_opt.flat_shape_bwd}, {"flat_poll_delay_ns", &g_opt.flat_poll_delay_ns}, {"flat_poll_delay_tail_ns", &g_opt.flat_poll_delay_tail_ns}, {"flat_poll_backoff_ns", &g_opt.flat_poll_backoff_ns},
 };
@@ -191,6 +193,24 @@ int cluster_occupancy(K kernel, KernelState* ks, int cs, int smem) {
     }
     ks->occ[ci] = n;
     return n;
+}
+
+// Launch with programmatic stream serialization (PDL): the kernels start with griddepcontrol.wait, so their launch latency
+// (and, for the resident kernels, their barrier set-up) overlaps the tail of whatever runs before them in the stream.
+// Safe for every kernel family except the flat one, whose CTAs wait on each other across the grid (see launch_flat).
+template <typename K, typename... Args>
+int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_opt.pdl.load() == 0 ? 0 : 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 // ------------------------------------------------------------------------------------------ planner
@@ -458,11 +478,22 @@ int launch_flat(K kernel, const P& p, const FlatPlan<TR>& fp, cudaStream_t st) {
     cfg.blockDim = dim3(TR::kThreads);
     cfg.dynamicSmemBytes = fp.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on each other's records
-    attr[0].val.cooperative = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_opt.flat_coop.load() != 0) {
+        attr[na].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on each other's records
+        attr[na].val.cooperative = 1;
+        ++na;
+    }
+    if (g_opt.flat_pdl.load() == 1) {
+        // programmatic dependent launch: this kernel's launch latency and barrier set-up overlap the tail of the kernel
+        // before it in the stream (it blocks in griddepcontrol.wait before its first global-memory access)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_opt.flat_coop.load() == 0 ? 0 : 1;
+    cfg.numAttrs = na;
     typename TR::Geom g = fp.g;
     return (int)cudaLaunchKernelEx(&cfg, kernel, p, g);
 }
@@ -615,13 +646,15 @@ int res_run(K kernel, int NS, const P& p, long long slabs, long long slab_bytes,
     cfg.blockDim = dim3(res::kThreads);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pl.g.CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see launch_pdl)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_opt.pdl.load() == 0 ? 1 : 2;
     g_opt.last_path.store(4);  // (3 is the channels-last path)
     g_opt.last_cs.store(pl.g.CS);
     g_opt.last_slots.store(pl.g.nch_max);
@@ -678,18 +711,18 @@ int fwd_typed(const FwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
         const unsigned grid = (unsigned)((slabs + 7) / 8);
         pl.grid_clusters = (int)grid;
         record_plan(pl);
-        micn_fwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+        launch_pdl(micn_fwd_small_kernel<T, EPI, 32>, dim3(grid), dim3(256), 0, st, p);
     } else if (pl.tps == 256) {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
         if (reg)
-            micn_fwd_small_kernel<T, EPI, 256, true><<<(unsigned)slabs, 256, 0, st>>>(p);
+            launch_pdl(micn_fwd_small_kernel<T, EPI, 256, true>, dim3((unsigned)slabs), dim3(256), 0, st, p);
         else
-            micn_fwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
+            launch_pdl(micn_fwd_small_kernel<T, EPI, 256>, dim3((unsigned)slabs), dim3(256), 0, st, p);
     } else {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
-        micn_fwd_small_kernel<T, EPI, 1024><<<(unsigned)slabs, 1024, 0, st>>>(p);
+        launch_pdl(micn_fwd_small_kernel<T, EPI, 1024>, dim3((unsigned)slabs), dim3(1024), 0, st, p);
     }
     return (int)cudaGetLastError();
 }
@@ -742,18 +775,18 @@ int bwd_typed(const BwdParams& p, bool can_cluster, const FlatWs* ws_flat, const
         const unsigned grid = (unsigned)((slabs + 7) / 8);
         pl.grid_clusters = (int)grid;
         record_plan(pl);
-        micn_bwd_small_kernel<T, EPI, 32><<<grid, 256, 0, st>>>(p);
+        launch_pdl(micn_bwd_small_kernel<T, EPI, 32>, dim3(grid), dim3(256), 0, st, p);
     } else if (pl.tps == 256) {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
         if (reg)
-            micn_bwd_small_kernel<T, EPI, 256, true><<<(unsigned)slabs, 256, 0, st>>>(p);
+            launch_pdl(micn_bwd_small_kernel<T, EPI, 256, true>, dim3((unsigned)slabs), dim3(256), 0, st, p);
         else
-            micn_bwd_small_kernel<T, EPI, 256><<<(unsigned)slabs, 256, 0, st>>>(p);
+            launch_pdl(micn_bwd_small_kernel<T, EPI, 256>, dim3((unsigned)slabs), dim3(256), 0, st, p);
     } else {
         pl.grid_clusters = (int)slabs;
         record_plan(pl);
-        micn_bwd_small_kernel<T, EPI, 1024><<<(unsigned)slabs, 1024, 0, st>>>(p);
+        launch_pdl(micn_bwd_small_kernel<T, EPI, 1024>, dim3((unsigned)slabs), dim3(1024), 0, st, p);
     }
     return (int)cudaGetLastError();
 }
@@ -823,10 +856,12 @@ bool cl_wide_ok(const ClParams& p) {
     return g_opt.cl_wide.load() != 0 && p.C % ClWide<T>::CPL == 0 && (bits & 15u) == 0;
 }
 
+// (the fused one-launch kernels are launched as programmatic dependents; the two-kernel route is not: measured on
+// [1,384,24^3] bf16 it made the fwd+bwd pair slower, 36.0 -> 40.8 us)
 template <typename T>
 int cl_fwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
     if (fused) {
-        micn_cl_fwd_fused_kernel<T><<<grid, kClFusedThreads, 0, st>>>(p);
+        launch_pdl(micn_cl_fwd_fused_kernel<T>, dim3(grid), dim3(kClFusedThreads), 0, st, p);
         return (int)cudaGetLastError();
     }
     if (cl_wide_ok<T>(p)) {
@@ -841,7 +876,7 @@ int cl_fwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
 template <typename T>
 int cl_bwd_typed(const ClParams& p, dim3 grid, bool fused, cudaStream_t st) {
     if (fused) {
-        micn_cl_bwd_fused_kernel<T><<<grid, kClFusedThreads, 0, st>>>(p);
+        launch_pdl(micn_cl_bwd_fused_kernel<T>, dim3(grid), dim3(kClFusedThreads), 0, st, p);
     } else {
         micn_cl_bwd_stats_kernel<T><<<grid, kClThreads, 0, st>>>(p);
         micn_cl_bwd_apply_kernel<T><<<grid, kClThreads, 0, st>>>(p);

@@ -160,6 +160,8 @@ __device__ __forceinline__ float4 cl_block_sum(float4 v, float4* sm, int warp, i
 // ---------------------------------------------------------------- forward
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_fwd_stats_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     __shared__ float4 sm[kClThreads];
     const ClTile t = cl_tile(p);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // (s0, q0, s1, q1) about the shift
@@ -200,6 +202,8 @@ __device__ __forceinline__ float2 cl_fold_stats(const float4* part, int MS, size
 
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_fwd_apply_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     __shared__ float4 coef[32];  // (a0, b0, a1, b1) per lane
     const ClTile t = cl_tile(p);
     if (t.warp == 0) {
@@ -279,6 +283,8 @@ __device__ __forceinline__ void cl_param_grads(const ClParams& p, const ClTile& 
 // ---------------------------------------------------------------- backward
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_stats_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     __shared__ float4 sm[kClThreads];
     const ClTile t = cl_tile(p);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // (S1_0, S2_0, S1_1, S2_1)
@@ -301,6 +307,8 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_stats_kernel(const ClP
 
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_bwd_apply_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     __shared__ float4 coefA[32];  // (A, B1, B0', mean) per channel 0
     __shared__ float4 coefB[32];  //                  ... channel 1
     const ClTile t = cl_tile(p);
@@ -436,6 +444,8 @@ __device__ __forceinline__ float2 cl_wide_block_sum(float* u, float* v, float2 (
 
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_fwd_stats_wide_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     using W = ClWide<T>;
     using V = VecT<T>;
     __shared__ float2 sm[kClWarps][kClTile];
@@ -474,6 +484,8 @@ __global__ void __launch_bounds__(kClThreads) micn_cl_fwd_stats_wide_kernel(cons
 
 template <typename T>
 __global__ void __launch_bounds__(kClThreads) micn_cl_fwd_apply_wide_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     using W = ClWide<T>;
     using V = VecT<T>;
     __shared__ float4 coef[32];  // (a0, b0, a1, b1) per channel pair
@@ -535,6 +547,8 @@ constexpr int kClFusedMaxRows = 1024;
 
 template <typename T>
 __global__ void __launch_bounds__(kClFusedThreads) micn_cl_fwd_fused_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     __shared__ float4 sm[kClFusedThreads];
     __shared__ float4 coef[32];
     const ClTile t = cl_tile(p);  // MS == 1: the CTA's row range is the whole column
@@ -587,6 +601,8 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_fwd_fused_kernel(cons
 
 template <typename T>
 __global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     __shared__ float4 sm[kClFusedThreads];
     __shared__ float4 coefA[32];
     __shared__ float4 coefB[32];
@@ -639,6 +655,8 @@ __global__ void __launch_bounds__(kClFusedThreads) micn_cl_bwd_fused_kernel(cons
 
 // d(gamma)/d(beta)[s][c] = sum over the samples of style s, in sample order (deterministic)
 __global__ void micn_cl_param_grads_kernel(const ClParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.num_styles * p.C) return;
     const int s = (int)(idx / p.C);

@@ -295,6 +295,8 @@ __device__ __forceinline__ uint4 fwd_apply(const uint4& xv, const uint4& rv, flo
 // ---------------------------------------------------------------------------------------------
 template <typename T, int EPI>
 __global__ void __launch_bounds__(kClusterThreads, 1) micn_fwd_cluster_kernel(const FwdParams p, const int S) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     extern __shared__ __align__(128) unsigned char smem[];
     const long long num_slabs = p.N * p.C;
     const ClusterCtx c = cluster_setup<1>(smem, S, p.M * (long long)sizeof(T) / 16);
@@ -580,6 +582,8 @@ __device__ __forceinline__ uint4 bwd_apply(const BwdSlab& s, const uint4& xv, co
 
 template <typename T, int EPI>
 __global__ void __launch_bounds__(kClusterThreads, 1) micn_bwd_cluster_kernel(const BwdParams p, const int S) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     constexpr int NS = (EPI == MICN_EPI_ADD_LRELU) ? 3 : 2;  // x, dy [, act_out]
     extern __shared__ __align__(128) unsigned char smem[];
     const long long num_slabs = p.N * p.C;

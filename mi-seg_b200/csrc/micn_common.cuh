@@ -577,6 +577,14 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; `pdl_wait` blocks until the predecessor grid has COMPLETED and its
+// memory is visible (a no-op for a normal launch), `pdl_launch_dependents` lets the successor's CTAs be placed as soon as
+// SMs free up.  The kernels here put only their shared-memory set-up before the wait: what overlaps is the launch latency
+// and the barrier initialisation, never a memory access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // named barrier over a subset of the CTA's warps (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -201,6 +201,9 @@ __device__ __forceinline__ FlatCtx flat_setup(unsigned char* smem, const FlatGeo
         if (t <= kFlatMaxSlots + kFlatNB) fence_mbar_init();
     }
     __syncthreads();
+    // everything above touched shared memory only; from here on global memory (workspace epoch, records, tensors)
+    pdl_wait();
+    pdl_launch_dependents();
     return c;
 }
 

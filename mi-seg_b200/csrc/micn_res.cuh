@@ -103,6 +103,10 @@ __device__ __forceinline__ Ctx setup(unsigned char* smem, const Geom& g, const c
     // peers may only touch this CTA's barrier / record slots once they exist: split cluster barrier, the wait half sits
     // right before the exchange, ~2 us of loads later
     if (g.CS > 1) cluster_arrive();
+    // programmatic dependent launch: the launch latency and the set-up above overlap the tail of the kernel before this
+    // one in the stream; global memory is touched only from here on
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         const uint64_t pol = l2_policy_evict_first();
         const char* const src[3] = {s0, s1, s2};

@@ -102,6 +102,8 @@ __device__ __forceinline__ void group_reduce_sum2(float& a, float& b, float* scr
 // ---------------------------------------------------------------------------------------------
 template <typename T, int EPI, int TPS, bool REG = false>
 __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_fwd_small_kernel(const FwdParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     using V = VecT<T>;
     constexpr int VN = V::N;
     __shared__ float scratch[32 * 4];
@@ -271,6 +273,8 @@ __device__ __forceinline__ void small_fold_channel(const BwdParams& p, long long
 
 template <typename T, int EPI, int TPS, bool REG = false>
 __global__ void __launch_bounds__(SmallCfg<TPS>::BLOCK) micn_bwd_small_kernel(const BwdParams p) {
+    pdl_wait();  // (programmatic dependent launch: nothing global is touched before the predecessor is through)
+    pdl_launch_dependents();
     using V = VecT<T>;
     constexpr int VN = V::N;
     __shared__ float scratch[32 * 4];

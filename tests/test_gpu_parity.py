@@ -25,6 +25,9 @@ def pkg():
         pytest.skip("no CUDA device")
     import mi_seg_b200
     mi_seg_b200._lib.lib()  # fail loudly if the extension is missing
+    if os.environ.get("MICN_TEST_FLAT_PDL"):  # the whole suite with the flat kernels launched as programmatic dependents
+        mi_seg_b200._lib.set_option("flat_pdl", 1)
+        mi_seg_b200._lib.set_option("flat_coop", 0)
     return mi_seg_b200
 
 
