@@ -18,8 +18,8 @@ Prints ONE JSON line (rank 0):
             call sequence (kind "port") only when that copy is absent
 `--impl reference` times that CPU module alone on the same config.
 
-Timing of `value`: the clocks sampler starts, then an untimed pre-warm of >= 50 steps (more with --warmup) brings the GPU
-to its load clocks, then `--regions` (default 5) timed regions of EXACTLY --steps steps each, every one bracketed by a
+Timing of `value`: the clocks sampler starts, then an untimed pre-warm of 200 steps brings the GPU to its load
+clocks, then `--regions` (default 5) timed regions of EXACTLY --steps steps each, every one bracketed by a
 barrier + synchronize and CUDA events, max over ranks per region; the MEDIAN region is reported (all of them are listed
 under "regions_ms").  Extra keys: model-level steps of the reference's own nets ("model_step": C-Swin-UNETR B=1/GPU,
 DDP over NCCL for N > 1; C-UNETR B=4 and the C-UNet CPU config at N=1) and the sharded sliding-window volume
@@ -437,7 +437,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -627,6 +627,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    if rank == 0:  # started first: nvidia-smi needs up to seconds for its first answer on an 8-GPU box
+        sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, c, s, m = workload(args)
@@ -775,13 +778,14 @@ def run_ours(args):
         def launch_pair(b):  # noqa: F811 - the collective (N > 1) is still issued from the host after every replay
             graphs[b].replay()
 
-    sampler = ClockSampler(local)
-    if rank == 0:  # BEFORE the pre-warm: nvidia-smi takes ~0.2 s to produce its first sample
-        sampler.start()
-        time.sleep(0.25)
     # untimed pre-warm, independent of --warmup: the GPU drops to its idle clocks within a fraction of a second of
     # inactivity (the sampler start above is one), and a 20-step region lasts 1.7 ms - shorter than the clock ramp
-    prewarm = max(50, args.warmup, 10 * args.steps)
+    # (a fixed count: with the fused exchange every rank must make the same sequence of calls.  Deliberately short - 16 ms:
+    # half a second of this load before the clock starts makes the step 4 % slower (84.5 instead of 80.8 us at 2 GPUs), the
+    # same burst-vs-sustained gap MEASURED_PEAKS.json records for its own figures, and the roofline's denominator is the
+    # burst copy rate)
+    prewarm = max(200, args.warmup, 10 * args.steps)
+    t_load0 = time.perf_counter()
     for i in range(prewarm):
         step(i)
     drain()
@@ -849,8 +853,17 @@ def run_ours(args):
 
     bwd_avg = region_us(lambda i: bwd(i % R, grads2[0]))
     fwd_avg = region_us(lambda i: fwd(i % R))
+    # clocks: the timed regions last 8 ms in all, nvidia-smi answers every 50 ms at best - so the same steps run on for
+    # ~0.35 s after the measurements and the sampler's answers between the start of the pre-warm and the end of this
+    # observation loop are reported (SM clock under exactly this load, throttle reasons)
+    for i in range(4000):
+        step(i)
+    drain()
+    torch.cuda.synchronize()
     t_region_end = time.perf_counter()
-    clocks = sampler.stop(t_wall0, t_region_end) if rank == 0 else None
+    clocks = sampler.stop(t_load0, t_region_end) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "pre-warm + timed regions + roofline regions + 4000 more steps of the same load (~0.4 s)"
 
     ms_step = ms_total / args.steps
     value = world * (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9

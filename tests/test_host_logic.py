@@ -41,6 +41,49 @@ def test_library_loads_and_exports_every_header_symbol():
     assert lib.micn_set_option(b"no_such_option", 1) != 0
 
 
+def test_round2_entry_points_validate_their_arguments_without_a_gpu():
+    """Host-side checks of the round-2 entry points (no compute call is made): sizes, fold modes, refusals."""
+    lib = pkg._lib.lib()
+    assert lib.micn_peer_buffer_bytes(48, 2, 8) == 64 + 4 * 8 * 2 * 48 * 16
+    assert lib.micn_peer_buffer_bytes(0, 2, 8) == 0 and lib.micn_peer_buffer_bytes(48, 2, 0) == 0
+    assert (pkg._lib.FOLD_NONE, pkg._lib.FOLD_THIS, pkg._lib.FOLD_PREVIOUS) == (0, 1, 2)
+    # no device here: the supported-query answers "no" instead of failing
+    assert lib.micn_dual_supported(1, 48, 96 ** 3, 1, 0) in (0, 1)
+    assert lib.micn_dual_supported(0, 48, 96 ** 3, 1, 0) == 0
+    # argument errors are reported before anything touches a device
+    assert lib.micn_allreduce_fold(None, 0, 2, 48, 2, None, None, None) == -1
+    assert lib.micn_fwd_dual(None, None, None, None, None, None, None, 2, None, None, None, None, None, 1, 4, 64, 9, 0.01, 1e-5,
+                             None, 0, None) == -2
+    for knob in ("pdl", "flat_pdl", "res_cs", "res_copies", "res_off", "res_min_bytes", "flat_refuse", "xchg_dbg"):
+        before = lib.micn_get_option(knob.encode())
+        assert lib.micn_set_option(knob.encode(), 1) == 0, knob
+        assert lib.micn_get_option(knob.encode()) == 1
+        assert lib.micn_set_option(knob.encode(), before) == 0
+
+
+def test_cpp_binding_loads_and_matches_the_library():
+    """mi-seg_b200/_micn_torch.so (csrc/micn_torch.cpp: C++ autograd functions over the same C ABI) is built by
+    __graft_entry__.build(); it must load here, report the library's version and refuse CPU tensors like the ctypes path."""
+    import torch
+
+    path = os.path.join(ROOT, "mi-seg_b200", "_micn_torch.so")
+    assert os.path.exists(path), "run `python -c 'import __graft_entry__ as g; g.build()'`"
+    f = importlib.import_module("mi-seg_b200.functional")
+    ext = f._ext()
+    assert ext is not None and pkg.binding_in_use() == "cpp"
+    assert ext.micn_version() == pkg._lib.lib().micn_version()
+    mod = pkg.FastConditionalInstanceNorm3d(2, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mod(torch.randn(2, 4, 4, 4, 4), [0, 1])
+    pkg.set_binding("ctypes")
+    try:
+        assert pkg.binding_in_use() == "ctypes"
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod(torch.randn(2, 4, 4, 4, 4), [0, 1])
+    finally:
+        pkg.set_binding("auto")
+
+
 def test_workspace_sizes_and_knobs_without_a_gpu():
     """Pure host arithmetic of the C ABI: workspace sizes grow with the problem, carry the fixed prefix (header +
     per-channel arrival counters) that lets one zero-filled workspace serve calls of any shape, and every knob the
