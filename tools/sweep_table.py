@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """Print a sweep result file as a table.
 usage: python tools/sweep_table.py gpurun_out/x_sweep.jsonl            (tools/flat_sweep.sh knob sweeps)
-       python tools/sweep_table.py --microbench gpurun_out/sweep.jsonl (bench.py --sweep --sweep-out: profiles/r01_microbench_sweep.txt)"""
+       python tools/sweep_table.py --microbench gpurun_out/sweep.jsonl (bench.py --sweep --sweep-out: profiles/r0N_microbench_sweep.txt)"""
 import json
 import sys
 
 if sys.argv[1] == "--microbench":
     print("# BASELINE.json configs[3]: instance_cond microbench sweep on one B200 (bench.py --sweep), device-resident inputs,")
     print("# CUDA events over back-to-back launches, rotating buffer sets; frac = (2+3)*E*s / (fwd+bwd) / 6542.1 GB/s (measured copy peak).")
-    print("# path: 0 = small (warp/CTA per slab), 1 = cluster, 2 = flat")
+    print("# path (of the backward, the last call): 0 = small (warp/CTA per slab), 1 = cluster, 2 = flat, 4 = resident (cluster per slab, shared-memory resident)")
     print(f"{'dtype':5s} {'S':>4s} {'N':>2s} {'C':>4s} {'path':>4s} {'fwd_us':>10s} {'bwd_us':>10s} {'fwd GB/s':>9s} {'bwd GB/s':>9s} {'frac':>6s}")
     for l in open(sys.argv[2]):
         if not l.startswith("{"):
