@@ -728,7 +728,7 @@ def run_ours(args):
         (bwd_fused if px is not None else bwd)((b + 1) % R, grads2[b])
 
     def drain():
-        if px is not None:  # the last step's exchange (every earlier one was folded by the step after it)
+        if px is not None and not os.environ.get("MICN_BENCH_SKIP_FOLD"):  # the last step's exchange (every earlier one was folded by the step after it)
             rc = lib.micn_allreduce_fold(px.ptrs, rank, world, c, S, grads2[0][0].data_ptr(), grads2[0][1].data_ptr(), stream)
             if rc:
                 raise RuntimeError(f"micn_allreduce_fold rc={rc}")
@@ -813,6 +813,11 @@ def run_ours(args):
             launches_region = (pkg._lib.get_option("launches") - launches0) if graphs is None else 2 * args.steps
     t_wall1 = time.perf_counter()
     launches = launches_region
+    if px is not None and os.environ.get("MICN_BENCH_XCHG_DBG"):  # (bring-up: wait statistics of the folds, see micn_flat.cuh)
+        torch.cuda.synchronize()
+        w = px.local[16:40].view(torch.int32).tolist()
+        print(f"[rank {rank}] fold waits: max {w[0]} ns, count {w[1]}, total {w[2]} ns, own-rank records {w[3]}, peer records {w[4]}",
+              file=sys.stderr, flush=True)
     per_rank_us = None
     if world > 1:  # max over ranks, per region (the spread between the GPUs of the box is reported beside it)
         mine = torch.tensor([statistics.median(region_ms) / args.steps * 1e3], device=dev, dtype=torch.float64)

@@ -129,13 +129,13 @@ int micn_bwd(const void* dy, const void* x, const void* act_out,
  * one collective of the path; tune.py:103-109 does it with DDP's NCCL all-reduce).  One process per GPU of an NVLink box;
  * `peer_bufs` is a HOST array of `world` DEVICE pointers: entry r is rank r's exchange buffer as mapped into THIS process
  * (CUDA IPC / symmetric memory; entry `rank` is the local one), each micn_peer_buffer_bytes() large, 16-byte aligned and
- * zero-filled once.  As soon as the sums of a channel are final, the kernel stores them as self-validating 16-byte records
- * straight into every peer's buffer (st.relaxed.sys over NVLink); at its end it folds the `world` records of every channel
- * straight into every peer's buffer (st.relaxed.sys over NVLink); the `world` records of every channel are then folded from
- * the rank's OWN buffer in rank order into dgamma / dbeta = the SUM over all ranks (bit-identical on every rank):
+ * zero-filled once.  The kernel keeps the final sums of every channel as self-validating 16-byte records in its own buffer
+ * and, once its gather warps are through their pieces, stores them straight into every peer's buffer (st.relaxed.sys over
+ * NVLink, hidden behind the last normalise tasks); the `world` records of every channel are folded from the rank's OWN
+ * buffer in rank order into dgamma / dbeta = the SUM over all ranks (bit-identical on every rank):
  *   MICN_FOLD_THIS      at the end of this kernel (synchronous all-reduce: exposes one NVLink latency + the skew between
  *                       the GPUs, a few microseconds, instead of a ~17 us NCCL launch);
- *   MICN_FOLD_PREVIOUS  at the START of this kernel, the PREVIOUS call's exchange (its records arrived a whole kernel ago:
+ *   MICN_FOLD_PREVIOUS  at the end of this kernel too, but the PREVIOUS call's exchange (its records arrived a whole kernel ago:
  *                       nothing to wait for) - dgamma / dbeta then lag one call behind, the way an asynchronous bucketed
  *                       all-reduce completes behind the backward pass; micn_allreduce_fold() delivers the last call's;
  *   MICN_FOLD_NONE      only store the records (fold later with micn_allreduce_fold()).

@@ -311,8 +311,10 @@ __device__ __forceinline__ bool ll_try_sys(const uint4* p, unsigned tag, float& 
 // Exchange buffer of one rank: 64-byte header (64-bit word {launch count : CTAs arrived}, as the workspace's), then
 // [4 slots][world source ranks][S*C] records, slot = launch count mod 4.  The tag of a launch is its count on this buffer:
 // every rank makes the same sequence of calls, so all ranks derive the same tag without talking to each other.  Four
-// slots: a peer can run at most two launches ahead of the slowest CTA of this GPU (its launch k+1 needs this GPU's records
-// of launch k), so the slot a fold reads is never the one a peer is writing.
+// slots: launch k of this GPU folds slot k (or k-1, lagged mode) at its end; a peer's launch k+1 cannot finish before this
+// GPU has emitted all of launch k (or k-1) - i.e. before launch k is running - and its launch k+2 not before launch k+1
+// runs here, so the earliest launch of a peer that can overlap this GPU's launch k is k+2, writing slot k+2: never the
+// slot (k or k-1) being folded, and k+3 (= k-1 mod 4) cannot have started.
 constexpr unsigned kXchgHeader = 64;
 constexpr unsigned kXchgSlots = 4;
 __device__ __forceinline__ unsigned xchg_epoch_tag(void* local_buf) {
@@ -328,26 +330,43 @@ __device__ __forceinline__ uint4* xchg_rec(void* buf, unsigned tag, unsigned src
 }
 // one final (style, channel) entry of this rank -> every rank's buffer (own included)
 __device__ __forceinline__ void xchg_emit(const BwdParams& p, unsigned xtag, unsigned idx, float dbeta, float dgamma) {
-    const unsigned SC = (unsigned)p.num_styles * (unsigned)p.C;
-    if ((p.xchg_mode >> 4) & 4) return;  // (bring-up: time the kernel without the peer stores)
-    for (int r = 0; r < p.xchg_world; ++r)
-        ll_store_sys(xchg_rec(p.xchg_peers[r], xtag, (unsigned)p.xchg_rank, (unsigned)p.xchg_world, SC, idx), dbeta, dgamma, xtag);
+    // (into this rank's OWN buffer; xchg_forward sends it on to the peers at the kernel's end)
+    const unsigned SC = (unsigned)p.num_styles * (unsigned)p.C, me = (unsigned)p.xchg_rank;
+    ll_store_sys(xchg_rec(p.xchg_peers[me], xtag, me, (unsigned)p.xchg_world, SC, idx), dbeta, dgamma, xtag);
 }
-// the same for the S entries of one channel at once, called by a whole warp: lane (s * world + r) stores entry s into
-// rank r's buffer, so all S * world peer stores leave in one instruction
+// the same for the S entries of one channel at once, called by a whole warp (one-sample case: the slab sums are final)
 __device__ __forceinline__ void xchg_emit_channel(const BwdParams& p, unsigned xtag, unsigned ch, int style, float dbeta,
                                                   float dgamma, int lane) {
-    const unsigned world = (unsigned)p.xchg_world, S = (unsigned)p.num_styles, C = (unsigned)p.C;
-    if ((p.xchg_mode >> 4) & 4) return;
-    for (unsigned q = lane; q < S * world; q += 32) {
-        const unsigned s = q / world, r = q - s * world;
+    const unsigned S = (unsigned)p.num_styles, C = (unsigned)p.C;
+    for (unsigned s = lane; s < S; s += 32) {
         const bool hit = (int)s == style;
-        uint4* dst = xchg_rec(p.xchg_peers[r], xtag, (unsigned)p.xchg_rank, world, S * C, s * C + ch);
-        if ((p.xchg_mode >> 4) & 8) {  // (bring-up: plain store instead of st.relaxed.sys)
-            *dst = make_uint4(__float_as_uint(hit ? dbeta : 0.f), xtag, __float_as_uint(hit ? dgamma : 0.f), xtag);
-            continue;
+        xchg_emit(p, xtag, s * C + ch, hit ? dbeta : 0.f, hit ? dgamma : 0.f);
+    }
+}
+// Forward this rank's records of launch `tag` from its OWN buffer to every peer's, one (entry, peer) pair per lane.  Called
+// by the gather warps once their pieces are done: a store into NVLink peer memory holds the issuing warp for microseconds,
+// which on the gather warps' critical path (mid-kernel, behind the record of a slab's first piece) cost the whole grid
+// 3 us per launch; here it hides behind the consumers' last L normalise tasks.
+__device__ __forceinline__ void xchg_forward(const BwdParams& p, unsigned tag, unsigned slot, unsigned nslots, int lane) {
+    const unsigned SC = (unsigned)p.num_styles * (unsigned)p.C, world = (unsigned)p.xchg_world, me = (unsigned)p.xchg_rank;
+    if ((p.xchg_mode >> 4) & 4) return;  // (bring-up: time the kernel without the peer stores)
+    void* mine = p.xchg_peers[me];
+    const unsigned total = SC * (world - 1u);
+    for (unsigned q = slot * 32u + (unsigned)lane; q < total; q += nslots * 32u) {
+        const unsigned idx = q / (world - 1u);
+        unsigned r = q - idx * (world - 1u);
+        r += r >= me ? 1u : 0u;
+        const uint4* src = xchg_rec(mine, tag, me, world, SC, idx);
+        float a, b;
+        if (!ll_try_sys(src, tag, a, b)) {  // (the channel's own gather warp, in some other CTA, may still be on its way)
+            const uint64_t t0 = globaltimer_ns();
+            uint32_t spins = 0;
+            do {
+                __nanosleep(100);
+                if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
+            } while (!ll_try_sys(src, tag, a, b));
         }
-        ll_store_sys(dst, hit ? dbeta : 0.f, hit ? dgamma : 0.f, xtag);
+        ll_store_sys(xchg_rec(p.xchg_peers[r], tag, me, world, SC, idx), a, b, tag);
     }
 }
 
@@ -368,6 +387,13 @@ __device__ __forceinline__ void xchg_fold(const BwdParams& p, unsigned tag, unsi
                     __nanosleep(100);
                     if (((++spins) & 0xffu) == 0 && globaltimer_ns() - t0 > MICN_WAIT_TIMEOUT_NS) __trap();
                 } while (!ll_try_sys(rec, tag, a, b));
+                if ((p.xchg_mode >> 4) & 64) {  // (bring-up: how long, how often and for which rank do folds wait?)
+                    unsigned* dbg = reinterpret_cast<unsigned*>(mine) + 4;
+                    atomicMax(dbg, (unsigned)(globaltimer_ns() - t0));
+                    atomicAdd(dbg + 1, 1u);
+                    atomicAdd(dbg + 2, (unsigned)(globaltimer_ns() - t0));
+                    atomicAdd(dbg + 3 + ((unsigned)lane == (unsigned)p.xchg_rank ? 0 : 1), 1u);
+                }
             }
         }
         float sa = 0.f, sb = 0.f;
@@ -862,14 +888,11 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
         // not by the publish warp, whose first record is on the critical path of every CTA of the slab
         const bool xchg = p.xchg_world > 1;
         if (xchg) {
-            if (warp == kFlatGatherWarp0 && lane == 0) c.tagw[1] = xchg_epoch_tag(p.xchg_peers[p.xchg_rank]);
+            if (warp == kFlatGatherWarp0 && lane == 0)
+                c.tagw[1] = ((p.xchg_mode >> 4) & 2) ? (tag | 0x80000000u) : xchg_epoch_tag(p.xchg_peers[p.xchg_rank]);
             bar_sync(2, kFlatGatherWarps * 32);
         }
         const unsigned xtag = xchg ? c.tagw[1] : 0u;
-        if (xchg && p.dgamma && (p.xchg_mode & 15) == 2 && (xtag & 0x7fffffffu) > 1u && !((p.xchg_mode >> 4) & 1))
-            // lagged mode: dgamma / dbeta receive the all-reduced gradients of the PREVIOUS call - its records arrived a
-            // whole kernel ago, nothing to wait for - while this call's records travel during this kernel
-            xchg_fold(p, xtag - 1u, cta * kFlatGatherWarps + (warp - kFlatGatherWarp0), G * kFlatGatherWarps, lane);
         for (unsigned j = warp - kFlatGatherWarp0; j < nj; j += kFlatGatherWarps) {
             const Ring e = entry_of(j);
             const PieceId pc = piece_of(g, j * G + cta);
@@ -968,8 +991,16 @@ __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm) micn_bwd_flat_ke
             }
             __syncwarp();
         }
+        if (xchg && p.dgamma)  // this launch's records: own buffer -> every peer's
+            xchg_forward(p, xtag, cta * kFlatGatherWarps + (warp - kFlatGatherWarp0), G * kFlatGatherWarps, lane);
         if (xchg && p.dgamma && (p.xchg_mode & 15) == 1)  // synchronous mode: this call's own exchange, folded at the kernel's end
             xchg_fold(p, xtag, cta * kFlatGatherWarps + (warp - kFlatGatherWarp0), G * kFlatGatherWarps, lane);
+        if (xchg && p.dgamma && (p.xchg_mode & 15) == 2 && (xtag & 0x7fffffffu) > 1u && !((p.xchg_mode >> 4) & 1))
+            // lagged mode: dgamma / dbeta receive the all-reduced gradients of the PREVIOUS call - its records arrived a
+            // whole kernel ago, nothing to wait for - while this call's records travel.  Done here, by gather warps that
+            // have nothing left to do while the consumers drain the last L pieces: at the kernel's START the same fold
+            // cost 2 us per step (measured at 2 GPUs: 80.7 against 78.6 us without it).
+            xchg_fold(p, xtag - 1u, cta * kFlatGatherWarps + (warp - kFlatGatherWarp0), G * kFlatGatherWarps, lane);
     } else {
         // ------------------------------------------------------------------ consumers: P1(s), P2(s - L) in order
         Ring ra{0u, 0u}, rb{0u, 0u};
