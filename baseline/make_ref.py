@@ -30,9 +30,15 @@ def main() -> int:
     shutil.copyfile(src_norm, os.path.join(dst, "conditional_instance_norm.py"))
     net_dst = os.path.join(ROOT, "baseline", "_ref", "networks")
     if os.path.isdir(net_dst):
+        for root, dirs, _files in os.walk(net_dst):
+            os.chmod(root, 0o755)
         shutil.rmtree(net_dst)
     shutil.copytree(os.path.join(REF, "networks"), net_dst,
                     ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "lightning_monai.py"))
+    for root, dirs, files in os.walk(os.path.join(ROOT, "baseline", "_ref")):  # (the checkout is read-only; the copies need not be)
+        for name in dirs + files:
+            os.chmod(os.path.join(root, name), 0o755 if name in dirs else 0o644)
+    os.chmod(os.path.join(dst, "conditional_instance_norm.py"), 0o644)
     print(f"make_ref: {dst}/conditional_instance_norm.py and {net_dst}/ written")
     return 0
 

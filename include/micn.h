@@ -162,7 +162,10 @@ int micn_bwd_allreduce(const void* dy, const void* x, const void* act_out,
 /* The same two calls with the activation slope read from DEVICE memory: `slope_dev` points at the single weight of
  * the nn.PReLU that follows the norm in C-UNet's ADN block ("NDA": norm -> dropout(0) -> PReLU,
  * networks/blocks/acti_norm.py:104-110, convolutions.py:173-179), so prelu(norm(x)) and its input gradient are one
- * kernel each and no host read of the parameter is needed.  epilogue must be MICN_EPI_LRELU or MICN_EPI_ADD_LRELU.
+ * kernel each and no host read of the parameter is needed.  epilogue must be MICN_EPI_LRELU or MICN_EPI_ADD_LRELU; with
+ * MICN_EPI_ADD_LRELU the backward recovers the activation mask from the sign of the OUTPUT, which is only valid for a
+ * slope > 0, and no slope gradient is produced (the Python module refuses that combination: MI-Seg has no
+ * prelu(norm(x) + r) - C-UNet adds its residual after the activation, convolutions.py:329).
  * The gradient of the slope itself is sum over pre <= 0 of dy * pre: for MICN_EPI_LRELU micn_bwd_prelu accumulates it in
  * the same pass and writes PARTIAL sums into `dslope_partial` (device fp32, at least max(N*C, 1024) entries,
  * ZERO-FILLED by the caller; one entry per CTA or per slab is written, the total is the gradient; may be NULL). */
