@@ -615,3 +615,100 @@ def test_fused_peer_exchange_two_ranks_emulated_on_one_gpu(pkg, option):
                                 ranks[0]["gf"][1].data_ptr(), 1, 4, 64, 256, 64, 0, 0, 0.01, ranks[0]["ws"].data_ptr(), wsb, ptrs, 0,
                                 world, 1, cur)
     assert rc == -7  # MICN_ERR_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------------ launch modes / bindings
+def test_flat_kernels_as_programmatic_dependents(pkg, option):
+    """The launch mode bench.py uses (flat_pdl = 1, flat_coop = 0: the persistent flat kernels queue as programmatic
+    dependents behind whatever runs before them): parity, and a chain of back-to-back launches on ONE workspace without any
+    synchronisation in between - every kernel must see the records and the epoch word of its predecessor completed
+    (griddepcontrol.wait sits before the first global-memory access)."""
+    import ctypes
+    option("flat_pdl", 1)
+    option("flat_coop", 0)
+    option("force_path", 2)
+    _case(pkg, (1, 3, 96, 96, 96), [1], 2, torch.bfloat16, seed=91)
+    _case(pkg, (2, 5, 48, 48, 48), [1, 0], 2, torch.float32, epilogue="add_lrelu", seed=92)
+    lib = pkg._lib.lib()
+    n, c, m, S = 2, 6, 48 ** 3, 2
+    gen = torch.Generator(device="cuda").manual_seed(93)
+    gam = 1 + 0.3 * torch.randn(S, c, device="cuda", generator=gen)
+    bet = 0.3 * torch.randn(S, c, device="cuda", generator=gen)
+    gp = (ctypes.c_void_p * S)(*[gam[k].data_ptr() for k in range(S)])
+    bp = (ctypes.c_void_p * S)(*[bet[k].data_ptr() for k in range(S)])
+    st = torch.tensor([1, 0], device="cuda")
+    xs = [(torch.randn(n, c, m, device="cuda", generator=gen) * (1 + k) + k).bfloat16() for k in range(4)]
+    dys = [torch.randn(n, c, m, device="cuda", generator=gen).bfloat16() for _ in range(4)]
+    ys = [torch.empty_like(xs[0]) for _ in range(4)]
+    dxs = [torch.empty_like(xs[0]) for _ in range(4)]
+    stats = [torch.empty(2, n * c, device="cuda") for _ in range(4)]
+    grads = [torch.empty(2, S, c, device="cuda") for _ in range(4)]
+    wsb = lib.micn_workspace_bytes(n, c, m, 1, S)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for rep in range(3):  # 24 kernels queued back to back
+        for k in range(4):
+            assert lib.micn_fwd(xs[k].data_ptr(), ys[k].data_ptr(), None, gp, bp, S, st.data_ptr(), stats[k][0].data_ptr(),
+                                stats[k][1].data_ptr(), n, c, m, c * m, m, 1, 1, 0.01, 1e-5, ws.data_ptr(), wsb, stream) == 0
+            assert lib.micn_bwd(dys[k].data_ptr(), xs[k].data_ptr(), None, gp, bp, S, st.data_ptr(), stats[k][0].data_ptr(),
+                                stats[k][1].data_ptr(), dxs[k].data_ptr(), None, grads[k][0].data_ptr(), grads[k][1].data_ptr(),
+                                n, c, m, c * m, m, 1, 1, 0.01, ws.data_ptr(), wsb, stream) == 0
+    torch.cuda.synchronize()
+    for k in range(4):
+        xn = xs[k].float().cpu().numpy().reshape(n, c, 48, 48, 48)
+        dyn = dys[k].float().cpu().numpy().reshape(n, c, 48, 48, 48)
+        yr, pre, m_, r_ = O.fwd_epilogue_f64(xn, [1, 0], gam.cpu().numpy(), bet.cpu().numpy())
+        dxr, _, dgr, dbr, _ = O.bwd_epilogue_f64(dyn, pre, xn, [1, 0], gam.cpu().numpy(), m_, r_)
+        assert rel_err(ys[k].float().cpu().numpy().reshape(xn.shape), yr) < 1e-2, k
+        assert rel_err(dxs[k].float().cpu().numpy().reshape(xn.shape), dxr) < 1e-2, k
+        assert rel_err(grads[k][1].cpu().numpy(), dbr) < 5e-3 and rel_err(grads[k][0].cpu().numpy(), dgr) < 5e-3, k
+
+
+def test_ctypes_binding_matches_the_cpp_binding(pkg):
+    """Two host bindings issue the same C-ABI calls: the C++ autograd extension (default when built) and
+    torch.autograd.Function + ctypes.  Same inputs -> bit-identical outputs and gradients, for the NC*, channels-last and
+    dual-norm entry points."""
+    if pkg.binding_in_use() != "cpp":
+        pytest.skip("the C++ binding is not built: the ctypes path is what every other test ran")
+    torch.manual_seed(17)
+
+    def run_all():
+        out = []
+        mod = pkg.FastConditionalInstanceNorm3d(2, 8).cuda()
+        mod2 = pkg.FastConditionalInstanceNorm3d(2, 8).cuda()
+        with torch.no_grad():
+            for mm_, sd in ((mod, 1), (mod2, 2)):
+                g = torch.Generator().manual_seed(sd)
+                for k in range(2):
+                    mm_.norms[k].weight.copy_(1 + 0.3 * torch.randn(8, generator=g))
+                    mm_.norms[k].bias.copy_(0.3 * torch.randn(8, generator=g))
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(2, 8, 12, 12, 12, generator=g).cuda().requires_grad_(True)
+        r = torch.randn(2, 8, 12, 12, 12, generator=g).cuda().requires_grad_(True)
+        dy = torch.randn(2, 8, 12, 12, 12, generator=g).cuda()
+        xcl = torch.randn(2, 12, 12, 12, 8, generator=g).cuda().permute(0, 4, 1, 2, 3).requires_grad_(True)
+        act = torch.nn.PReLU(init=0.25).cuda()
+        for fn in (lambda: mod(x, [1, 0]), lambda: mod.forward_fused(x, [1, 0], "lrelu"),
+                   lambda: mod.forward_fused(x, [1, 0], "add_lrelu", residual=r),
+                   lambda: mod.forward_fused(x, [1, 0], "lrelu", slope=act.weight), lambda: mod(xcl, [0, 1]),
+                   lambda: pkg.norms.forward_fused_dual(mod, x, mod2, r, [1, 1])):
+            for t in (x, r, xcl, act.weight, *mod.parameters(), *mod2.parameters()):
+                t.grad = None
+            y = fn()
+            y.backward(dy if y.shape == dy.shape else torch.ones_like(y))
+            out.append([y.detach().clone()] + [None if t.grad is None else t.grad.clone()
+                                               for t in (x, r, xcl, act.weight, *mod.parameters(), *mod2.parameters())])
+        return out
+
+    a = run_all()
+    pkg.set_binding("ctypes")
+    try:
+        assert pkg.binding_in_use() == "ctypes"
+        b = run_all()
+    finally:
+        pkg.set_binding("auto")
+    for case_a, case_b in zip(a, b):
+        for ta, tb in zip(case_a, case_b):
+            assert (ta is None) == (tb is None)
+            if ta is not None:
+                assert torch.equal(ta, tb)
