@@ -136,6 +136,20 @@ def test_fused_epilogues_match_reference_block_golden(pkg, path):
 
 
 # ------------------------------------------------------------------------------------------------ seeded cases vs oracle
+KINK = 1e-5
+
+
+def follow_kernel_on_the_kink(pre, y, band=KINK):
+    """LeakyReLU has no derivative at 0: where the float64 pre-activation is within `band` of it, fp32 arithmetic may land
+    on either side (one element in ~10^7 does), and dx / d(gamma) / d(beta) legitimately follow that choice.  The oracle's
+    backward takes the side the kernel's own forward output shows for those elements - and only for those."""
+    y = np.asarray(y, dtype=np.float64)
+    near = np.abs(pre) < band
+    if not near.any():
+        return pre
+    return np.where(near, np.where(y > 0, band, -band), pre)
+
+
 def _case(pkg, shape, styles, num_styles, dtype, epilogue="none", seed=0, stride_pad=0, mean=1.0, std=2.0):
     gen = torch.Generator().manual_seed(seed)
     n, c = shape[0], shape[1]
@@ -167,6 +181,7 @@ def _case(pkg, shape, styles, num_styles, dtype, epilogue="none", seed=0, stride
         drr = None
     else:
         yr, pre, m_, r_ = O.fwd_epilogue_f64(xn, styles, gamma, beta, residual=rn if epilogue == "add_lrelu" else None)
+        pre = follow_kernel_on_the_kink(pre, y.detach().float().cpu().numpy())
         dxr, drr, dgr, dbr, _ = O.bwd_epilogue_f64(dyn, pre, xn, styles, gamma, m_, r_,
                                                    has_residual=epilogue == "add_lrelu")
     tol = TOL[dtype] * max(1.0, abs(mean) / std / 0.5)
@@ -273,7 +288,7 @@ def test_channels_last_input_native_and_reference_layout(pkg):
     y1 = mod(xv, [0, 1])
     assert pkg._lib.get_option("last_path") == 3
     assert y1.shape == xv.shape and y1.stride() == xv.stride()
-    assert float((y1 - y_ref).abs().max()) < 1e-5
+    assert float((y1 - y_ref).detach().abs().max()) < 1e-5
     pkg.set_channels_last_native(False)
     try:
         y2 = mod(xv, [0, 1])

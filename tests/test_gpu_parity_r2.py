@@ -13,7 +13,8 @@ import torch
 
 from conftest import rel_err
 from oracle import micn_oracle as O
-from test_gpu_parity import SHAPES, TOL, _case, _grads, _make_block, _module, pkg  # noqa: F401  (pkg is a fixture)
+from test_gpu_parity import (SHAPES, TOL, _case, _grads, _make_block, _module, follow_kernel_on_the_kink,  # noqa: F401
+                             pkg)  # (pkg is a fixture)
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +50,7 @@ def _case_chunked(pkg, shape, styles, num_styles, dtype, seed=0, epilogue="none"
             dxr, dgr, dbr, _ = O.bwd_f64(dyn, xn, styles, gam[:, sl], m_, r_)
         else:
             yr, pre, m_, r_ = O.fwd_epilogue_f64(xn, styles, gam[:, sl], bet[:, sl])
+            pre = follow_kernel_on_the_kink(pre, y.detach()[:, sl].float().cpu().numpy())
             dxr, _, dgr, dbr, _ = O.bwd_epilogue_f64(dyn, pre, xn, styles, gam[:, sl], m_, r_)
         worst["y"] = max(worst["y"], rel_err(y.detach()[:, sl].float().cpu().numpy(), yr))
         worst["dx"] = max(worst["dx"], rel_err(x.grad[:, sl].float().cpu().numpy(), dxr))
@@ -440,7 +442,7 @@ def test_resident_path_cuda_graph_replay(pkg):
 
 
 # ------------------------------------------------------------------------------------------------ dual-norm epilogue
-def _dual_case(pkg, shape, styles, num_styles, dtype, seed=0, plain=False, expect_dual=True):
+def _dual_case(pkg, shape, styles, num_styles, dtype, seed=0, plain=False, expect_dual=True, band=None):
     gen = torch.Generator().manual_seed(seed)
     n, c = shape[0], shape[1]
     S = 1 if plain else num_styles
@@ -470,6 +472,7 @@ def _dual_case(pkg, shape, styles, num_styles, dtype, seed=0, plain=False, expec
     assert pkg._lib.get_option("launches") - launches0 == (2 if expect_dual else 4)
     an, bn, dyn = aq.float().numpy(), bq.float().numpy(), dyq.float().numpy()
     out, pre, sa, sb = O.fwd_dual_f64(an, bn, st_or, ga, ba, gb, bb)
+    pre = follow_kernel_on_the_kink(pre, y.detach().float().cpu().numpy(), **({} if band is None else {"band": band}))
     da, db, dga, dba, dgb, dbb, present = O.bwd_dual_f64(dyn, pre, an, bn, st_or, ga, gb, sa, sb)
     tol = TOL[dtype]
     ptol = 5e-5 if dtype == torch.float32 else 5e-3
@@ -712,3 +715,74 @@ def test_ctypes_binding_matches_the_cpp_binding(pkg):
             assert (ta is None) == (tb is None)
             if ta is not None:
                 assert torch.equal(ta, tb)
+
+
+# ------------------------------------------------------------------------------------------------ mid-size ragged shapes
+def _mid_size_cases(count, seed):
+    """Slab lengths 20 k ... 700 k elements (the resident / flat / cluster range), dimensions drawn so that about half of
+    the lengths are not a multiple of the 16-byte vector (head / tail peeling, unequal shares inside a cluster, pieces that
+    do not divide the slab); the tensors stay under 6 M elements so the float64 oracle finishes in a second."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(count):
+        target = int(np.exp(rng.uniform(np.log(20000), np.log(700000))))
+        d0 = int(rng.randint(9, 60))
+        d1 = int(rng.randint(9, 60))
+        d2 = max(2, target // (d0 * d1))
+        if k % 2 == 0:
+            d2 = (d2 + 7) // 8 * 8  # every other case aligned for all dtypes
+        m = d0 * d1 * d2
+        slabs_max = max(1, 6_000_000 // m)
+        n = int(rng.randint(1, 5))
+        c = int(rng.randint(1, max(2, min(24, slabs_max // n + 1))))
+        num_styles = int(rng.randint(1, 4))
+        styles = [int(rng.randint(0, num_styles)) for _ in range(n)]
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.randint(0, 3))]
+        epilogue = ["none", "lrelu", "add_lrelu"][int(rng.randint(0, 3))]
+        path = [-1, 1, 2, 4][k % 4]
+        out.append(((n, c, d0, d1, d2), styles, num_styles, dtype, epilogue, path, k))
+    return out
+
+
+@pytest.mark.parametrize("shape,styles,num_styles,dtype,epilogue,path,k", _mid_size_cases(32, 20261019),
+                         ids=lambda v: None if not isinstance(v, int) else None)
+def test_seeded_random_mid_size_shapes_vs_oracle(pkg, option, shape, styles, num_styles, dtype, epilogue, path, k):
+    """Ragged mid-size shapes nobody picked by hand, on the automatic choice and with each of the cluster / flat / resident
+    paths requested (a path that cannot take the shape falls through to the next one, as in the product)."""
+    if path >= 0:
+        option("force_path", path)
+    _case(pkg, shape, styles, num_styles, dtype, epilogue=epilogue, seed=300 + k)
+
+
+def _mid_size_dual_cases(count, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(count):
+        target = int(np.exp(rng.uniform(np.log(4000), np.log(500000))))
+        d0, d1 = int(rng.randint(5, 50)), int(rng.randint(5, 50))
+        d2 = max(2, target // (d0 * d1))
+        if k % 2 == 0:
+            d2 = (d2 + 7) // 8 * 8
+        m = d0 * d1 * d2
+        n = int(rng.randint(1, 4))
+        c = int(rng.randint(1, max(2, min(16, 3_000_000 // (m * n) + 1))))
+        styles = [int(rng.randint(0, 3)) for _ in range(n)]
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.randint(0, 3))]
+        out.append(((n, c, d0, d1, d2), styles, dtype, [-1, 2][k % 2], k))
+    return out
+
+
+@pytest.mark.parametrize("shape,styles,dtype,path,k", _mid_size_dual_cases(12, 20261020),
+                         ids=lambda v: None if not isinstance(v, int) else None)
+def test_seeded_random_dual_norm_shapes_vs_oracle(pkg, option, shape, styles, dtype, path, k):
+    """The dual-norm epilogue on ragged shapes: one launch per direction where micn_dual_supported says so, the
+    two-launch composition otherwise - same results either way."""
+    if path >= 0:
+        option("force_path", path)
+    n, c = shape[0], shape[1]
+    m = int(np.prod(shape[2:]))
+    ok = pkg.functional.dual_supported(n, c, m, dtype, False) and pkg.functional.dual_supported(n, c, m, dtype, True)
+    # the two-launch composition rounds norm_a's output to the tensor dtype before the add: in 16-bit types the sum lands
+    # on the other side of the kink within that rounding (|value| * 2^-9), not just within fp32 noise
+    band = None if ok or dtype == torch.float32 else 8e-3
+    _dual_case(pkg, shape, styles, 3, dtype, seed=400 + k, expect_dual=ok, band=band)
