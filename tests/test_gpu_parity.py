@@ -307,20 +307,32 @@ def test_channels_last_input_native_and_reference_layout(pkg):
                                         ((3, 136, 1500), "wide_loads_ragged_tile"),
                                         ((2, 20, 1300), "wide_fp32_only_c20")], ids=lambda v: v if isinstance(v, str) else None)
 def test_channels_last_route_vs_oracle(pkg, shape, name, dtype):
-    gen = torch.Generator().manual_seed(len(name))
+    n = shape[0]
+    _cl_case(pkg, shape, [(i * 5 + 1) % 3 for i in range(n)], 3, dtype, seed=len(name))
+
+
+def _cl_case(pkg, shape, styles, num_styles, dtype, seed=0, offset=0):
+    """Logical NC* tensor in channels-last memory (stride_C = 1), optionally `offset` elements into its allocation (an
+    offset that breaks the 16-byte alignment sends the call to the pair kernels instead of the wide ones)."""
+    gen = torch.Generator().manual_seed(seed)
     n, c = shape[0], shape[1]
-    styles = [(i * 5 + 1) % 3 for i in range(n)]
-    gamma = (1 + 0.3 * torch.randn(3, c, generator=gen)).numpy()
-    beta = (0.3 * torch.randn(3, c, generator=gen)).numpy()
+    gamma = (1 + 0.3 * torch.randn(num_styles, c, generator=gen)).numpy()
+    beta = (0.3 * torch.randn(num_styles, c, generator=gen)).numpy()
     x32 = torch.randn(*shape, generator=gen) * 2 + 1
     dy32 = torch.randn(*shape, generator=gen)
     xq, dyq = x32.to(dtype), dy32.to(dtype)
     perm = [0] + list(range(2, len(shape))) + [1]
     inv = [0, len(shape) - 1] + list(range(1, len(shape) - 1))
-    x = xq.permute(perm).contiguous().cuda().permute(inv).requires_grad_(True)  # logical NC*, channels-last memory
+    xcl = xq.permute(perm).contiguous()
+    if offset:
+        buf = torch.zeros(xcl.numel() + offset, dtype=dtype, device="cuda")
+        buf[offset:] = xcl.cuda().reshape(-1)
+        x = buf[offset:].view(xcl.shape).permute(inv).requires_grad_(True)
+    else:
+        x = xcl.cuda().permute(inv).requires_grad_(True)  # logical NC*, channels-last memory
     assert x.stride(1) == 1
-    w = [torch.from_numpy(gamma[s]).cuda().requires_grad_(True) for s in range(3)]
-    b = [torch.from_numpy(beta[s]).cuda().requires_grad_(True) for s in range(3)]
+    w = [torch.from_numpy(gamma[s]).cuda().requires_grad_(True) for s in range(num_styles)]
+    b = [torch.from_numpy(beta[s]).cuda().requires_grad_(True) for s in range(num_styles)]
     st = torch.tensor(styles, dtype=torch.int64, device="cuda")
     y = pkg.instance_cond(x, st, w, b)
     assert pkg._lib.get_option("last_path") == 3 and y.stride() == x.stride()
@@ -328,13 +340,41 @@ def test_channels_last_route_vs_oracle(pkg, shape, name, dtype):
     torch.cuda.synchronize()
     xn, dyn = xq.float().numpy(), dyq.float().numpy()
     yr, m_, r_ = O.fwd_f64(xn, styles, gamma, beta)
-    dxr, dgr, dbr, _ = O.bwd_f64(dyn, xn, styles, gamma, m_, r_)
+    dxr, dgr, dbr, present = O.bwd_f64(dyn, xn, styles, gamma, m_, r_)
     tol = TOL[dtype]
     assert rel_err(y.detach().float().cpu().numpy(), yr) < tol
     assert rel_err(x.grad.float().cpu().numpy(), dxr) < tol
     ptol = 5e-5 if dtype == torch.float32 else 5e-3
-    assert rel_err(np.stack([t.grad.cpu().numpy() for t in w]), dgr) < ptol
-    assert rel_err(np.stack([t.grad.cpu().numpy() for t in b]), dbr) < ptol
+    zero = np.zeros(c, dtype=np.float32)
+    assert [t.grad is not None for t in w] == list(present) or all(t.grad is not None for t in w)
+    assert rel_err(np.stack([zero if t.grad is None else t.grad.cpu().numpy() for t in w]), dgr) < ptol
+    assert rel_err(np.stack([zero if t.grad is None else t.grad.cpu().numpy() for t in b]), dbr) < ptol
+
+
+def _cl_random_cases(count, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(count):
+        c = 2 * int(np.exp(rng.uniform(np.log(1), np.log(400))))          # even channel counts 2 ... 800
+        rows = int(np.exp(rng.uniform(np.log(2), np.log(30000))))
+        n = int(rng.randint(1, 6))
+        while n * c * rows > 3_000_000:
+            rows = max(2, rows // 2)
+        num_styles = int(rng.randint(1, 5))
+        styles = [int(rng.randint(0, num_styles)) for _ in range(n)]
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.randint(0, 3))]
+        offset = [0, 0, 2, 4, 8][int(rng.randint(0, 5))]                 # elements: 4 ... 32 bytes into the allocation
+        out.append(((n, c, rows), styles, num_styles, dtype, offset, k))
+    return out
+
+
+@pytest.mark.parametrize("shape,styles,num_styles,dtype,offset,k", _cl_random_cases(30, 20261021),
+                         ids=lambda v: None if not isinstance(v, int) else None)
+def test_channels_last_seeded_random_shapes_vs_oracle(pkg, shape, styles, num_styles, dtype, offset, k):
+    """Token-major shapes nobody picked by hand: 2 ... 800 channels (ragged 64-channel tiles), 2 ... 30 k rows (the fused
+    short-column kernels, the two-kernel route, its wide variant and the ragged row splits), 1-5 samples with 1-4 styles
+    (the in-kernel parameter-gradient fold), tensors that start 4 ... 32 bytes into their allocation."""
+    _cl_case(pkg, shape, styles, num_styles, dtype, seed=500 + k, offset=offset)
 
 
 def test_channels_last_odd_channel_count_takes_the_copy_route(pkg):

@@ -786,3 +786,29 @@ def test_seeded_random_dual_norm_shapes_vs_oracle(pkg, option, shape, styles, dt
     # on the other side of the kink within that rounding (|value| * 2^-9), not just within fp32 noise
     band = None if ok or dtype == torch.float32 else 8e-3
     _dual_case(pkg, shape, styles, 3, dtype, seed=400 + k, expect_dual=ok, band=band)
+
+
+def _many_slab_cases(count, seed):
+    """Many short slabs (8 k ... 64 k elements, up to 8 samples x 64 channels) pushed onto the flat / resident / cluster
+    paths: slabs much smaller than a CTA's share, several slabs per CTA, the per-channel fold over many samples."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(count):
+        m = 8 * int(np.exp(rng.uniform(np.log(1000), np.log(8000))))
+        n = int(rng.randint(2, 9))
+        c = int(rng.randint(8, 65))
+        while n * c * m > 6_000_000:
+            c = max(1, c // 2)
+        num_styles = int(rng.randint(1, 5))
+        styles = [int(rng.randint(0, num_styles)) for _ in range(n)]
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.randint(0, 3))]
+        epilogue = ["none", "lrelu", "add_lrelu"][int(rng.randint(0, 3))]
+        out.append(((n, c, m), styles, num_styles, dtype, epilogue, [2, 4, 1][k % 3], k))
+    return out
+
+
+@pytest.mark.parametrize("shape,styles,num_styles,dtype,epilogue,path,k", _many_slab_cases(18, 20261022),
+                         ids=lambda v: None if not isinstance(v, int) else None)
+def test_seeded_random_many_slabs_vs_oracle(pkg, option, shape, styles, num_styles, dtype, epilogue, path, k):
+    option("force_path", path)
+    _case(pkg, shape, styles, num_styles, dtype, epilogue=epilogue, seed=600 + k)
