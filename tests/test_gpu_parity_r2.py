@@ -812,3 +812,45 @@ def _many_slab_cases(count, seed):
 def test_seeded_random_many_slabs_vs_oracle(pkg, option, shape, styles, num_styles, dtype, epilogue, path, k):
     option("force_path", path)
     _case(pkg, shape, styles, num_styles, dtype, epilogue=epilogue, seed=600 + k)
+
+
+def test_two_streams_run_concurrently_with_their_own_workspaces(pkg):
+    """Calls issued from two CUDA streams overlap on the device (cooperative flat kernels queue behind each other, the
+    resident and small ones share the SMs); every stream has its own workspace (records, epoch word, arrival counters), so
+    the results are bit-identical to the same calls issued one after the other."""
+    torch.manual_seed(23)
+    shapes = [(2, 5, 48, 48, 48), (1, 48, 32, 32, 32), (3, 20, 6, 6, 6), (1, 3, 96, 96, 96)]
+    mods = [pkg.FastConditionalInstanceNorm3d(3, sh[1]).cuda() for sh in shapes]
+    for mod in mods:
+        with torch.no_grad():
+            for k in range(3):
+                mod.norms[k].weight.normal_(1, 0.3)
+                mod.norms[k].bias.normal_(0, 0.3)
+    xs = [(torch.randn(*sh, device="cuda") * 2 + 1).bfloat16() for sh in shapes]
+    dys = [torch.randn(*sh, device="cuda").bfloat16() for sh in shapes]
+    sts = [[(i + j) % 3 for i in range(sh[0])] for j, sh in enumerate(shapes)]
+
+    def one(j):
+        x = xs[j].clone().requires_grad_(True)
+        for t in mods[j].parameters():
+            t.grad = None
+        y = mods[j].forward_fused(x, sts[j], "lrelu")
+        y.backward(dys[j])
+        return [y.detach(), x.grad] + [None if t.grad is None else t.grad.clone() for t in mods[j].parameters()]
+
+    serial = [one(j) for j in range(len(shapes))]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for s_ in streams:
+        s_.wait_stream(torch.cuda.current_stream())
+    for rep in range(4):
+        got = {}
+        for j in range(len(shapes)):  # modules differ per call, so the two streams never touch the same .grad
+            with torch.cuda.stream(streams[(j + rep) % 2]):
+                got[j] = one(j)
+        torch.cuda.synchronize()
+        for j in range(len(shapes)):
+            for a_, b_ in zip(serial[j], got[j]):
+                assert (a_ is None) == (b_ is None)
+                if a_ is not None:
+                    assert torch.equal(a_, b_), (rep, j)
