@@ -903,3 +903,54 @@ def test_results_do_not_depend_on_timing(pkg, option, shape, path):
         for a_, b_ in zip(quiet, got):
             assert torch.equal(a_, b_), rep
     torch.cuda.synchronize()
+
+
+def _prelu_cases(count, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(count):
+        m = int(np.exp(rng.uniform(np.log(30), np.log(400000))))
+        if k % 2 == 0:
+            m = (m + 7) // 8 * 8
+        n = int(rng.randint(1, 4))
+        c = int(rng.randint(1, max(2, min(20, 2_000_000 // (m * n) + 1))))
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.randint(0, 3))]
+        init = float(rng.uniform(0.05, 0.6))
+        out.append(((n, c, m), [int(rng.randint(0, 2)) for _ in range(n)], dtype, init, [-1, 2, 4, 0][k % 4], k))
+    return out
+
+
+@pytest.mark.parametrize("shape,styles,dtype,init,path,k", _prelu_cases(16, 20261023),
+                         ids=lambda v: None if not isinstance(v, int) else None)
+def test_seeded_random_prelu_shapes_vs_oracle(pkg, option, shape, styles, dtype, init, path, k):
+    """The learnable-slope epilogue (UnetBasicBlock's ADN with PReLU) on ragged shapes and every path that produces the
+    slope-gradient partials (small, flat, resident): y, dx, d(gamma)/d(beta) and d(slope) against the float64 oracle."""
+    if path >= 0:
+        option("force_path", path)
+    gen = torch.Generator().manual_seed(700 + k)
+    n, c = shape[0], shape[1]
+    gamma = (1 + 0.3 * torch.randn(2, c, generator=gen)).numpy()
+    beta = (0.3 * torch.randn(2, c, generator=gen)).numpy()
+    mod = _module(pkg, 1, 2, gamma, beta)
+    act = torch.nn.PReLU(init=init).cuda()
+    xq = (torch.randn(*shape, generator=gen) * 2 + 1).to(dtype)
+    dyq = torch.randn(*shape, generator=gen).to(dtype)
+    x = xq.cuda().requires_grad_(True)
+    y = mod.forward_fused(x, styles, "lrelu", slope=act.weight)
+    y.backward(dyq.cuda())
+    torch.cuda.synchronize()
+    xn, dyn = xq.float().numpy(), dyq.float().numpy()
+    a0 = float(np.float32(init))
+    yr, pre, m_, r_ = O.fwd_prelu_f64(xn, styles, gamma, beta, a0)
+    pre = follow_kernel_on_the_kink(pre, y.detach().float().cpu().numpy())
+    dxr, dgr, dbr, dar, present = O.bwd_prelu_f64(dyn, pre, xn, styles, gamma, m_, r_, a0)
+    tol = TOL[dtype]
+    assert rel_err(y.detach().float().cpu().numpy(), yr) < tol
+    assert rel_err(x.grad.float().cpu().numpy(), dxr) < tol
+    dg, db, pres = _grads(mod)
+    ptol = 5e-5 if dtype == torch.float32 else 5e-3
+    assert rel_err(dg, dgr) < ptol and rel_err(db, dbr) < ptol and pres == list(present)
+    # a sum of n*c*m products of O(1): absolute error grows like the square root of the count times the I/O rounding
+    da = float(act.weight.grad.item())
+    scale = max(1.0, abs(dar), float(np.sqrt(n * c * shape[2])))
+    assert abs(da - dar) <= (1e-4 if dtype == torch.float32 else 2e-2) * scale, (da, dar)
