@@ -60,10 +60,11 @@ def parse_args():
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the PyTorch/ATen GPU comparison leg (clean ncu launch lists)")
     ap.add_argument("--no-model-calls", action="store_true", help="skip the C-Swin-UNETR norm-call-list leg")
     ap.add_argument("--regions", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
-    ap.add_argument("--launch", default="stream", choices=["stream", "graph"],
+    ap.add_argument("--launch", default="stream", choices=["stream", "graph", "graphR"],
                     help="stream (default): the two C-ABI calls are issued from Python every step; graph: the micn_fwd + micn_bwd "
                          "pair of every buffer set is captured once into a CUDA graph and replayed (the calls keep no per-launch "
-                         "state on the host)")
+                         "state on the host); graphR: ONE graph holds the steps of all R buffer sets (--steps must be a multiple "
+                         "of R; N > 1 needs the fused exchange) - programmatic dependent launch then spans the step boundaries")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
                     help="N > 1: how d(gamma)/d(beta) are all-reduced every step.  fused (default): inside the backward kernel, "
                          "records stored straight into every peer's memory over NVLink (micn_bwd_allreduce); nccl: an "
@@ -778,6 +779,30 @@ def run_ours(args):
         def launch_pair(b):  # noqa: F811 - the collective (N > 1) is still issued from the host after every replay
             graphs[b].replay()
 
+    graph_all = None
+    if args.launch == "graphR":  # (experiment, never the default: R consecutive steps in one graph)
+        if (world > 1 and px is None) or args.steps % R:
+            raise SystemExit(f"--launch graphR: --steps must be a multiple of R = {R}, and N > 1 needs --collective fused")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            stream = side.cuda_stream
+            graph_all = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_all, stream=side):
+                for i in range(R):
+                    fwd(i)
+                    (bwd_fused if px is not None else bwd)((i + 1) % R, grads2[i])
+        torch.cuda.current_stream().wait_stream(side)
+        stream = torch.cuda.current_stream().cuda_stream
+
+    def run_steps(k):
+        if graph_all is None:
+            for i in range(k):
+                step(i)
+        else:
+            for _ in range((k + R - 1) // R):
+                graph_all.replay()
+
     # untimed pre-warm, independent of --warmup: the GPU drops to its idle clocks within a fraction of a second of
     # inactivity (the sampler start above is one), and a 20-step region lasts 1.7 ms - shorter than the clock ramp
     # (a fixed count: with the fused exchange every rank must make the same sequence of calls.  Deliberately short - 16 ms:
@@ -786,8 +811,7 @@ def run_ours(args):
     # burst copy rate)
     prewarm = max(200, args.warmup, 10 * args.steps)
     t_load0 = time.perf_counter()
-    for i in range(prewarm):
-        step(i)
+    run_steps(prewarm)
     drain()
     torch.cuda.synchronize()
     launches_region = None
@@ -800,8 +824,7 @@ def run_ours(args):
         launches0 = pkg._lib.get_option("launches")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            step(i)
+        run_steps(args.steps)
         drain()  # every step's collective completes inside the timed region
         e1.record()
         torch.cuda.synchronize()
@@ -810,7 +833,7 @@ def run_ours(args):
             torch.cuda.synchronize()
         region_ms.append(e0.elapsed_time(e1))
         if launches_region is None:
-            launches_region = (pkg._lib.get_option("launches") - launches0) if graphs is None else 2 * args.steps
+            launches_region = (pkg._lib.get_option("launches") - launches0) if graphs is None and graph_all is None else 2 * args.steps
     t_wall1 = time.perf_counter()
     launches = launches_region
     if px is not None and os.environ.get("MICN_BENCH_XCHG_DBG"):  # (bring-up: wait statistics of the folds, see micn_flat.cuh)
